@@ -1,0 +1,85 @@
+"""In-tree build of libcslam_b200.so (nvcc, sm_100a only).
+
+The shared object is written next to this file so that it travels with the
+repo snapshot to the GPU box; there is no JIT cache and no fallback build.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libcslam_b200.so")
+
+SOURCES = [
+    "lib.cu",
+    "nns.cu",
+    "nns_coarse_tc.cu",
+    "heads.cu",
+    "mac.cu",
+]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
+    "-cudart", "static",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; cannot build libcslam_b200.so")
+    return exe
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(HERE, "..", "include", "cslam_b200.h"))
+    deps.append(os.path.abspath(__file__))
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source into one shared library; returns its path."""
+    if not force and not needs_build():
+        return LIB
+    nvcc = _nvcc()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    procs = []
+    objs = []
+    for s in srcs:
+        obj = os.path.join(objdir, s.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd))
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    failed = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        text = out.decode(errors="replace")
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"[cslam_b200.build] {s} failed:\n{text}\n")
+        elif verbose or text.strip():
+            sys.stderr.write(f"[cslam_b200.build] {s}:\n{text}\n")
+    if failed:
+        raise RuntimeError("nvcc failed; see messages above")
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-cudart", "static",
+                                                "-gencode", "arch=compute_100a,code=sm_100a"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,908 @@
+// Cosine nearest-neighbour matching over a growable descriptor pool resident in
+// HBM.  B200-native replacement for cslam/nns_matching.py:6-76
+// (NearestNeighborsMatching): the arithmetic the reference does with a Python
+// loop over scipy.spatial.distance.cosine runs here as
+//
+//   append   : k_nns_append          fp32 row store + float32 |x|^2 + fp16 unit-norm shadow
+//   prepare  : k_nns_prep_queries    float64 query copy, |q|^2, fp16 unit-norm query tile
+//   candidates: k_nns_coarse_tc      tcgen05 GEMM with fused threshold filter (nns_coarse_tc.cu)
+//              k_nns_coarse_exact    fp64 SIMT scan with the same interface (validation /
+//                                    escalation path; still on the GPU)
+//   threshold: k_nns_tau_select      k'-th largest sampled score per query (radix select)
+//   result   : k_nns_select_rerank   top-k' by coarse score, exact float64 cosine from the
+//                                    float32 rows exactly as the reference scores them,
+//                                    sort, rigorous error-bound check
+//
+// Exactness argument: every pool row outside the re-ranked
+// set has coarse score < T, and |coarse - exact| <= eps by construction
+// (fp16 rounding of unit vectors + fp32 accumulation), so if T + eps <= s_k
+// (the exact k-th best of the re-ranked set) no outside row can enter the
+// top-k.  When the check fails the window is widened to {coarse >= s_k - eps};
+// if even that is impossible the query is re-run through the exact scan.
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "nns_internal.cuh"
+
+namespace cslam {
+namespace {
+
+constexpr int kRerankMax = 2048;   // largest re-rank set handled in shared memory
+constexpr int kMaxK = 1024;        // largest k accepted by search
+constexpr int kSelThreads = 512;
+constexpr int kStageRows = 4096;   // host->device staging granularity for add_host
+
+// ---------------------------------------------------------------------------
+// k_nns_append: one warp per appended row.
+//   data[row, :]   = x                         (float32, the reference's `.data`)
+//   vv[row]        = sum_i x_i^2 in float32    (np.dot(v, v) on a float32 row,
+//                                               scipy correlation(): vv)
+//   shadow[row, :] = fp16(x / sqrt(vv)), zero padded to dim_pad
+// ---------------------------------------------------------------------------
+__global__ void k_nns_append(const float* __restrict__ src, int64_t count, int dim, int dim_pad,
+                             float* __restrict__ data, float* __restrict__ vv,
+                             __half* __restrict__ shadow, int64_t row_base) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (w >= count) return;
+  const float* x = src + w * dim;
+  const int64_t row = row_base + w;
+  float acc = 0.f;
+  for (int i = lane; i < dim; i += 32) {
+    const float v = x[i];
+    acc = fmaf(v, v, acc);
+  }
+  const float s = warp_sum(acc);
+  const float inv = s > 0.f ? 1.0f / sqrtf(s) : 0.f;
+  float* drow = data + row * dim;
+  __half* srow = shadow + row * dim_pad;
+  for (int i = lane; i < dim_pad; i += 32) {
+    if (i < dim) {
+      const float v = x[i];
+      drow[i] = v;
+      srow[i] = __float2half_rn(v * inv);
+    } else {
+      srow[i] = __float2half_rn(0.f);
+    }
+  }
+  if (lane == 0) vv[row] = s;
+}
+
+// ---------------------------------------------------------------------------
+// k_nns_prep_queries: one warp per query row of the padded tile buffer.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void k_nns_prep_queries(const T* __restrict__ q, int nq, int nq_pad, int dim,
+                                   int dim_pad, double* __restrict__ q64, double* __restrict__ uu,
+                                   __half* __restrict__ qh) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= nq_pad) return;
+  __half* hrow = qh + static_cast<size_t>(w) * dim_pad;
+  if (w >= nq) {
+    for (int i = lane; i < dim_pad; i += 32) hrow[i] = __float2half_rn(0.f);
+    return;
+  }
+  const T* x = q + static_cast<size_t>(w) * dim;
+  double acc = 0.0;
+  for (int i = lane; i < dim; i += 32) {
+    const double v = static_cast<double>(x[i]);
+    acc = fma(v, v, acc);
+  }
+  const double s = warp_sum(acc);
+  const double inv = s > 0.0 ? 1.0 / sqrt(s) : 0.0;
+  double* drow = q64 + static_cast<size_t>(w) * dim;
+  for (int i = lane; i < dim_pad; i += 32) {
+    if (i < dim) {
+      const double v = static_cast<double>(x[i]);
+      drow[i] = v;
+      hrow[i] = __float2half_rn(static_cast<float>(v * inv));
+    } else {
+      hrow[i] = __float2half_rn(0.f);
+    }
+  }
+  if (lane == 0) uu[w] = s;
+}
+
+// ---------------------------------------------------------------------------
+// k_nns_coarse_exact: same contract as k_nns_coarse_tc but scores in float64
+// on the SIMT pipes.  One warp per pool row, looping over the query tile.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_nns_coarse_exact(const float* __restrict__ data, const float* __restrict__ vv, int dim,
+                   const double* __restrict__ q64, const double* __restrict__ uu,
+                   CoarseParams prm) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+    const int row0 = static_cast<int>(static_cast<int64_t>(tile) * prm.tile_stride * kCoarseBN);
+    for (int r = warp; r < kCoarseBN; r += warps_per_block) {
+      const int row = row0 + r;
+      if (row >= prm.n_rows) break;
+      const float* x = data + static_cast<size_t>(row) * dim;
+      const double vvd = static_cast<double>(vv[row]);
+      for (int q = 0; q < prm.nq; ++q) {
+        const double* qv = q64 + static_cast<size_t>(prm.q_row0 + q) * dim;
+        double acc = 0.0;
+        for (int i = lane; i < dim; i += 32) acc = fma(qv[i], static_cast<double>(x[i]), acc);
+        const double uv = warp_sum(acc);
+        if (lane == 0) {
+          const float s = static_cast<float>(uv / sqrt(uu[prm.q_row0 + q] * vvd));
+          const float tau = prm.tau ? prm.tau[q] : -INFINITY;
+          if (s >= tau) {
+            const unsigned int pos = atomicAdd(prm.cnt + q, 1u);
+            if (pos < static_cast<unsigned int>(prm.cand_cap))
+              prm.cand[static_cast<size_t>(q) * prm.cand_cap + pos] =
+                  make_uint2(__float_as_uint(s), static_cast<uint32_t>(row));
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Block-wide radix select: key of the `kth` largest (1-based) score among
+// c[0..n).  4 passes of 8 bits, MSB first.  s_hist: 256 counters, s_ctl: 2 words.
+// ---------------------------------------------------------------------------
+__device__ uint32_t block_kth_largest_key(const uint2* __restrict__ c, int n, int kth,
+                                          uint32_t* s_hist, uint32_t* s_ctl) {
+  uint32_t prefix = 0, mask = 0;
+  int remaining = kth;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t key = f32_to_key(__uint_as_float(c[i].x));
+      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      int d = 255;
+      for (; d > 0; --d) {
+        const int h = static_cast<int>(s_hist[d]);
+        if (acc + h >= remaining) break;
+        acc += h;
+      }
+      s_ctl[0] = static_cast<uint32_t>(d);
+      s_ctl[1] = static_cast<uint32_t>(remaining - acc);
+    }
+    __syncthreads();
+    prefix |= s_ctl[0] << shift;
+    mask |= 255u << shift;
+    remaining = static_cast<int>(s_ctl[1]);
+    __syncthreads();
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+k_nns_tau_select(const uint2* __restrict__ cand, const unsigned int* __restrict__ cnt,
+                 int cand_cap, int kth, float* __restrict__ tau) {
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_ctl[2];
+  const int q = blockIdx.x;
+  const int n = static_cast<int>(min(cnt[q], static_cast<unsigned int>(cand_cap)));
+  const uint2* c = cand + static_cast<size_t>(q) * cand_cap;
+  if (n < kth) {
+    if (threadIdx.x == 0) tau[q] = -INFINITY;
+    return;
+  }
+  const uint32_t key = block_kth_largest_key(c, n, kth, s_hist, s_ctl);
+  if (threadIdx.x == 0) tau[q] = key_to_f32(key);
+}
+
+// ---------------------------------------------------------------------------
+// k_nns_select_rerank: one block per query.
+// ---------------------------------------------------------------------------
+struct RerankParams {
+  const uint2* cand;
+  const unsigned int* cnt;
+  int cand_cap;
+  const float* tau;  // nullptr: candidate list is the whole pool
+  const float* data;
+  const float* vv;
+  int dim;
+  int n_rows;
+  const double* q64;  // already offset to the tile's first query
+  const double* uu;
+  int k;
+  int window;
+  float eps;
+  int32_t* out_idx;   // [nq, k], offset to the tile's first query
+  double* out_sims;
+  int* flags;         // [nq]: 0 fast path, 1 widened window, 2 needs exact re-run
+};
+
+__device__ __forceinline__ bool ranks_before(double sa, int ia, double sb, int ib) {
+  // descending similarity, ties by descending row id (np.argsort(...)[::-1])
+  return (sa > sb) || (sa == sb && ia > ib);
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+k_nns_select_rerank(RerankParams p) {
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_ctl[2];
+  __shared__ int s_count;
+  __shared__ double s_sim[kRerankMax];
+  __shared__ int s_idx[kRerankMax];
+
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const uint2* c = p.cand + static_cast<size_t>(q) * p.cand_cap;
+  const unsigned int raw_cnt = p.cnt[q];
+  const int kk = min(p.k, p.n_rows);
+  int32_t* oi = p.out_idx + static_cast<size_t>(q) * p.k;
+  double* os = p.out_sims + static_cast<size_t>(q) * p.k;
+
+  for (int j = tid; j < p.k; j += blockDim.x) {
+    oi[j] = -1;
+    os[j] = nan("");
+  }
+  if (raw_cnt > static_cast<unsigned int>(p.cand_cap) || static_cast<int>(raw_cnt) < kk) {
+    if (tid == 0) p.flags[q] = 2;  // overflow (or inconsistent threshold): exact re-run
+    return;
+  }
+  const int n_c = static_cast<int>(raw_cnt);
+  const double tau_q = p.tau ? static_cast<double>(p.tau[q]) : -INFINITY;
+  const double* qv = p.q64 + static_cast<size_t>(q) * p.dim;
+  const double uuq = p.uu[q];
+
+  int flag = 0;
+  // threshold on the coarse score for this round; round 0 = k'-th largest
+  float thr;
+  {
+    const int want = min(p.window, n_c);
+    if (want >= n_c) {
+      thr = -INFINITY;
+    } else {
+      thr = key_to_f32(block_kth_largest_key(c, n_c, want, s_hist, s_ctl));
+    }
+  }
+  for (int round = 0; round < 2; ++round) {
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int i = tid; i < n_c; i += blockDim.x) {
+      const uint2 e = c[i];
+      if (__uint_as_float(e.x) >= thr) {
+        const int pos = atomicAdd(&s_count, 1);
+        if (pos < kRerankMax) s_idx[pos] = static_cast<int>(e.y);
+      }
+    }
+    __syncthreads();
+    const int count = s_count;
+    if (count > kRerankMax || count < kk) {
+      flag = 2;
+      break;
+    }
+    // exact float64 cosine of every selected row (reference: nns_matching.py:58 ->
+    // scipy correlation(): 1 - clip(1 - uv/sqrt(uu*vv), 0, 2))
+    for (int i = warp; i < count; i += nwarps) {
+      const int row = s_idx[i];
+      const float* x = p.data + static_cast<size_t>(row) * p.dim;
+      double acc = 0.0;
+      for (int d = lane; d < p.dim; d += 32) acc = fma(qv[d], static_cast<double>(x[d]), acc);
+      const double uv = warp_sum(acc);
+      if (lane == 0) {
+        double dist = 1.0 - uv / sqrt(uuq * static_cast<double>(p.vv[row]));
+        dist = fmin(fmax(dist, 0.0), 2.0);
+        double sim = 1.0 - dist;
+        if (!(sim == sim)) sim = -INFINITY;  // NaN (zero-norm row) ranks last
+        s_sim[i] = sim;
+      }
+    }
+    // pad to a power of two and bitonic-sort (descending, ties by descending row id)
+    int P = 1;
+    while (P < count) P <<= 1;
+    for (int i = count + tid; i < P; i += blockDim.x) {
+      s_sim[i] = -INFINITY;
+      s_idx[i] = -1;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = tid; t < (P >> 1); t += blockDim.x) {
+          const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+          const int hi = lo + stride;
+          const bool desc_block = ((lo & size) == 0);
+          const double sa = s_sim[lo], sb = s_sim[hi];
+          const int ia = s_idx[lo], ib = s_idx[hi];
+          const bool a_first = ranks_before(sa, ia, sb, ib);
+          if (desc_block ? !a_first : a_first) {
+            s_sim[lo] = sb; s_sim[hi] = sa;
+            s_idx[lo] = ib; s_idx[hi] = ia;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (kk == 0) break;
+    const double s_k = s_sim[kk - 1];
+    // everything outside the re-ranked set has coarse score < bound
+    const double bound = (count == n_c) ? tau_q : static_cast<double>(thr);
+    if (bound == -INFINITY || bound + static_cast<double>(p.eps) <= s_k) break;  // proven
+    if (round == 1) {
+      flag = 2;
+      break;
+    }
+    const double t2 = s_k - static_cast<double>(p.eps);
+    if (t2 < tau_q) {
+      flag = 2;  // rows below the candidate threshold could still qualify
+      break;
+    }
+    // round down to float so that {coarse >= thr} is a superset of {coarse >= t2}
+    float t2f = static_cast<float>(t2);
+    if (static_cast<double>(t2f) > t2) t2f = nextafterf(t2f, -INFINITY);
+    thr = t2f;
+    flag = 1;
+    __syncthreads();
+  }
+  if (flag != 2) {
+    for (int j = tid; j < kk; j += blockDim.x) {
+      oi[j] = s_idx[j];
+      os[j] = s_sim[j];
+    }
+  }
+  if (tid == 0) p.flags[q] = flag;
+}
+
+__global__ void k_fill_empty(int32_t* idx, double* sims, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    idx[i] = -1;
+    sims[i] = nan("");
+  }
+}
+
+}  // namespace
+}  // namespace cslam
+
+// ---------------------------------------------------------------------------
+// Handle
+// ---------------------------------------------------------------------------
+using namespace cslam;
+
+struct cslam_nns {
+  int device = 0;
+  int dim = 0;
+  int dim_pad = 0;
+  int num_sms = 148;
+  int64_t n = 0;
+  int64_t cap = 0;
+  float* d_data = nullptr;
+  __half* d_shadow = nullptr;
+  float* d_vv = nullptr;
+  TensorMapBlob tmap_p;
+  cudaStream_t stream = nullptr;
+
+  // host -> device staging for add_host
+  float* h_stage = nullptr;   // pinned [kStageRows, dim]
+  float* d_stage = nullptr;   // [kStageRows, dim]
+  int64_t staged = 0;
+
+  // search workspace
+  int q_cap = 0;              // rows in the query buffers (multiple of kCoarseBM)
+  void* d_qraw = nullptr;     // raw queries for the host variant (f64-sized)
+  double* d_q64 = nullptr;
+  double* d_uu = nullptr;
+  __half* d_qh = nullptr;
+  TensorMapBlob tmap_q;
+  float* d_tau = nullptr;         // [kCoarseBM]
+  unsigned int* d_cnt = nullptr;  // [kCoarseBM]
+  int* d_flags = nullptr;         // [kCoarseBM]
+  int* h_flags = nullptr;         // pinned [kCoarseBM]
+  DevBuf<uint2> cand;
+  int cand_cap = 0;
+  int out_cap_q = 0, out_cap_k = 0;
+  int32_t* d_out_idx = nullptr;
+  double* d_out_sims = nullptr;
+  void* h_q = nullptr;        // pinned query staging
+  size_t h_q_bytes = 0;
+  int32_t* h_out_idx = nullptr;
+  double* h_out_sims = nullptr;
+  size_t h_out_elems = 0;
+
+  int mode = 0;
+  int window = 128;
+  int sample_rows = 16384;
+
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
+  int last_coarse_launches = 0;
+  bool timing_valid = false;
+};
+
+namespace cslam {
+namespace {
+
+int nns_reserve_rows(cslam_nns* h, int64_t need) {
+  if (need <= h->cap) return CSLAM_OK;
+  int64_t ncap = h->cap > 0 ? h->cap : 1024;
+  while (ncap < need) ncap *= 2;
+  ncap = (ncap + kCoarseBN - 1) / kCoarseBN * kCoarseBN;
+  if (ncap > 0x7fffff00ll) {
+    set_error("descriptor pool limited to 2^31 rows");
+    return CSLAM_ERR_LIMIT;
+  }
+  float* nd = nullptr;
+  __half* ns = nullptr;
+  float* nv = nullptr;
+  CSLAM_TRY(dev_alloc(&nd, static_cast<size_t>(ncap) * h->dim));
+  CSLAM_TRY(dev_alloc(&ns, static_cast<size_t>(ncap) * h->dim_pad));
+  CSLAM_TRY(dev_alloc(&nv, static_cast<size_t>(ncap)));
+  CSLAM_CUDA(cudaMemsetAsync(ns, 0, static_cast<size_t>(ncap) * h->dim_pad * sizeof(__half),
+                             h->stream));
+  if (h->n > 0) {
+    CSLAM_CUDA(cudaMemcpyAsync(nd, h->d_data, static_cast<size_t>(h->n) * h->dim * sizeof(float),
+                               cudaMemcpyDeviceToDevice, h->stream));
+    CSLAM_CUDA(cudaMemcpyAsync(ns, h->d_shadow,
+                               static_cast<size_t>(h->n) * h->dim_pad * sizeof(__half),
+                               cudaMemcpyDeviceToDevice, h->stream));
+    CSLAM_CUDA(cudaMemcpyAsync(nv, h->d_vv, static_cast<size_t>(h->n) * sizeof(float),
+                               cudaMemcpyDeviceToDevice, h->stream));
+  }
+  CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+  dev_free(h->d_data);
+  dev_free(h->d_shadow);
+  dev_free(h->d_vv);
+  h->d_data = nd;
+  h->d_shadow = ns;
+  h->d_vv = nv;
+  h->cap = ncap;
+  CSLAM_TRY(make_fp16_rowmajor_tmap(&h->tmap_p, h->d_shadow, h->cap, h->dim_pad, kCoarseBN));
+  return CSLAM_OK;
+}
+
+int nns_append_device(cslam_nns* h, const float* d_rows, int64_t count, cudaStream_t s) {
+  if (count <= 0) return CSLAM_OK;
+  CSLAM_TRY(nns_reserve_rows(h, h->n + count));
+  const int threads = 256;
+  const int64_t blocks = (count * 32 + threads - 1) / threads;
+  k_nns_append<<<static_cast<unsigned int>(blocks), threads, 0, s>>>(
+      d_rows, count, h->dim, h->dim_pad, h->d_data, h->d_vv, h->d_shadow, h->n);
+  CSLAM_LAUNCH_CHECK();
+  h->n += count;
+  return CSLAM_OK;
+}
+
+int nns_flush(cslam_nns* h) {
+  if (h->staged == 0) return CSLAM_OK;
+  CSLAM_CUDA(cudaMemcpyAsync(h->d_stage, h->h_stage,
+                             static_cast<size_t>(h->staged) * h->dim * sizeof(float),
+                             cudaMemcpyHostToDevice, h->stream));
+  CSLAM_TRY(nns_append_device(h, h->d_stage, h->staged, h->stream));
+  // the pinned staging buffer is reused by the next add: wait for the copy
+  CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+  h->staged = 0;
+  return CSLAM_OK;
+}
+
+int nns_reserve_queries(cslam_nns* h, int nq, int k) {
+  const int need = (nq + kCoarseBM - 1) / kCoarseBM * kCoarseBM;
+  if (need > h->q_cap) {
+    dev_free(h->d_q64);
+    dev_free(h->d_uu);
+    dev_free(h->d_qh);
+    if (h->d_qraw) { cudaFree(h->d_qraw); h->d_qraw = nullptr; }
+    CSLAM_TRY(dev_alloc(&h->d_q64, static_cast<size_t>(need) * h->dim));
+    CSLAM_TRY(dev_alloc(&h->d_uu, static_cast<size_t>(need)));
+    CSLAM_TRY(dev_alloc(&h->d_qh, static_cast<size_t>(need) * h->dim_pad));
+    CSLAM_CUDA(cudaMalloc(&h->d_qraw, static_cast<size_t>(need) * h->dim * sizeof(double)));
+    h->q_cap = need;
+    CSLAM_TRY(make_fp16_rowmajor_tmap(&h->tmap_q, h->d_qh, need, h->dim_pad, kCoarseBM));
+  }
+  if (!h->d_tau) {
+    CSLAM_TRY(dev_alloc(&h->d_tau, kCoarseBM));
+    CSLAM_TRY(dev_alloc(&h->d_cnt, kCoarseBM));
+    CSLAM_TRY(dev_alloc(&h->d_flags, kCoarseBM));
+    CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), kCoarseBM * sizeof(int)));
+  }
+  (void)k;
+  return CSLAM_OK;
+}
+
+// One query tile (<= kCoarseBM queries starting at q0) through candidate
+// generation + re-rank.  `exact` selects the fp64 scan instead of the tensor
+// cores.  Results land in out_idx/out_sims (device, [*, k], already offset).
+int nns_run_tile(cslam_nns* h, int q0, int nqt, int k, bool exact, int32_t* out_idx,
+                 double* out_sims, cudaStream_t s, bool time_it) {
+  const int n_rows = static_cast<int>(h->n);
+  const int num_tiles = (n_rows + kCoarseBN - 1) / kCoarseBN;
+  const int window = std::min(kRerankMax / 2, std::max(h->window, 2 * k));
+  const bool exhaustive = n_rows <= 2 * h->sample_rows;
+  const int cap_needed =
+      exhaustive ? std::max(num_tiles * kCoarseBN, 256) : std::max(2 * h->sample_rows, 32768);
+  if (cap_needed > h->cand_cap) {
+    CSLAM_CUDA(cudaStreamSynchronize(s));
+    CSLAM_TRY(h->cand.reserve(static_cast<size_t>(cap_needed) * kCoarseBM));
+    h->cand_cap = cap_needed;
+  }
+  // fp16 rounding of both unit-norm operands (2 * 2^-11), fp32 accumulation over
+  // dim_pad terms, fp16 subnormal flush; exact scan only rounds the score to fp32.
+  const float eps = exact ? 1.0e-6f
+                          : (0.0009765625f + static_cast<float>(h->dim_pad) * 1.1920929e-7f +
+                             4.0e-6f);
+
+  CoarseParams cp;
+  cp.num_kb = h->dim_pad / 64;
+  cp.n_rows = n_rows;
+  cp.nq = nqt;
+  cp.q_row0 = q0;
+  cp.cnt = h->d_cnt;
+  cp.cand = h->cand.p;
+  cp.cand_cap = h->cand_cap;
+
+  auto launch_coarse = [&](int tiles, int stride, const float* tau, bool timed) -> int {
+    cp.num_tiles = tiles;
+    cp.tile_stride = stride;
+    cp.tau = tau;
+    CSLAM_CUDA(cudaMemsetAsync(h->d_cnt, 0, kCoarseBM * sizeof(unsigned int), s));
+    if (timed) CSLAM_CUDA(cudaEventRecord(h->ev_c0, s));
+    if (exact) {
+      const int grid = std::min(tiles, h->num_sms * 4);
+      k_nns_coarse_exact<<<grid, 256, 0, s>>>(h->d_data, h->d_vv, h->dim, h->d_q64, h->d_uu, cp);
+      CSLAM_LAUNCH_CHECK();
+    } else {
+      CSLAM_TRY(launch_coarse_tc(&h->tmap_q, &h->tmap_p, cp, h->num_sms, s));
+    }
+    if (timed) CSLAM_CUDA(cudaEventRecord(h->ev_c1, s));
+    h->last_coarse_launches++;
+    return CSLAM_OK;
+  };
+
+  const float* tau = nullptr;
+  if (exhaustive) {
+    CSLAM_TRY(launch_coarse(num_tiles, 1, nullptr, time_it));
+  } else {
+    const int sample_tiles = h->sample_rows / kCoarseBN;
+    const int stride = std::max(1, (num_tiles - 1) / sample_tiles);
+    CSLAM_TRY(launch_coarse(sample_tiles, stride, nullptr, false));
+    k_nns_tau_select<<<nqt, kSelThreads, 0, s>>>(h->cand.p, h->d_cnt, h->cand_cap, window,
+                                                  h->d_tau);
+    CSLAM_LAUNCH_CHECK();
+    tau = h->d_tau;
+    CSLAM_TRY(launch_coarse(num_tiles, 1, tau, time_it));
+  }
+
+  RerankParams rp;
+  rp.cand = h->cand.p;
+  rp.cnt = h->d_cnt;
+  rp.cand_cap = h->cand_cap;
+  rp.tau = tau;
+  rp.data = h->d_data;
+  rp.vv = h->d_vv;
+  rp.dim = h->dim;
+  rp.n_rows = n_rows;
+  rp.q64 = h->d_q64 + static_cast<size_t>(q0) * h->dim;
+  rp.uu = h->d_uu + q0;
+  rp.k = k;
+  rp.window = window;
+  rp.eps = eps;
+  rp.out_idx = out_idx;
+  rp.out_sims = out_sims;
+  rp.flags = h->d_flags;
+  k_nns_select_rerank<<<nqt, kSelThreads, 0, s>>>(rp);
+  CSLAM_LAUNCH_CHECK();
+  return CSLAM_OK;
+}
+
+template <typename T>
+int launch_prep(cslam_nns* h, const void* d_q, int nq, int nq_pad, cudaStream_t s) {
+  const int threads = 256;
+  const int blocks = (nq_pad * 32 + threads - 1) / threads;
+  k_nns_prep_queries<T><<<blocks, threads, 0, s>>>(static_cast<const T*>(d_q), nq, nq_pad, h->dim,
+                                                   h->dim_pad, h->d_q64, h->d_uu, h->d_qh);
+  CSLAM_LAUNCH_CHECK();
+  return CSLAM_OK;
+}
+
+int nns_search_impl(cslam_nns* h, const void* d_queries, int dtype, int nq, int k,
+                    int32_t* d_out_idx, double* d_out_sims, cudaStream_t s, int64_t* out_info) {
+  CSLAM_REQUIRE(nq >= 0 && k >= 1 && k <= kMaxK, "search: need nq >= 0 and 1 <= k <= %d (k=%d)",
+                kMaxK, k);
+  CSLAM_REQUIRE(dtype == CSLAM_DTYPE_F32 || dtype == CSLAM_DTYPE_F64, "search: bad dtype %d",
+                dtype);
+  const int64_t launches0 = g_launches.load();
+  int64_t info[4] = {0, 0, 0, 0};
+  h->last_coarse_launches = 0;
+  h->timing_valid = false;
+  if (nq == 0) {
+    if (out_info) memcpy(out_info, info, sizeof(info));
+    return CSLAM_OK;
+  }
+  CSLAM_TRY(nns_flush(h));
+  if (h->n == 0) {
+    const size_t tot = static_cast<size_t>(nq) * k;
+    k_fill_empty<<<static_cast<unsigned int>((tot + 255) / 256), 256, 0, s>>>(d_out_idx,
+                                                                             d_out_sims, tot);
+    CSLAM_LAUNCH_CHECK();
+    if (out_info) {
+      info[3] = g_launches.load() - launches0;
+      memcpy(out_info, info, sizeof(info));
+    }
+    return CSLAM_OK;
+  }
+  CSLAM_TRY(nns_reserve_queries(h, nq, k));
+  const int nq_pad = (nq + kCoarseBM - 1) / kCoarseBM * kCoarseBM;
+  if (dtype == CSLAM_DTYPE_F32) {
+    CSLAM_TRY(launch_prep<float>(h, d_queries, nq, nq_pad, s));
+  } else {
+    CSLAM_TRY(launch_prep<double>(h, d_queries, nq, nq_pad, s));
+  }
+  CSLAM_CUDA(cudaEventRecord(h->ev_t0, s));
+  const bool exact = (h->mode == 1);
+  for (int q0 = 0; q0 < nq; q0 += kCoarseBM) {
+    const int nqt = std::min(kCoarseBM, nq - q0);
+    int32_t* oi = d_out_idx + static_cast<size_t>(q0) * k;
+    double* os = d_out_sims + static_cast<size_t>(q0) * k;
+    CSLAM_TRY(nns_run_tile(h, q0, nqt, k, exact, oi, os, s, /*time_it=*/q0 + kCoarseBM >= nq));
+    // escalation check: read the per-query flags
+    CSLAM_CUDA(cudaMemcpyAsync(h->h_flags, h->d_flags, nqt * sizeof(int), cudaMemcpyDeviceToHost,
+                               s));
+    CSLAM_CUDA(cudaStreamSynchronize(s));
+    std::vector<int> redo;
+    for (int i = 0; i < nqt; ++i) {
+      if (h->h_flags[i] == 2) redo.push_back(i);
+      else if (h->h_flags[i] == 1) info[1]++;
+      else info[0]++;
+    }
+    for (int i : redo) {
+      if (exact) {
+        set_error("nns search: exact scan could not resolve query %d (more than %d tied rows?)",
+                  q0 + i, kRerankMax);
+        return CSLAM_ERR_LIMIT;
+      }
+      CSLAM_TRY(nns_run_tile(h, q0 + i, 1, k, true, oi + static_cast<size_t>(i) * k,
+                             os + static_cast<size_t>(i) * k, s, false));
+      CSLAM_CUDA(cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CSLAM_CUDA(cudaStreamSynchronize(s));
+      if (h->h_flags[0] == 2) {
+        set_error("nns search: exact scan could not resolve query %d (more than %d tied rows?)",
+                  q0 + i, kRerankMax);
+        return CSLAM_ERR_LIMIT;
+      }
+      info[2]++;
+    }
+  }
+  CSLAM_CUDA(cudaEventRecord(h->ev_t1, s));
+  h->timing_valid = true;
+  info[3] = g_launches.load() - launches0;
+  if (out_info) memcpy(out_info, info, sizeof(info));
+  return CSLAM_OK;
+}
+
+}  // namespace
+}  // namespace cslam
+
+extern "C" {
+
+int cslam_nns_create(int dim, int device, cslam_nns_t** out) {
+  CSLAM_REQUIRE(out != nullptr, "nns_create: out is NULL");
+  *out = nullptr;
+  CSLAM_REQUIRE(dim > 0 && dim <= 65536, "nns_create: dim must be in [1, 65536] (got %d)", dim);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("nns_create: no CUDA device available (this library has no CPU fallback)");
+    return CSLAM_ERR_CUDA;
+  }
+  CSLAM_REQUIRE(device >= 0 && device < ndev, "nns_create: device %d out of range [0,%d)", device,
+                ndev);
+  DeviceGuard g(device);
+  if (!g.ok) {
+    set_error("nns_create: cannot select device %d", device);
+    return CSLAM_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  CSLAM_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("nns_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+              prop.major, prop.minor);
+    return CSLAM_ERR_CUDA;
+  }
+  cslam_nns* h = new cslam_nns();
+  h->device = device;
+  h->dim = dim;
+  h->dim_pad = (dim + 63) / 64 * 64;
+  h->num_sms = prop.multiProcessorCount;
+  int st = CSLAM_OK;
+  do {
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { st = CSLAM_ERR_CUDA; break; }
+    if (cudaMallocHost(reinterpret_cast<void**>(&h->h_stage),
+                       static_cast<size_t>(kStageRows) * dim * sizeof(float)) != cudaSuccess) { st = CSLAM_ERR_OOM; break; }
+    if (cudaMalloc(reinterpret_cast<void**>(&h->d_stage),
+                   static_cast<size_t>(kStageRows) * dim * sizeof(float)) != cudaSuccess) { st = CSLAM_ERR_OOM; break; }
+    if (cudaEventCreate(&h->ev_t0) != cudaSuccess || cudaEventCreate(&h->ev_t1) != cudaSuccess ||
+        cudaEventCreate(&h->ev_c0) != cudaSuccess || cudaEventCreate(&h->ev_c1) != cudaSuccess) { st = CSLAM_ERR_CUDA; break; }
+  } while (0);
+  if (st != CSLAM_OK) {
+    set_error("nns_create: resource allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cslam_nns_destroy(h);
+    return st;
+  }
+  *out = h;
+  return CSLAM_OK;
+}
+
+int cslam_nns_destroy(cslam_nns_t* h) {
+  if (!h) return CSLAM_OK;
+  DeviceGuard g(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  dev_free(h->d_data);
+  dev_free(h->d_shadow);
+  dev_free(h->d_vv);
+  dev_free(h->d_stage);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  dev_free(h->d_q64);
+  dev_free(h->d_uu);
+  dev_free(h->d_qh);
+  if (h->d_qraw) cudaFree(h->d_qraw);
+  dev_free(h->d_tau);
+  dev_free(h->d_cnt);
+  dev_free(h->d_flags);
+  if (h->h_flags) cudaFreeHost(h->h_flags);
+  h->cand.release();
+  dev_free(h->d_out_idx);
+  dev_free(h->d_out_sims);
+  if (h->h_q) cudaFreeHost(h->h_q);
+  if (h->h_out_idx) cudaFreeHost(h->h_out_idx);
+  if (h->h_out_sims) cudaFreeHost(h->h_out_sims);
+  if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+  if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+  if (h->ev_c0) cudaEventDestroy(h->ev_c0);
+  if (h->ev_c1) cudaEventDestroy(h->ev_c1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return CSLAM_OK;
+}
+
+int cslam_nns_add_host(cslam_nns_t* h, const void* rows, int dtype, int64_t count) {
+  CSLAM_REQUIRE(h && (rows || count == 0) && count >= 0, "nns_add_host: bad arguments");
+  CSLAM_REQUIRE(dtype == CSLAM_DTYPE_F32 || dtype == CSLAM_DTYPE_F64, "nns_add_host: bad dtype %d",
+                dtype);
+  DeviceGuard g(h->device);
+  int64_t done = 0;
+  while (done < count) {
+    const int64_t take = std::min<int64_t>(count - done, kStageRows - h->staged);
+    float* dst = h->h_stage + h->staged * h->dim;
+    const size_t elems = static_cast<size_t>(take) * h->dim;
+    if (dtype == CSLAM_DTYPE_F32) {
+      memcpy(dst, static_cast<const float*>(rows) + done * h->dim, elems * sizeof(float));
+    } else {
+      const double* src = static_cast<const double*>(rows) + done * h->dim;
+      for (size_t i = 0; i < elems; ++i) dst[i] = static_cast<float>(src[i]);  // `.data` is float32
+    }
+    h->staged += take;
+    done += take;
+    if (h->staged == kStageRows) CSLAM_TRY(nns_flush(h));
+  }
+  return CSLAM_OK;
+}
+
+int cslam_nns_add_device(cslam_nns_t* h, const float* d_rows, int64_t count, void* stream) {
+  CSLAM_REQUIRE(h && (d_rows || count == 0) && count >= 0, "nns_add_device: bad arguments");
+  DeviceGuard g(h->device);
+  CSLAM_TRY(nns_flush(h));
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  return nns_append_device(h, d_rows, count, s);
+}
+
+int64_t cslam_nns_size(cslam_nns_t* h) { return h ? h->n + h->staged : 0; }
+int cslam_nns_dim(cslam_nns_t* h) { return h ? h->dim : 0; }
+
+int cslam_nns_read_rows(cslam_nns_t* h, int64_t start, int64_t count, float* out) {
+  CSLAM_REQUIRE(h && out && start >= 0 && count >= 0, "nns_read_rows: bad arguments");
+  DeviceGuard g(h->device);
+  CSLAM_TRY(nns_flush(h));
+  CSLAM_REQUIRE(start + count <= h->n, "nns_read_rows: range [%lld,%lld) exceeds size %lld",
+                static_cast<long long>(start), static_cast<long long>(start + count),
+                static_cast<long long>(h->n));
+  if (count == 0) return CSLAM_OK;
+  CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+  CSLAM_CUDA(cudaMemcpy(out, h->d_data + start * h->dim,
+                        static_cast<size_t>(count) * h->dim * sizeof(float),
+                        cudaMemcpyDeviceToHost));
+  return CSLAM_OK;
+}
+
+int cslam_nns_search_device(cslam_nns_t* h, const void* d_queries, int dtype, int nq, int k,
+                            int32_t* d_out_idx, double* d_out_sims, void* stream,
+                            int64_t* out_info) {
+  CSLAM_REQUIRE(h && (nq == 0 || (d_queries && d_out_idx && d_out_sims)),
+                "nns_search_device: NULL argument");
+  DeviceGuard g(h->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  return nns_search_impl(h, d_queries, dtype, nq, k, d_out_idx, d_out_sims, s, out_info);
+}
+
+int cslam_nns_search_host(cslam_nns_t* h, const void* queries, int dtype, int nq, int k,
+                          int32_t* out_idx, double* out_sims, int64_t* out_info) {
+  CSLAM_REQUIRE(h && (nq == 0 || (queries && out_idx && out_sims)),
+                "nns_search_host: NULL argument");
+  CSLAM_REQUIRE(nq >= 0 && k >= 1 && k <= kMaxK, "search: need nq >= 0 and 1 <= k <= %d (k=%d)",
+                kMaxK, k);
+  CSLAM_REQUIRE(dtype == CSLAM_DTYPE_F32 || dtype == CSLAM_DTYPE_F64, "search: bad dtype %d",
+                dtype);
+  if (nq == 0) return nns_search_impl(h, nullptr, dtype, 0, k, nullptr, nullptr, nullptr, out_info);
+  DeviceGuard g(h->device);
+  cudaStream_t s = h->stream;
+  const size_t esz = dtype == CSLAM_DTYPE_F32 ? sizeof(float) : sizeof(double);
+  const size_t qbytes = static_cast<size_t>(nq) * h->dim * esz;
+  CSLAM_TRY(nns_reserve_queries(h, nq, k));
+  if (qbytes > h->h_q_bytes) {
+    if (h->h_q) cudaFreeHost(h->h_q);
+    h->h_q = nullptr;
+    h->h_q_bytes = 0;
+    CSLAM_CUDA(cudaMallocHost(&h->h_q, qbytes));
+    h->h_q_bytes = qbytes;
+  }
+  const size_t oel = static_cast<size_t>(nq) * k;
+  if (oel > h->h_out_elems) {
+    if (h->h_out_idx) cudaFreeHost(h->h_out_idx);
+    if (h->h_out_sims) cudaFreeHost(h->h_out_sims);
+    h->h_out_idx = nullptr;
+    h->h_out_sims = nullptr;
+    dev_free(h->d_out_idx);
+    dev_free(h->d_out_sims);
+    h->h_out_elems = 0;
+    CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_out_idx), oel * sizeof(int32_t)));
+    CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_out_sims), oel * sizeof(double)));
+    CSLAM_TRY(dev_alloc(&h->d_out_idx, oel));
+    CSLAM_TRY(dev_alloc(&h->d_out_sims, oel));
+    h->h_out_elems = oel;
+  }
+  memcpy(h->h_q, queries, qbytes);
+  CSLAM_CUDA(cudaMemcpyAsync(h->d_qraw, h->h_q, qbytes, cudaMemcpyHostToDevice, s));
+  CSLAM_TRY(nns_search_impl(h, h->d_qraw, dtype, nq, k, h->d_out_idx, h->d_out_sims, s, out_info));
+  CSLAM_CUDA(cudaMemcpyAsync(h->h_out_idx, h->d_out_idx, oel * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, s));
+  CSLAM_CUDA(cudaMemcpyAsync(h->h_out_sims, h->d_out_sims, oel * sizeof(double),
+                             cudaMemcpyDeviceToHost, s));
+  CSLAM_CUDA(cudaStreamSynchronize(s));
+  memcpy(out_idx, h->h_out_idx, oel * sizeof(int32_t));
+  memcpy(out_sims, h->h_out_sims, oel * sizeof(double));
+  return CSLAM_OK;
+}
+
+int cslam_nns_set_mode(cslam_nns_t* h, int mode) {
+  CSLAM_REQUIRE(h && (mode == 0 || mode == 1), "nns_set_mode: mode must be 0 or 1");
+  h->mode = mode;
+  return CSLAM_OK;
+}
+
+int cslam_nns_set_params(cslam_nns_t* h, int rerank_window, int sample_rows) {
+  CSLAM_REQUIRE(h, "nns_set_params: NULL handle");
+  CSLAM_REQUIRE(rerank_window >= 1 && rerank_window <= kRerankMax / 2,
+                "nns_set_params: rerank_window must be in [1,%d]", kRerankMax / 2);
+  CSLAM_REQUIRE(sample_rows >= kCoarseBN && sample_rows % kCoarseBN == 0 && sample_rows <= 65536,
+                "nns_set_params: sample_rows must be a multiple of %d in [%d, 65536]", kCoarseBN,
+                kCoarseBN);
+  h->window = rerank_window;
+  h->sample_rows = sample_rows;
+  return CSLAM_OK;
+}
+
+int cslam_nns_last_timing(cslam_nns_t* h, float* coarse_ms, int* coarse_launches,
+                          float* total_ms) {
+  CSLAM_REQUIRE(h, "nns_last_timing: NULL handle");
+  CSLAM_REQUIRE(h->timing_valid, "nns_last_timing: no completed search to report");
+  DeviceGuard g(h->device);
+  CSLAM_CUDA(cudaEventSynchronize(h->ev_t1));
+  float c = 0.f, t = 0.f;
+  CSLAM_CUDA(cudaEventElapsedTime(&c, h->ev_c0, h->ev_c1));
+  CSLAM_CUDA(cudaEventElapsedTime(&t, h->ev_t0, h->ev_t1));
+  if (coarse_ms) *coarse_ms = c;
+  if (coarse_launches) *coarse_launches = h->last_coarse_launches;
+  if (total_ms) *total_ms = t;
+  return CSLAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,365 @@
+// Coarse cosine scoring of a query tile against a descriptor pool on the
+// 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by
+// TMA into 128B-swizzled shared memory), with the candidate filter fused into
+// the epilogue.
+//
+// Replaces the per-row Python loop of NearestNeighborsMatching.search
+// (reference cslam/nns_matching.py:55-58) for the *candidate generation*
+// stage; the exact float64 scores the reference returns are recomputed for the
+// survivors by k_nns_select_rerank (nns.cu).
+//
+//   D[128 queries, 256 pool rows] += Qh[128, 64] * Ph[256, 64]^T      (fp16 in, fp32 acc)
+//
+// Layout
+//   * Qh  [128*T, dim_pad] fp16, rows L2-normalised, zero padded   (A operand, K-major)
+//   * Ph  [cap,   dim_pad] fp16, rows L2-normalised, zero padded   (B operand, K-major)
+//   * TMEM: 2 accumulator buffers x 256 fp32 columns = all 512 columns; TMEM lane m
+//     holds query m, column j holds pool row (tile_row0 + j).
+// Warp roles (256 threads, 1 CTA / SM, persistent over pool tiles):
+//   warp 0    TMA producer (one lane)       warp 1  MMA issuer (one lane)
+//   warp 2    TMEM allocator                warp 3  idle
+//   warps 4-7 epilogue: thread = query; tcgen05.ld 32 columns at a time, compare
+//             with the query's threshold tau, append survivors (score, row) to the
+//             query's candidate list in global memory.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "nns_internal.cuh"
+
+namespace cslam {
+namespace {
+
+constexpr int BM = kCoarseBM;  // queries per tile (UMMA M)
+constexpr int BN = kCoarseBN;  // pool rows per tile (UMMA N)
+constexpr int BK = 64;         // fp16 elements per k-block = one 128B swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 1024>>4 | version=1 [46,48) |
+// layout_type=SWIZZLE_128B(2) [61,64).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16,
+// both K-major, N>>3 at [17,23), M>>4 at [24,29).
+constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) |
+                            (static_cast<uint32_t>(BN >> 3) << 17) |
+                            (static_cast<uint32_t>(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct PipeState {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+  }
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
+                const __grid_constant__ CUtensorMap tmap_p, CoarseParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto smem_a = [&](int s) { return smem_base + s * STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * STAGE_BYTES + A_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_p) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int num_kb = prm.num_kb;
+  const int first_tile = blockIdx.x;
+  const int tile_step = gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps;
+      for (int tile = first_tile; tile < prm.num_tiles; tile += tile_step) {
+        const int row0 = static_cast<int>(static_cast<int64_t>(tile) * prm.tile_stride * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
+          mbar_expect_tx(full_bar(ps.stage), STAGE_BYTES);
+          tma_load_2d(smem_a(ps.stage), &tmap_q, full_bar(ps.stage), kb * BK, prm.q_row0,
+                      kEvictLast);
+          tma_load_2d(smem_b(ps.stage), &tmap_p, full_bar(ps.stage), kb * BK, row0,
+                      kEvictFirst);
+          ps.advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      PipeState ps;
+      int it = 0;
+      for (int tile = first_tile; tile < prm.num_tiles; tile += tile_step, ++it) {
+        const int buf = it & 1;
+        mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(ps.stage), ps.phase);
+          tc_fence_after();
+          const uint32_t a0 = smem_a(ps.stage);
+          const uint32_t b0 = smem_b(ps.stage);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = make_sw128_desc(a0 + k * (UMMA_K * 2));
+            const uint64_t bdesc = make_sw128_desc(b0 + k * (UMMA_K * 2));
+            umma_f16(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(ps.stage));  // frees the smem slot once the MMAs retire
+          ps.advance();
+        }
+        umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    const int q = ew * 32 + lane;
+    const bool q_valid = q < prm.nq;
+    const float tau = (q_valid && prm.tau != nullptr) ? prm.tau[q] : -INFINITY;
+    unsigned int* my_cnt = prm.cnt + (q_valid ? q : 0);
+    uint2* my_cand = prm.cand + static_cast<size_t>(q_valid ? q : 0) * prm.cand_cap;
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    int it = 0;
+    for (int tile = first_tile; tile < prm.num_tiles; tile += tile_step, ++it) {
+      const int buf = it & 1;
+      const int row0 = static_cast<int>(static_cast<int64_t>(tile) * prm.tile_stride * BN);
+      mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(lane_taddr + static_cast<uint32_t>(buf * BN + c), r);
+        tmem_ld_wait();
+        if (q_valid) {
+          float m = __uint_as_float(r[0]);
+#pragma unroll
+          for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+          if (m >= tau) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float s = __uint_as_float(r[j]);
+              const int row = row0 + c + j;
+              if (s >= tau && row < prm.n_rows) {
+                const unsigned int pos = atomicAdd(my_cnt, 1u);
+                if (pos < static_cast<unsigned int>(prm.cand_cap))
+                  my_cand[pos] = make_uint2(__float_as_uint(s), static_cast<uint32_t>(row));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !p) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+}  // namespace
+
+int make_fp16_rowmajor_tmap(void* out_map, const void* base, int64_t rows, int cols_pad,
+                            int box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return CSLAM_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols_pad), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols_pad) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld cols=%d box_rows=%d",
+              static_cast<int>(r), static_cast<long long>(rows), cols_pad, box_rows);
+    return CSLAM_ERR_CUDA;
+  }
+  return CSLAM_OK;
+}
+
+int launch_coarse_tc(const void* tmap_q, const void* tmap_p, const CoarseParams& prm,
+                     int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CSLAM_CUDA(cudaFuncSetAttribute(k_nns_coarse_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    SMEM_BYTES));
+    attr_set = true;
+  }
+  if (prm.num_tiles <= 0) return CSLAM_OK;
+  const int grid = prm.num_tiles < num_sms ? prm.num_tiles : num_sms;
+  k_nns_coarse_tc<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(
+      *reinterpret_cast<const CUtensorMap*>(tmap_q), *reinterpret_cast<const CUtensorMap*>(tmap_p),
+      prm);
+  CSLAM_LAUNCH_CHECK();
+  return CSLAM_OK;
+}
+
+}  // namespace cslam

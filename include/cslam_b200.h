@@ -1,0 +1,114 @@
+/*
+ * cslam_b200.h — C ABI of libcslam_b200.so, the B200 (sm_100a) loop-closure
+ * front end for Swarm-SLAM's `cslam` package.
+ *
+ * The reference (lajoiepy/cslam) has NO FFI on this path: its boundary is the
+ * Python class API.  Every entry point below therefore cites the reference
+ * Python method whose arithmetic it replaces; the Python classes in
+ * `cslam_b200/` keep the reference names/signatures and call these symbols
+ * through ctypes (see INTEGRATION.md for the stub a cslam maintainer adds).
+ *
+ * Conventions
+ *   - plain C types only: pointers, sizes, ints.  No torch / C++ types.
+ *   - every function returns an int status (CSLAM_OK == 0, <0 = error) unless
+ *     documented otherwise; `cslam_last_error()` returns a thread-local
+ *     human-readable message for the last failure.  Nothing throws across
+ *     the ABI.
+ *   - "host" variants take host pointers and perform the H2D / D2H copies
+ *     themselves; "device" variants take device pointers valid on the
+ *     handle's device and are asynchronous on the given stream
+ *     (`stream` is a `cudaStream_t` passed as void*; NULL = the handle's own
+ *     stream).
+ *   - handles are not re-entrant (the reference is single-threaded:
+ *     cslam/loop_closure_detection_node.py:106-110).
+ *   - there is NO CPU fallback: without a CUDA device every compute call
+ *     returns CSLAM_ERR_CUDA.
+ */
+#ifndef CSLAM_B200_H
+#define CSLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSLAM_OK 0
+#define CSLAM_ERR_INVALID -1   /* bad argument */
+#define CSLAM_ERR_CUDA -2      /* CUDA runtime / driver failure, or no device */
+#define CSLAM_ERR_OOM -3       /* allocation failure */
+#define CSLAM_ERR_LIMIT -4     /* request exceeds a documented limit */
+#define CSLAM_ERR_SINGULAR -5  /* Laplacian singular / graph disconnected
+                                  (reference: SuperLU RuntimeError swallowed by
+                                  cslam/algebraic_connectivity_maximization.py:448-466) */
+#define CSLAM_ERR_NOCONV -6    /* iterative solver did not converge */
+
+#define CSLAM_DTYPE_F32 0
+#define CSLAM_DTYPE_F64 1
+
+/* ---- library ---------------------------------------------------------- */
+const char* cslam_version(void);
+const char* cslam_last_error(void);
+/* number of visible CUDA devices (0 if none / driver missing) */
+int cslam_device_count(void);
+/* total kernels launched by this library in this process (bench `gpu_launches`) */
+int64_t cslam_launch_count(void);
+
+/* ---- A6: cosine nearest-neighbour matching --------------------------- *
+ * Replaces cslam/nns_matching.py:6-76 (NearestNeighborsMatching).
+ * Pool rows are stored float32 exactly like the reference's `.data`
+ * (nns_matching.py:21,39); scoring of the returned matches is
+ *   sim = 1 - clip(1 - q.x / sqrt((q.q) (x.x)), 0, 2)          (float64)
+ * i.e. scipy.spatial.distance.cosine as called at nns_matching.py:58,
+ * with x.x accumulated in float32 as np.dot(float32,float32) does.
+ */
+typedef struct cslam_nns cslam_nns_t;
+
+/* dim > 0; device = CUDA ordinal.  (NearestNeighborsMatching.__init__, :10-21) */
+int cslam_nns_create(int dim, int device, cslam_nns_t** out);
+int cslam_nns_destroy(cslam_nns_t* h);
+/* Append `count` rows ([count, dim] row-major, dtype F32 or F64; F64 is
+ * rounded to float32 on store like `self.data[self.n] = vector`, :39).
+ * Row ids are assigned consecutively from the current size.  (add_item, :23-40) */
+int cslam_nns_add_host(cslam_nns_t* h, const void* rows, int dtype, int64_t count);
+/* Same, rows already on the device as float32. */
+int cslam_nns_add_device(cslam_nns_t* h, const float* d_rows, int64_t count, void* stream);
+int64_t cslam_nns_size(cslam_nns_t* h);
+int cslam_nns_dim(cslam_nns_t* h);
+/* Copy rows [start, start+count) of the float32 pool to host (`.data`). */
+int cslam_nns_read_rows(cslam_nns_t* h, int64_t start, int64_t count, float* out);
+
+/* Top-k search for `nq` queries ([nq, dim], F32 or F64).  (search, :42-61)
+ * out_idx  [nq, k] int32 row ids, best first; unused slots = -1
+ * out_sims [nq, k] float64 similarities; unused slots = NaN
+ * Each query returns min(k, size) matches.  Ties in similarity are ordered
+ * by DESCENDING row id (what np.argsort(sim)[::-1] yields for equal keys,
+ * nns_matching.py:60).  1 <= k <= 1024.
+ * out_info (optional, may be NULL) [4] int64:
+ *   [0] queries answered by the tensor-core coarse pass + exact re-rank
+ *   [1] queries that needed a widened re-rank window
+ *   [2] queries re-run through the exact fp64 scan kernel
+ *   [3] kernels launched by this call                                   */
+int cslam_nns_search_host(cslam_nns_t* h, const void* queries, int dtype, int nq, int k,
+                          int32_t* out_idx, double* out_sims, int64_t* out_info);
+/* Device variant: queries/out_* are device pointers; async on `stream`
+ * except for the (rare) escalation check, which synchronises the stream. */
+int cslam_nns_search_device(cslam_nns_t* h, const void* d_queries, int dtype, int nq, int k,
+                            int32_t* d_out_idx, double* d_out_sims, void* stream,
+                            int64_t* out_info);
+/* Tuning / test hooks.  mode: 0 = auto (tcgen05 coarse pass + exact re-rank,
+ * escalating to the exact scan only when the error-bound check fails),
+ * 1 = force the exact fp64 scan kernel (validation path, still GPU). */
+int cslam_nns_set_mode(cslam_nns_t* h, int mode);
+/* re-rank window k' (default 128), sample rows for the threshold pass
+ * (default 16384; pools <= 2*sample are scored exhaustively). */
+int cslam_nns_set_params(cslam_nns_t* h, int rerank_window, int sample_rows);
+/* Time (ms, CUDA events on the handle's stream) of the coarse kernel launches
+ * of the last search call and how many there were. */
+int cslam_nns_last_timing(cslam_nns_t* h, float* coarse_ms, int* coarse_launches,
+                          float* total_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSLAM_B200_H */

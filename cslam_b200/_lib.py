@@ -47,7 +47,7 @@ SIGNATURES = {
     "cslam_nns_search_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "cslam_nns_search_device": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "cslam_nns_set_mode": (_i, [_vp, _i]),
-    "cslam_nns_set_params": (_i, [_vp, _i, _i]),
+    "cslam_nns_set_sample_rows": (_i, [_vp, _i]),
     "cslam_nns_last_timing": (_i, [_vp, _P(_f), _P(_i), _P(_f)]),
 }
 

@@ -8,17 +8,18 @@
 //   candidates: k_nns_coarse_tc      tcgen05 GEMM with fused threshold filter (nns_coarse_tc.cu)
 //              k_nns_coarse_exact    fp64 SIMT scan with the same interface (validation /
 //                                    escalation path; still on the GPU)
-//   threshold: k_nns_tau_select      k'-th largest sampled score per query (radix select)
-//   result   : k_nns_select_rerank   top-k' by coarse score, exact float64 cosine from the
-//                                    float32 rows exactly as the reference scores them,
-//                                    sort, rigorous error-bound check
+//   threshold: k_nns_tau_select      k-th largest sampled chunk maximum - 2 eps per query
+//   result   : k_nns_select          keep {coarse >= c_k - 2 eps} (c_k = k-th largest coarse)
+//              k_nns_rerank          exact float64 cosine of the kept float32 rows, exactly
+//                                    as the reference scores them
+//              k_nns_finalize        sort (similarity desc, row id desc), emit top-k
 //
-// Exactness argument: every pool row outside the re-ranked
-// set has coarse score < T, and |coarse - exact| <= eps by construction
-// (fp16 rounding of unit vectors + fp32 accumulation), so if T + eps <= s_k
-// (the exact k-th best of the re-ranked set) no outside row can enter the
-// top-k.  When the check fails the window is widened to {coarse >= s_k - eps};
-// if even that is impossible the query is re-run through the exact scan.
+// Exactness argument (spelled out above k_nns_select and in DESIGN.md): with
+// |coarse - exact| <= eps for every row (fp16 rounding of unit vectors + fp32
+// accumulation), the exact top-k is contained in {coarse >= c_k - 2 eps}, and the
+// candidate threshold tau is chosen <= c_k - 2 eps, so the kept set provably contains the
+// exact top-k; only capacity limits can fail, and those re-run the query through the
+// exact fp64 scan kernel.
 #include <cuda_fp16.h>
 #include <math.h>
 
@@ -133,12 +134,26 @@ k_nns_coarse_exact(const float* __restrict__ data, const float* __restrict__ vv,
         const double uv = warp_sum(acc);
         if (lane == 0) {
           const float s = static_cast<float>(uv / sqrt(uu[prm.q_row0 + q] * vvd));
+          if (prm.mode == 1) {
+            atomicMax(prm.smax + static_cast<size_t>(q) * prm.smax_stride +
+                          tile * (kCoarseBN / kChunk) + r / kChunk,
+                      f32_to_key(s));
+            continue;
+          }
           const float tau = prm.tau ? prm.tau[q] : -INFINITY;
           if (s >= tau) {
-            const unsigned int pos = atomicAdd(prm.cnt + q, 1u);
-            if (pos < static_cast<unsigned int>(prm.cand_cap))
-              prm.cand[static_cast<size_t>(q) * prm.cand_cap + pos] =
-                  make_uint2(__float_as_uint(s), static_cast<uint32_t>(row));
+            unsigned int* qc = prm.cnt + static_cast<size_t>(q) * (prm.nsub + 1);
+            uint2* qcand = prm.cand + static_cast<size_t>(q) * cand_slots(prm.nsub);
+            const uint2 e = make_uint2(__float_as_uint(s), static_cast<uint32_t>(row));
+            const int sub = blockIdx.x * 2 + (r >= kCoarseBN / 2 ? 1 : 0);
+            const unsigned int pos = atomicAdd(qc + sub, 1u);
+            if (pos < static_cast<unsigned int>(kSegCap)) {
+              qcand[static_cast<size_t>(sub) * kSegCap + pos] = e;
+            } else {
+              const unsigned int opos = atomicAdd(qc + prm.nsub, 1u);
+              if (opos < static_cast<unsigned int>(kOvfCap))
+                qcand[static_cast<size_t>(prm.nsub) * kSegCap + opos] = e;
+            }
           }
         }
       }
@@ -147,20 +162,116 @@ k_nns_coarse_exact(const float* __restrict__ data, const float* __restrict__ vv,
 }
 
 // ---------------------------------------------------------------------------
-// Block-wide radix select: key of the `kth` largest (1-based) score among
-// c[0..n).  4 passes of 8 bits, MSB first.  s_hist: 256 counters, s_ctl: 2 words.
+// k_nns_tau_select: tau[q] = (the `kth` largest of the sampled chunk maxima) - slack.
+// Every chunk maximum is a distinct pool row, so at least `kth` pool rows score
+// >= that value: the pool's kth largest coarse score is >= tau[q] + slack.
 // ---------------------------------------------------------------------------
-__device__ uint32_t block_kth_largest_key(const uint2* __restrict__ c, int n, int kth,
-                                          uint32_t* s_hist, uint32_t* s_ctl) {
+constexpr int kTauThreads = 256;
+constexpr int kTauMax = 4096;  // max sampled chunks per query
+
+__global__ void __launch_bounds__(kTauThreads)
+k_nns_tau_select(const uint32_t* __restrict__ smax, int stride, int nchunks, int kth,
+                 float slack, float* __restrict__ tau) {
+  __shared__ uint32_t s[kTauMax];
+  const int q = blockIdx.x;
+  int P = 1;
+  while (P < nchunks) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += blockDim.x)
+    s[i] = i < nchunks ? smax[static_cast<size_t>(q) * stride + i] : 0u;
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int st = size >> 1; st > 0; st >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const int lo = ((t & ~(st - 1)) << 1) | (t & (st - 1));  // st is a power of two
+        const int hi = lo + st;
+        const bool desc = ((lo & size) == 0);
+        const uint32_t a = s[lo], b = s[hi];
+        if (desc ? (a < b) : (a > b)) { s[lo] = b; s[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    // round toward -inf: a threshold that is too low only costs candidates
+    float t = -INFINITY;
+    if (kth <= nchunks) t = __fsub_rd(key_to_f32(s[kth - 1]), slack);
+    tau[q] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Candidate-list traversal.  A query's list is `nsub` private sub-segments of
+// kSegCap slots (s_cnt[sub] valid entries each) plus the overflow region
+// (s_cnt[nsub] entries).  All kSelThreads threads call `f(valid, entry)`
+// convergently so that f may use warp collectives.
+// ---------------------------------------------------------------------------
+template <typename F>
+__device__ __forceinline__ void for_each_candidate(const uint2* __restrict__ c,
+                                                   const uint32_t* s_cnt, int nsub, F f) {
+  constexpr int kPerSweep = kSelThreads / kSegCap;
+  const int off = threadIdx.x & (kSegCap - 1);
+  for (int base = 0; base < nsub; base += kPerSweep) {
+    const int sub = base + threadIdx.x / kSegCap;
+    const bool valid = sub < nsub && off < static_cast<int>(s_cnt[sub]);
+    uint2 e = make_uint2(0u, 0u);
+    if (valid) e = c[static_cast<size_t>(sub) * kSegCap + off];
+    f(valid, e);
+  }
+  const int n_ovf = static_cast<int>(s_cnt[nsub]);
+  const uint2* o = c + static_cast<size_t>(nsub) * kSegCap;
+  for (int base = 0; base < n_ovf; base += kSelThreads) {
+    const int i = base + threadIdx.x;
+    const bool valid = i < n_ovf;
+    uint2 e = make_uint2(0u, 0u);
+    if (valid) e = o[i];
+    f(valid, e);
+  }
+}
+
+// Loads the per-sub-segment counts of query q into shared memory (clamped to capacity).
+// s_tot[0] = stored candidates, s_tot[1] = 1 if the overflow region dropped entries.
+__device__ int load_counts(const unsigned int* __restrict__ cnt, int nsub, uint32_t* s_cnt,
+                           int* s_tot) {
+  if (threadIdx.x == 0) {
+    s_tot[0] = 0;
+    s_tot[1] = 0;
+  }
+  __syncthreads();
+  int local = 0;
+  for (int i = threadIdx.x; i <= nsub; i += blockDim.x) {
+    const unsigned int raw = cnt[i];
+    const unsigned int lim = (i == nsub) ? kOvfCap : kSegCap;
+    const unsigned int v = raw < lim ? raw : lim;
+    s_cnt[i] = v;
+    local += static_cast<int>(v);
+    if (i == nsub && raw > lim) s_tot[1] = 1;
+  }
+  if (local) atomicAdd(&s_tot[0], local);
+  __syncthreads();
+  return s_tot[0];
+}
+
+// Block-wide radix select over a candidate list in global memory: key of the `kth`
+// largest (1-based) score.  4 passes of 8 bits, MSB first; histogram updates are
+// aggregated per warp with match_any.  Only used for lists too long for shared memory.
+__device__ uint32_t block_kth_largest_key(const uint2* __restrict__ c, const uint32_t* s_cnt,
+                                          int nsub, int kth, uint32_t* s_hist, uint32_t* s_ctl) {
   uint32_t prefix = 0, mask = 0;
   int remaining = kth;
+  const int lane = threadIdx.x & 31;
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint32_t key = f32_to_key(__uint_as_float(c[i].x));
-      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
-    }
+    for_each_candidate(c, s_cnt, nsub, [&](bool valid, uint2 e) {
+      const uint32_t key = f32_to_key(__uint_as_float(e.x));
+      const bool take = valid && ((key & mask) == prefix);
+      const unsigned int active = __ballot_sync(0xffffffffu, take);
+      if (take) {
+        const uint32_t digit = (key >> shift) & 255u;
+        const unsigned int peers = __match_any_sync(active, digit);
+        if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], __popc(peers));
+      }
+    });
     __syncthreads();
     if (threadIdx.x == 0) {
       int acc = 0;
@@ -182,177 +293,271 @@ __device__ uint32_t block_kth_largest_key(const uint2* __restrict__ c, int n, in
   return prefix;
 }
 
-__global__ void __launch_bounds__(kSelThreads)
-k_nns_tau_select(const uint2* __restrict__ cand, const unsigned int* __restrict__ cnt,
-                 int cand_cap, int kth, float* __restrict__ tau) {
-  __shared__ uint32_t s_hist[256];
-  __shared__ uint32_t s_ctl[2];
-  const int q = blockIdx.x;
-  const int n = static_cast<int>(min(cnt[q], static_cast<unsigned int>(cand_cap)));
-  const uint2* c = cand + static_cast<size_t>(q) * cand_cap;
-  if (n < kth) {
-    if (threadIdx.x == 0) tau[q] = -INFINITY;
-    return;
-  }
-  const uint32_t key = block_kth_largest_key(c, n, kth, s_hist, s_ctl);
-  if (threadIdx.x == 0) tau[q] = key_to_f32(key);
-}
+// ---------------------------------------------------------------------------
+// Result stage, three kernels (so that the exact re-rank spreads over the whole GPU):
+//   k_nns_select   (block per query)  sort the candidate list by coarse score, find the
+//                  k-th largest coarse score c_k and keep every candidate with
+//                  coarse >= c_k - 2*eps  (see the proof below)
+//   k_nns_rerank   (warp per kept row) exact float64 cosine from the float32 row, exactly
+//                  as the reference scores it (nns_matching.py:58 -> scipy correlation())
+//   k_nns_finalize (block per query)  sort by (similarity desc, row id desc), write top-k
+//
+// Sufficiency of the kept set.  |coarse_j - exact_j| <= eps for every pool row j.  The k
+// rows with the largest coarse scores have exact >= c_k - eps, so the exact k-th best
+// similarity s_k >= c_k - eps.  A row of the exact top-k has exact >= s_k, hence
+// coarse >= s_k - eps >= c_k - 2*eps: it is kept.  The candidate list itself holds every
+// row with coarse >= tau, and tau <= c_k - 2*eps by construction (k_nns_tau_select), so no
+// qualifying row is missing from the list.  The only ways to fail are capacity limits
+// (list overflow, kept set larger than kRerankMax); those raise flag 2 and the query is
+// re-run through the exact fp64 scan.
+// ---------------------------------------------------------------------------
+constexpr int kMaxSub = 2048;   // upper bound on sub-segments per query
+constexpr int kListMax = 8192;  // candidate lists up to this length are sorted in smem
 
-// ---------------------------------------------------------------------------
-// k_nns_select_rerank: one block per query.
-// ---------------------------------------------------------------------------
-struct RerankParams {
+struct SelectParams {
   const uint2* cand;
   const unsigned int* cnt;
-  int cand_cap;
-  const float* tau;  // nullptr: candidate list is the whole pool
-  const float* data;
-  const float* vv;
-  int dim;
+  int nsub;
+  const float* tau;   // nullptr: candidate list is the whole pool
   int n_rows;
-  const double* q64;  // already offset to the tile's first query
-  const double* uu;
   int k;
-  int window;
   float eps;
-  int32_t* out_idx;   // [nq, k], offset to the tile's first query
-  double* out_sims;
-  int* flags;         // [nq]: 0 fast path, 1 widened window, 2 needs exact re-run
+  int* sel_rows;      // [nq, kRerankMax]
+  int* sel_cnt;       // [nq]
+  int* flags;         // [nq]: 0 ok, 2 needs exact re-run
 };
 
-__device__ __forceinline__ bool ranks_before(double sa, int ia, double sb, int ib) {
-  // descending similarity, ties by descending row id (np.argsort(...)[::-1])
-  return (sa > sb) || (sa == sb && ia > ib);
-}
+constexpr size_t kSelSmemBytes =
+    sizeof(uint32_t) * kListMax + sizeof(int) * kListMax + sizeof(uint32_t) * (kMaxSub + 1);
 
 __global__ void __launch_bounds__(kSelThreads)
-k_nns_select_rerank(RerankParams p) {
+k_nns_select(SelectParams p) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(sel_smem);
+  int* s_row = reinterpret_cast<int*>(s_key + kListMax);
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_row + kListMax);  // [kMaxSub + 1]
   __shared__ uint32_t s_hist[256];
   __shared__ uint32_t s_ctl[2];
+  __shared__ int s_tot[2];
   __shared__ int s_count;
-  __shared__ double s_sim[kRerankMax];
-  __shared__ int s_idx[kRerankMax];
 
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int warp = tid >> 5;
-  const int nwarps = blockDim.x >> 5;
-  const uint2* c = p.cand + static_cast<size_t>(q) * p.cand_cap;
-  const unsigned int raw_cnt = p.cnt[q];
+  const int nsub = p.nsub;
+  const uint2* c = p.cand + static_cast<size_t>(q) * cand_slots(nsub);
   const int kk = min(p.k, p.n_rows);
-  int32_t* oi = p.out_idx + static_cast<size_t>(q) * p.k;
-  double* os = p.out_sims + static_cast<size_t>(q) * p.k;
+  int* out_rows = p.sel_rows + static_cast<size_t>(q) * kRerankMax;
 
-  for (int j = tid; j < p.k; j += blockDim.x) {
-    oi[j] = -1;
-    os[j] = nan("");
-  }
-  if (raw_cnt > static_cast<unsigned int>(p.cand_cap) || static_cast<int>(raw_cnt) < kk) {
-    if (tid == 0) p.flags[q] = 2;  // overflow (or inconsistent threshold): exact re-run
+  const int n_c = load_counts(p.cnt + static_cast<size_t>(q) * (nsub + 1), nsub, s_cnt, s_tot);
+  if (s_tot[1] != 0 || n_c < kk) {
+    if (tid == 0) { p.flags[q] = 2; p.sel_cnt[q] = 0; }  // dropped candidates: exact re-run
     return;
   }
-  const int n_c = static_cast<int>(raw_cnt);
-  const double tau_q = p.tau ? static_cast<double>(p.tau[q]) : -INFINITY;
-  const double* qv = p.q64 + static_cast<size_t>(q) * p.dim;
-  const double uuq = p.uu[q];
-
-  int flag = 0;
-  // threshold on the coarse score for this round; round 0 = k'-th largest
-  float thr;
-  {
-    const int want = min(p.window, n_c);
-    if (want >= n_c) {
-      thr = -INFINITY;
-    } else {
-      thr = key_to_f32(block_kth_largest_key(c, n_c, want, s_hist, s_ctl));
-    }
+  if (kk == 0) {
+    if (tid == 0) { p.flags[q] = 0; p.sel_cnt[q] = 0; }
+    return;
   }
-  for (int round = 0; round < 2; ++round) {
-    if (tid == 0) s_count = 0;
+  const double tau_q = p.tau ? static_cast<double>(p.tau[q]) : -INFINITY;
+  const bool in_smem = n_c <= kListMax;
+  float c_k;  // k-th largest coarse score
+  if (in_smem) {
+    // Compact the sparse sub-segments into shared memory.  Thread t owns sub-segments
+    // [4t, 4t+4) (+ a slice of the overflow region); offsets come from a block-wide
+    // exclusive scan of the counts so the copy loops are independent loads.
+    constexpr int kPerThread = (kMaxSub + kSelThreads - 1) / kSelThreads;  // 4
+    uint32_t my_cnt[kPerThread];
+    uint32_t my_sum = 0;
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+      const int sub = tid * kPerThread + j;
+      my_cnt[j] = sub < nsub ? s_cnt[sub] : 0u;
+      my_sum += my_cnt[j];
+    }
+    uint32_t incl = my_sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_hist[tid >> 5] = incl;  // warp totals (s_hist is free here)
     __syncthreads();
-    for (int i = tid; i < n_c; i += blockDim.x) {
-      const uint2 e = c[i];
-      if (__uint_as_float(e.x) >= thr) {
-        const int pos = atomicAdd(&s_count, 1);
-        if (pos < kRerankMax) s_idx[pos] = static_cast<int>(e.y);
+    if (tid < 32) {
+      const int nw = kSelThreads / 32;
+      uint32_t w = tid < nw ? s_hist[tid] : 0u;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += v;
+      }
+      s_hist[32 + tid] = w;  // inclusive scan of warp totals
+    }
+    __syncthreads();
+    uint32_t pos = incl - my_sum + ((tid >> 5) > 0 ? s_hist[32 + (tid >> 5) - 1] : 0u);
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+      const uint2* seg = c + static_cast<size_t>(tid * kPerThread + j) * kSegCap;
+      for (uint32_t e = 0; e < my_cnt[j]; ++e) {
+        const uint2 v = seg[e];
+        s_key[pos] = f32_to_key(__uint_as_float(v.x));
+        s_row[pos] = static_cast<int>(v.y);
+        ++pos;
+      }
+    }
+    {
+      const int n_ovf = static_cast<int>(s_cnt[nsub]);
+      const int base = n_c - n_ovf;  // overflow entries go last
+      const uint2* o = c + static_cast<size_t>(nsub) * kSegCap;
+      for (int i = tid; i < n_ovf; i += blockDim.x) {
+        const uint2 v = o[i];
+        s_key[base + i] = f32_to_key(__uint_as_float(v.x));
+        s_row[base + i] = static_cast<int>(v.y);
       }
     }
     __syncthreads();
-    const int count = s_count;
-    if (count > kRerankMax || count < kk) {
-      flag = 2;
-      break;
-    }
-    // exact float64 cosine of every selected row (reference: nns_matching.py:58 ->
-    // scipy correlation(): 1 - clip(1 - uv/sqrt(uu*vv), 0, 2))
-    for (int i = warp; i < count; i += nwarps) {
-      const int row = s_idx[i];
-      const float* x = p.data + static_cast<size_t>(row) * p.dim;
-      double acc = 0.0;
-      for (int d = lane; d < p.dim; d += 32) acc = fma(qv[d], static_cast<double>(x[d]), acc);
-      const double uv = warp_sum(acc);
-      if (lane == 0) {
-        double dist = 1.0 - uv / sqrt(uuq * static_cast<double>(p.vv[row]));
-        dist = fmin(fmax(dist, 0.0), 2.0);
-        double sim = 1.0 - dist;
-        if (!(sim == sim)) sim = -INFINITY;  // NaN (zero-norm row) ranks last
-        s_sim[i] = sim;
-      }
-    }
-    // pad to a power of two and bitonic-sort (descending, ties by descending row id)
     int P = 1;
-    while (P < count) P <<= 1;
-    for (int i = count + tid; i < P; i += blockDim.x) {
-      s_sim[i] = -INFINITY;
-      s_idx[i] = -1;
+    while (P < n_c) P <<= 1;
+    for (int i = n_c + tid; i < P; i += blockDim.x) {
+      s_key[i] = 0u;
+      s_row[i] = -1;
     }
     __syncthreads();
     for (int size = 2; size <= P; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int st = size >> 1; st > 0; st >>= 1) {
         for (int t = tid; t < (P >> 1); t += blockDim.x) {
-          const int lo = ((t / stride) * (stride << 1)) + (t % stride);
-          const int hi = lo + stride;
-          const bool desc_block = ((lo & size) == 0);
-          const double sa = s_sim[lo], sb = s_sim[hi];
-          const int ia = s_idx[lo], ib = s_idx[hi];
-          const bool a_first = ranks_before(sa, ia, sb, ib);
-          if (desc_block ? !a_first : a_first) {
-            s_sim[lo] = sb; s_sim[hi] = sa;
-            s_idx[lo] = ib; s_idx[hi] = ia;
+          const int lo = ((t & ~(st - 1)) << 1) | (t & (st - 1));  // st is a power of two
+          const int hi = lo + st;
+          const bool desc = ((lo & size) == 0);
+          const uint32_t ka = s_key[lo], kb = s_key[hi];
+          const int ra = s_row[lo], rb = s_row[hi];
+          const bool a_first = (ka > kb) || (ka == kb && ra > rb);
+          if (desc ? !a_first : a_first) {
+            s_key[lo] = kb; s_key[hi] = ka;
+            s_row[lo] = rb; s_row[hi] = ra;
           }
         }
         __syncthreads();
       }
     }
-    if (kk == 0) break;
-    const double s_k = s_sim[kk - 1];
-    // everything outside the re-ranked set has coarse score < bound
-    const double bound = (count == n_c) ? tau_q : static_cast<double>(thr);
-    if (bound == -INFINITY || bound + static_cast<double>(p.eps) <= s_k) break;  // proven
-    if (round == 1) {
-      flag = 2;
-      break;
+    c_k = key_to_f32(s_key[kk - 1]);
+  } else {
+    c_k = key_to_f32(block_kth_largest_key(c, s_cnt, nsub, kk, s_hist, s_ctl));
+  }
+  // keep {coarse >= c_k - 2 eps}; round the threshold DOWN to float (superset)
+  const double t2 = static_cast<double>(c_k) - 2.0 * static_cast<double>(p.eps);
+  float thr = static_cast<float>(t2);
+  if (static_cast<double>(thr) > t2) thr = nextafterf(thr, -INFINITY);
+  if (static_cast<double>(thr) < tau_q && n_c < p.n_rows) {
+    // rows below the candidate threshold could qualify (cannot happen when tau was chosen
+    // by k_nns_tau_select for this k; guards caller-supplied thresholds)
+    if (tid == 0) { p.flags[q] = 2; p.sel_cnt[q] = 0; }
+    return;
+  }
+  int count;
+  if (in_smem) {
+    const uint32_t thr_key = f32_to_key(thr);
+    int lo = 0, hi = n_c;  // first index with key < thr_key (list sorted descending)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_key[mid] >= thr_key) lo = mid + 1; else hi = mid;
     }
-    const double t2 = s_k - static_cast<double>(p.eps);
-    if (t2 < tau_q) {
-      flag = 2;  // rows below the candidate threshold could still qualify
-      break;
-    }
-    // round down to float so that {coarse >= thr} is a superset of {coarse >= t2}
-    float t2f = static_cast<float>(t2);
-    if (static_cast<double>(t2f) > t2) t2f = nextafterf(t2f, -INFINITY);
-    thr = t2f;
-    flag = 1;
+    count = lo;
+    if (count <= kRerankMax)
+      for (int i = tid; i < count; i += blockDim.x) out_rows[i] = s_row[i];
+  } else {
+    if (tid == 0) s_count = 0;
     __syncthreads();
+    for_each_candidate(c, s_cnt, nsub, [&](bool valid, uint2 e) {
+      if (valid && __uint_as_float(e.x) >= thr) {
+        const int pos = atomicAdd(&s_count, 1);
+        if (pos < kRerankMax) out_rows[pos] = static_cast<int>(e.y);
+      }
+    });
+    __syncthreads();
+    count = s_count;
   }
-  if (flag != 2) {
-    for (int j = tid; j < kk; j += blockDim.x) {
-      oi[j] = s_idx[j];
-      os[j] = s_sim[j];
+  if (tid == 0) {
+    const bool bad = count > kRerankMax || count < kk;
+    p.flags[q] = bad ? 2 : 0;
+    p.sel_cnt[q] = bad ? 0 : count;
+  }
+}
+
+// One warp per (query, kept row).  grid.x covers kRerankMax rows, grid.y = queries.
+__global__ void __launch_bounds__(256)
+k_nns_rerank(const int* __restrict__ sel_rows, const int* __restrict__ sel_cnt,
+             const float* __restrict__ data, const float* __restrict__ vv, int dim,
+             const double* __restrict__ q64, const double* __restrict__ uu,
+             double* __restrict__ sel_sims) {
+  const int q = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= sel_cnt[q]) return;
+  const int row = sel_rows[static_cast<size_t>(q) * kRerankMax + i];
+  const float* x = data + static_cast<size_t>(row) * dim;
+  const double* qv = q64 + static_cast<size_t>(q) * dim;
+  double acc = 0.0;
+  for (int d = lane; d < dim; d += 32) acc = fma(qv[d], static_cast<double>(x[d]), acc);
+  const double uv = warp_sum(acc);
+  if (lane == 0) {
+    double dist = 1.0 - uv / sqrt(uu[q] * static_cast<double>(vv[row]));
+    dist = fmin(fmax(dist, 0.0), 2.0);
+    double sim = 1.0 - dist;
+    if (!(sim == sim)) sim = -INFINITY;  // NaN (zero-norm row) ranks last
+    sel_sims[static_cast<size_t>(q) * kRerankMax + i] = sim;
+  }
+}
+
+__device__ __forceinline__ bool ranks_before(double sa, int ia, double sb, int ib) {
+  // descending similarity, ties by descending row id
+  return (sa > sb) || (sa == sb && ia > ib);
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+k_nns_finalize(const int* __restrict__ sel_rows, const int* __restrict__ sel_cnt,
+               const double* __restrict__ sel_sims, const int* __restrict__ flags, int n_rows,
+               int k, int32_t* __restrict__ out_idx, double* __restrict__ out_sims) {
+  __shared__ double s_sim[kRerankMax];
+  __shared__ int s_idx[kRerankMax];
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  int32_t* oi = out_idx + static_cast<size_t>(q) * k;
+  double* os = out_sims + static_cast<size_t>(q) * k;
+  const int kk = min(k, n_rows);
+  const int count = sel_cnt[q];
+  if (flags[q] != 0 || count < kk) {
+    for (int j = tid; j < k; j += blockDim.x) { oi[j] = -1; os[j] = nan(""); }
+    return;
+  }
+  int P = 1;
+  while (P < count) P <<= 1;
+  for (int i = tid; i < P; i += blockDim.x) {
+    const bool v = i < count;
+    s_sim[i] = v ? sel_sims[static_cast<size_t>(q) * kRerankMax + i] : -INFINITY;
+    s_idx[i] = v ? sel_rows[static_cast<size_t>(q) * kRerankMax + i] : -1;
+  }
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int st = size >> 1; st > 0; st >>= 1) {
+      for (int t = tid; t < (P >> 1); t += blockDim.x) {
+        const int lo = ((t & ~(st - 1)) << 1) | (t & (st - 1));  // st is a power of two
+        const int hi = lo + st;
+        const bool desc_block = ((lo & size) == 0);
+        const double sa = s_sim[lo], sb = s_sim[hi];
+        const int ia = s_idx[lo], ib = s_idx[hi];
+        const bool a_first = ranks_before(sa, ia, sb, ib);
+        if (desc_block ? !a_first : a_first) {
+          s_sim[lo] = sb; s_sim[hi] = sa;
+          s_idx[lo] = ib; s_idx[hi] = ia;
+        }
+      }
+      __syncthreads();
     }
   }
-  if (tid == 0) p.flags[q] = flag;
+  for (int j = tid; j < k; j += blockDim.x) {
+    oi[j] = j < kk ? s_idx[j] : -1;
+    os[j] = j < kk ? s_sim[j] : nan("");
+  }
 }
 
 __global__ void k_fill_empty(int32_t* idx, double* sims, size_t n) {
@@ -397,11 +602,15 @@ struct cslam_nns {
   __half* d_qh = nullptr;
   TensorMapBlob tmap_q;
   float* d_tau = nullptr;         // [kCoarseBM]
-  unsigned int* d_cnt = nullptr;  // [kCoarseBM]
   int* d_flags = nullptr;         // [kCoarseBM]
+  int* d_sel_rows = nullptr;      // [kCoarseBM, kRerankMax] rows kept for the exact re-rank
+  int* d_sel_cnt = nullptr;       // [kCoarseBM]
+  double* d_sel_sims = nullptr;   // [kCoarseBM, kRerankMax]
   int* h_flags = nullptr;         // pinned [kCoarseBM]
-  DevBuf<uint2> cand;
-  int cand_cap = 0;
+  DevBuf<uint2> cand;             // [kCoarseBM, cand_slots(nsub)]
+  unsigned int* d_cnt = nullptr;  // [kCoarseBM, nsub + 1]
+  int nsub = 0;
+  DevBuf<uint32_t> smax;          // [kCoarseBM, sample chunks] sampled chunk maxima (keys)
   int out_cap_q = 0, out_cap_k = 0;
   int32_t* d_out_idx = nullptr;
   double* d_out_sims = nullptr;
@@ -412,8 +621,7 @@ struct cslam_nns {
   size_t h_out_elems = 0;
 
   int mode = 0;
-  int window = 128;
-  int sample_rows = 16384;
+  int sample_rows = 32768;
 
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
   int last_coarse_launches = 0;
@@ -501,9 +709,11 @@ int nns_reserve_queries(cslam_nns* h, int nq, int k) {
   }
   if (!h->d_tau) {
     CSLAM_TRY(dev_alloc(&h->d_tau, kCoarseBM));
-    CSLAM_TRY(dev_alloc(&h->d_cnt, kCoarseBM));
     CSLAM_TRY(dev_alloc(&h->d_flags, kCoarseBM));
-    CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), kCoarseBM * sizeof(int)));
+    CSLAM_TRY(dev_alloc(&h->d_sel_rows, static_cast<size_t>(kCoarseBM) * kRerankMax));
+    CSLAM_TRY(dev_alloc(&h->d_sel_cnt, kCoarseBM));
+    CSLAM_TRY(dev_alloc(&h->d_sel_sims, static_cast<size_t>(kCoarseBM) * kRerankMax));
+    CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), 2 * kCoarseBM * sizeof(int)));
   }
   (void)k;
   return CSLAM_OK;
@@ -516,15 +726,24 @@ int nns_run_tile(cslam_nns* h, int q0, int nqt, int k, bool exact, int32_t* out_
                  double* out_sims, cudaStream_t s, bool time_it) {
   const int n_rows = static_cast<int>(h->n);
   const int num_tiles = (n_rows + kCoarseBN - 1) / kCoarseBN;
-  const int window = std::min(kRerankMax / 2, std::max(h->window, 2 * k));
-  const bool exhaustive = n_rows <= 2 * h->sample_rows;
-  const int cap_needed =
-      exhaustive ? std::max(num_tiles * kCoarseBN, 256) : std::max(2 * h->sample_rows, 32768);
-  if (cap_needed > h->cand_cap) {
+  const bool exhaustive = n_rows <= h->sample_rows;
+  const int sample_tiles = h->sample_rows / kCoarseBN;
+  // dump passes (tau = -inf, small pools) give every CTA exactly one tile, i.e. each
+  // sub-segment exactly kSegCap entries; the filtered pass runs one CTA per SM.
+  const int max_grid = std::max(h->num_sms, sample_tiles);
+  const int nsub_needed = 2 * max_grid;
+  if (nsub_needed > h->nsub) {
+    CSLAM_REQUIRE(nsub_needed <= kMaxSub, "nns: %d sub-segments exceed the limit %d", nsub_needed,
+                  kMaxSub);
     CSLAM_CUDA(cudaStreamSynchronize(s));
-    CSLAM_TRY(h->cand.reserve(static_cast<size_t>(cap_needed) * kCoarseBM));
-    h->cand_cap = cap_needed;
+    CSLAM_TRY(h->cand.reserve(cand_slots(nsub_needed) * kCoarseBM));
+    dev_free(h->d_cnt);
+    CSLAM_TRY(dev_alloc(&h->d_cnt, static_cast<size_t>(kCoarseBM) * (nsub_needed + 1)));
+    h->nsub = nsub_needed;
   }
+  const int smax_stride = sample_tiles * (kCoarseBN / kChunk);
+  CSLAM_REQUIRE(smax_stride <= kTauMax, "nns: sample_rows too large");
+  CSLAM_TRY(h->smax.reserve(static_cast<size_t>(kCoarseBM) * smax_stride));
   // fp16 rounding of both unit-norm operands (2 * 2^-11), fp32 accumulation over
   // dim_pad terms, fp16 subnormal flush; exact scan only rounds the score to fp32.
   const float eps = exact ? 1.0e-6f
@@ -532,26 +751,38 @@ int nns_run_tile(cslam_nns* h, int q0, int nqt, int k, bool exact, int32_t* out_
                              4.0e-6f);
 
   CoarseParams cp;
+  cp.mode = 0;
   cp.num_kb = h->dim_pad / 64;
   cp.n_rows = n_rows;
   cp.nq = nqt;
   cp.q_row0 = q0;
   cp.cnt = h->d_cnt;
   cp.cand = h->cand.p;
-  cp.cand_cap = h->cand_cap;
+  cp.nsub = h->nsub;
+  cp.smax = h->smax.p;
+  cp.smax_stride = smax_stride;
 
-  auto launch_coarse = [&](int tiles, int stride, const float* tau, bool timed) -> int {
+  auto launch_coarse = [&](int mode, int tiles, int stride, const float* tau, bool timed) -> int {
+    cp.mode = mode;
     cp.num_tiles = tiles;
     cp.tile_stride = stride;
     cp.tau = tau;
-    CSLAM_CUDA(cudaMemsetAsync(h->d_cnt, 0, kCoarseBM * sizeof(unsigned int), s));
+    if (mode == 0) {
+      CSLAM_CUDA(cudaMemsetAsync(
+          h->d_cnt, 0, static_cast<size_t>(kCoarseBM) * (h->nsub + 1) * sizeof(unsigned int), s));
+    } else if (exact) {
+      CSLAM_CUDA(cudaMemsetAsync(h->smax.p, 0,
+                                 static_cast<size_t>(kCoarseBM) * smax_stride * sizeof(uint32_t),
+                                 s));
+    }
     if (timed) CSLAM_CUDA(cudaEventRecord(h->ev_c0, s));
+    // unfiltered passes: one tile per CTA; filtered full pass: persistent, one CTA per SM
+    const int grid = tau == nullptr ? std::min(tiles, max_grid) : std::min(tiles, h->num_sms);
     if (exact) {
-      const int grid = std::min(tiles, h->num_sms * 4);
       k_nns_coarse_exact<<<grid, 256, 0, s>>>(h->d_data, h->d_vv, h->dim, h->d_q64, h->d_uu, cp);
       CSLAM_LAUNCH_CHECK();
     } else {
-      CSLAM_TRY(launch_coarse_tc(&h->tmap_q, &h->tmap_p, cp, h->num_sms, s));
+      CSLAM_TRY(launch_coarse_tc(&h->tmap_q, &h->tmap_p, cp, grid, s));
     }
     if (timed) CSLAM_CUDA(cudaEventRecord(h->ev_c1, s));
     h->last_coarse_launches++;
@@ -560,36 +791,46 @@ int nns_run_tile(cslam_nns* h, int q0, int nqt, int k, bool exact, int32_t* out_
 
   const float* tau = nullptr;
   if (exhaustive) {
-    CSLAM_TRY(launch_coarse(num_tiles, 1, nullptr, time_it));
+    CSLAM_TRY(launch_coarse(0, num_tiles, 1, nullptr, time_it));
   } else {
-    const int sample_tiles = h->sample_rows / kCoarseBN;
-    const int stride = std::max(1, (num_tiles - 1) / sample_tiles);
-    CSLAM_TRY(launch_coarse(sample_tiles, stride, nullptr, false));
-    k_nns_tau_select<<<nqt, kSelThreads, 0, s>>>(h->cand.p, h->d_cnt, h->cand_cap, window,
-                                                  h->d_tau);
+    // sample pass over `sample_tiles` full tiles spread evenly over the pool
+    const int full_tiles = n_rows / kCoarseBN;
+    const int stride = std::max(1, full_tiles / sample_tiles);
+    CSLAM_TRY(launch_coarse(1, sample_tiles, stride, nullptr, false));
+    // tau = (k-th largest sampled chunk maximum) - 2 eps.  The sampled maxima are distinct
+    // pool rows, so the pool's k-th largest coarse score c_k >= that value and therefore
+    // tau <= c_k - 2 eps: every row k_nns_select needs is in the candidate list.
+    k_nns_tau_select<<<nqt, kTauThreads, 0, s>>>(h->smax.p, smax_stride, smax_stride,
+                                                  std::min(k, n_rows), 2.0f * eps, h->d_tau);
     CSLAM_LAUNCH_CHECK();
     tau = h->d_tau;
-    CSLAM_TRY(launch_coarse(num_tiles, 1, tau, time_it));
+    CSLAM_TRY(launch_coarse(0, num_tiles, 1, tau, time_it));
   }
 
-  RerankParams rp;
-  rp.cand = h->cand.p;
-  rp.cnt = h->d_cnt;
-  rp.cand_cap = h->cand_cap;
-  rp.tau = tau;
-  rp.data = h->d_data;
-  rp.vv = h->d_vv;
-  rp.dim = h->dim;
-  rp.n_rows = n_rows;
-  rp.q64 = h->d_q64 + static_cast<size_t>(q0) * h->dim;
-  rp.uu = h->d_uu + q0;
-  rp.k = k;
-  rp.window = window;
-  rp.eps = eps;
-  rp.out_idx = out_idx;
-  rp.out_sims = out_sims;
-  rp.flags = h->d_flags;
-  k_nns_select_rerank<<<nqt, kSelThreads, 0, s>>>(rp);
+  SelectParams sp;
+  sp.cand = h->cand.p;
+  sp.cnt = h->d_cnt;
+  sp.nsub = h->nsub;
+  sp.tau = tau;
+  sp.n_rows = n_rows;
+  sp.k = k;
+  sp.eps = eps;
+  sp.sel_rows = h->d_sel_rows;
+  sp.sel_cnt = h->d_sel_cnt;
+  sp.flags = h->d_flags;
+  CSLAM_CUDA(cudaFuncSetAttribute(k_nns_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kSelSmemBytes)));
+  k_nns_select<<<nqt, kSelThreads, kSelSmemBytes, s>>>(sp);
+  CSLAM_LAUNCH_CHECK();
+  // one warp per kept row; blocks beyond a query's kept count exit immediately
+  const int rr_rows = exhaustive ? std::min(kRerankMax, std::max(n_rows, 1)) : kRerankMax;
+  dim3 rgrid((rr_rows + 7) / 8, nqt);
+  k_nns_rerank<<<rgrid, 256, 0, s>>>(h->d_sel_rows, h->d_sel_cnt, h->d_data, h->d_vv, h->dim,
+                                     h->d_q64 + static_cast<size_t>(q0) * h->dim, h->d_uu + q0,
+                                     h->d_sel_sims);
+  CSLAM_LAUNCH_CHECK();
+  k_nns_finalize<<<nqt, kSelThreads, 0, s>>>(h->d_sel_rows, h->d_sel_cnt, h->d_sel_sims,
+                                             h->d_flags, n_rows, k, out_idx, out_sims);
   CSLAM_LAUNCH_CHECK();
   return CSLAM_OK;
 }
@@ -647,12 +888,14 @@ int nns_search_impl(cslam_nns* h, const void* d_queries, int dtype, int nq, int 
     // escalation check: read the per-query flags
     CSLAM_CUDA(cudaMemcpyAsync(h->h_flags, h->d_flags, nqt * sizeof(int), cudaMemcpyDeviceToHost,
                                s));
+    CSLAM_CUDA(cudaMemcpyAsync(h->h_flags + kCoarseBM, h->d_sel_cnt, nqt * sizeof(int),
+                               cudaMemcpyDeviceToHost, s));
     CSLAM_CUDA(cudaStreamSynchronize(s));
     std::vector<int> redo;
     for (int i = 0; i < nqt; ++i) {
       if (h->h_flags[i] == 2) redo.push_back(i);
-      else if (h->h_flags[i] == 1) info[1]++;
       else info[0]++;
+      info[1] += h->h_flags[kCoarseBM + i];
     }
     for (int i : redo) {
       if (exact) {
@@ -748,8 +991,12 @@ int cslam_nns_destroy(cslam_nns_t* h) {
   dev_free(h->d_tau);
   dev_free(h->d_cnt);
   dev_free(h->d_flags);
+  dev_free(h->d_sel_rows);
+  dev_free(h->d_sel_cnt);
+  dev_free(h->d_sel_sims);
   if (h->h_flags) cudaFreeHost(h->h_flags);
   h->cand.release();
+  h->smax.release();
   dev_free(h->d_out_idx);
   dev_free(h->d_out_sims);
   if (h->h_q) cudaFreeHost(h->h_q);
@@ -878,14 +1125,12 @@ int cslam_nns_set_mode(cslam_nns_t* h, int mode) {
   return CSLAM_OK;
 }
 
-int cslam_nns_set_params(cslam_nns_t* h, int rerank_window, int sample_rows) {
-  CSLAM_REQUIRE(h, "nns_set_params: NULL handle");
-  CSLAM_REQUIRE(rerank_window >= 1 && rerank_window <= kRerankMax / 2,
-                "nns_set_params: rerank_window must be in [1,%d]", kRerankMax / 2);
-  CSLAM_REQUIRE(sample_rows >= kCoarseBN && sample_rows % kCoarseBN == 0 && sample_rows <= 65536,
-                "nns_set_params: sample_rows must be a multiple of %d in [%d, 65536]", kCoarseBN,
-                kCoarseBN);
-  h->window = rerank_window;
+int cslam_nns_set_sample_rows(cslam_nns_t* h, int sample_rows) {
+  CSLAM_REQUIRE(h, "nns_set_sample_rows: NULL handle");
+  CSLAM_REQUIRE(sample_rows >= kCoarseBN && sample_rows % kCoarseBN == 0 &&
+                    sample_rows / kChunk <= kTauMax,
+                "nns_set_sample_rows: must be a multiple of %d in [%d, %d]", kCoarseBN, kCoarseBN,
+                kTauMax * kChunk);
   h->sample_rows = sample_rows;
   return CSLAM_OK;
 }

@@ -15,12 +15,14 @@
 //   * Ph  [cap,   dim_pad] fp16, rows L2-normalised, zero padded   (B operand, K-major)
 //   * TMEM: 2 accumulator buffers x 256 fp32 columns = all 512 columns; TMEM lane m
 //     holds query m, column j holds pool row (tile_row0 + j).
-// Warp roles (256 threads, 1 CTA / SM, persistent over pool tiles):
+// Warp roles (384 threads, 1 CTA / SM, persistent over pool tiles):
 //   warp 0    TMA producer (one lane)       warp 1  MMA issuer (one lane)
 //   warp 2    TMEM allocator                warp 3  idle
-//   warps 4-7 epilogue: thread = query; tcgen05.ld 32 columns at a time, compare
-//             with the query's threshold tau, append survivors (score, row) to the
-//             query's candidate list in global memory.
+//   warps 4-11 epilogue: thread = (query, column half); tcgen05.ld 32 columns at a
+//             time, compare with the query's threshold tau, append survivors
+//             (score, row) to the thread's private sub-segment of the query's candidate
+//             list in global memory (no atomics).  In sample mode only the maximum of
+//             each 32-row chunk is stored (input of the threshold selection).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -38,7 +40,7 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
@@ -186,7 +188,7 @@ k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 128);
+      mbar_init(tempty_bar(b), 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -249,13 +251,26 @@ k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
-    const int q = ew * 32 + lane;
+    // 8 epilogue warps: warp % 4 selects the TMEM lane quarter (hardware rule), the
+    // upper/lower group of four warps takes column half 0/1 of every tile.
+    const int ew = warp - 4;
+    const int quarter = ew & 3;
+    const int half = ew >> 2;
+    const int q = quarter * 32 + lane;
     const bool q_valid = q < prm.nq;
-    const float tau = (q_valid && prm.tau != nullptr) ? prm.tau[q] : -INFINITY;
-    unsigned int* my_cnt = prm.cnt + (q_valid ? q : 0);
-    uint2* my_cand = prm.cand + static_cast<size_t>(q_valid ? q : 0) * prm.cand_cap;
-    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    const int qs = q_valid ? q : 0;
+    // invalid (padding) queries never hit: +inf threshold
+    const float tau = !q_valid ? INFINITY : (prm.tau != nullptr ? prm.tau[q] : -INFINITY);
+    const size_t slots = cand_slots(prm.nsub);
+    uint2* my_seg = prm.cand + static_cast<size_t>(qs) * slots +
+                    static_cast<size_t>(blockIdx.x * 2 + half) * kSegCap;
+    uint2* my_ovf = prm.cand + static_cast<size_t>(qs) * slots +
+                    static_cast<size_t>(prm.nsub) * kSegCap;
+    unsigned int* my_cnt = prm.cnt + static_cast<size_t>(qs) * (prm.nsub + 1);
+    uint32_t* my_smax = prm.smax + static_cast<size_t>(qs) * prm.smax_stride;
+    unsigned int my_count = 0;
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    constexpr int HALF_N = BN / 2;
     int it = 0;
     for (int tile = first_tile; tile < prm.num_tiles; tile += tile_step, ++it) {
       const int buf = it & 1;
@@ -263,23 +278,35 @@ k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
       mbar_wait(tfull_bar(buf), (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = half * HALF_N; c < (half + 1) * HALF_N; c += kChunk) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(lane_taddr + static_cast<uint32_t>(buf * BN + c), r);
         tmem_ld_wait();
-        if (q_valid) {
-          float m = __uint_as_float(r[0]);
+        float m[8];
 #pragma unroll
-          for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
-          if (m >= tau) {
+        for (int j = 0; j < 8; ++j)
+          m[j] = fmaxf(fmaxf(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])),
+                       fmaxf(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+        const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])),
+                               fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+        if (prm.mode == 1) {
+          if (q_valid) my_smax[tile * (BN / kChunk) + c / kChunk] = f32_to_key(mx);
+        } else if (__any_sync(0xffffffffu, mx >= tau)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float s = __uint_as_float(r[j]);
-              const int row = row0 + c + j;
-              if (s >= tau && row < prm.n_rows) {
-                const unsigned int pos = atomicAdd(my_cnt, 1u);
-                if (pos < static_cast<unsigned int>(prm.cand_cap))
-                  my_cand[pos] = make_uint2(__float_as_uint(s), static_cast<uint32_t>(row));
+          for (int j = 0; j < 32; ++j) {
+            const float s = __uint_as_float(r[j]);
+            const int row = row0 + c + j;
+            const bool hit = (s >= tau) && (row < prm.n_rows);
+            if (__any_sync(0xffffffffu, hit)) {
+              if (hit) {
+                const uint2 e = make_uint2(__float_as_uint(s), static_cast<uint32_t>(row));
+                if (my_count < static_cast<unsigned int>(kSegCap)) {
+                  my_seg[my_count] = e;
+                } else {
+                  const unsigned int pos = atomicAdd(my_cnt + prm.nsub, 1u);
+                  if (pos < static_cast<unsigned int>(kOvfCap)) my_ovf[pos] = e;
+                }
+                ++my_count;
               }
             }
           }
@@ -288,6 +315,8 @@ k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
     }
+    if (q_valid && prm.mode == 0)
+      my_cnt[blockIdx.x * 2 + half] = min(my_count, static_cast<unsigned int>(kSegCap));
   }
 
   tc_fence_before();
@@ -345,16 +374,11 @@ int make_fp16_rowmajor_tmap(void* out_map, const void* base, int64_t rows, int c
   return CSLAM_OK;
 }
 
-int launch_coarse_tc(const void* tmap_q, const void* tmap_p, const CoarseParams& prm,
-                     int num_sms, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CSLAM_CUDA(cudaFuncSetAttribute(k_nns_coarse_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    SMEM_BYTES));
-    attr_set = true;
-  }
-  if (prm.num_tiles <= 0) return CSLAM_OK;
-  const int grid = prm.num_tiles < num_sms ? prm.num_tiles : num_sms;
+int launch_coarse_tc(const void* tmap_q, const void* tmap_p, const CoarseParams& prm, int grid,
+                     cudaStream_t stream) {
+  CSLAM_CUDA(cudaFuncSetAttribute(k_nns_coarse_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  SMEM_BYTES));
+  if (prm.num_tiles <= 0 || grid <= 0) return CSLAM_OK;
   k_nns_coarse_tc<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(
       *reinterpret_cast<const CUtensorMap*>(tmap_q), *reinterpret_cast<const CUtensorMap*>(tmap_p),
       prm);

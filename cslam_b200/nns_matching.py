@@ -158,10 +158,62 @@ class NearestNeighborsMatching(object):
         items, similarities = self.search(query, 1)
         return items[0], similarities[0]
 
+    # -- device-resident extensions (torch CUDA tensors; no host copies) ---------
+    def add_items_device(self, rows, items=None):
+        """Append a float32 CUDA tensor [m, dim]; items default to the row ids."""
+        import torch
+        assert rows.is_cuda and rows.dtype == torch.float32 and rows.dim() == 2
+        rows = rows.contiguous()
+        if self._h is None:
+            self._device = rows.device.index
+            self._create(rows.shape[1])
+        m = rows.shape[0]
+        if items is None:
+            self.items.update((self.n + j, self.n + j) for j in range(m))
+        else:
+            self.items.update((self.n + j, it) for j, it in enumerate(items))
+        stream = torch.cuda.current_stream(rows.device).cuda_stream
+        _lib.check(_lib.load().cslam_nns_add_device(self._h, _lib.ptr(rows), m,
+                                                    ctypes.c_void_p(stream)))
+        self.n += m
+        while self.n > self._capacity:
+            self._capacity = 1000 if self._capacity == 0 else 2 * self._capacity
+
+    def search_batch_device(self, queries, k, out=None):
+        """queries: CUDA tensor [nq, dim] float32/float64 -> (idx int32, sims float64)
+        CUDA tensors [nq, min(k, n)], computed on torch's current stream."""
+        import torch
+        assert queries.is_cuda and queries.dim() == 2
+        queries = queries.contiguous()
+        dt = _lib.DTYPE_F32 if queries.dtype == torch.float32 else _lib.DTYPE_F64
+        if dt == _lib.DTYPE_F64 and queries.dtype != torch.float64:
+            queries = queries.double()
+        nq = queries.shape[0]
+        kk = min(int(k), self.n)
+        if out is None:
+            idx = torch.empty((nq, kk), dtype=torch.int32, device=queries.device)
+            sims = torch.empty((nq, kk), dtype=torch.float64, device=queries.device)
+        else:
+            idx, sims = out
+        info = np.zeros(4, dtype=np.int64)
+        stream = torch.cuda.current_stream(queries.device).cuda_stream
+        _lib.check(_lib.load().cslam_nns_search_device(self._h, _lib.ptr(queries), dt, nq, kk,
+                                                       _lib.ptr(idx), _lib.ptr(sims),
+                                                       ctypes.c_void_p(stream), _lib.ptr(info)))
+        self.last_info = info
+        return idx, sims
+
+    def last_timing(self):
+        """(coarse_ms, coarse_launches, total_ms) of the last search (CUDA events)."""
+        c, n, t = ctypes.c_float(), ctypes.c_int(), ctypes.c_float()
+        _lib.check(_lib.load().cslam_nns_last_timing(self._h, ctypes.byref(c), ctypes.byref(n),
+                                                     ctypes.byref(t)))
+        return c.value, n.value, t.value
+
     # -- tuning hooks ----------------------------------------------------------
     def set_mode(self, mode):
         """0 = tensor-core coarse pass + exact re-rank (default); 1 = exact fp64 scan."""
         _lib.check(_lib.load().cslam_nns_set_mode(self._h, int(mode)))
 
-    def set_params(self, rerank_window=128, sample_rows=16384):
-        _lib.check(_lib.load().cslam_nns_set_params(self._h, int(rerank_window), int(sample_rows)))
+    def set_sample_rows(self, sample_rows=32768):
+        _lib.check(_lib.load().cslam_nns_set_sample_rows(self._h, int(sample_rows)))

@@ -81,12 +81,13 @@ int cslam_nns_read_rows(cslam_nns_t* h, int64_t start, int64_t count, float* out
 /* Top-k search for `nq` queries ([nq, dim], F32 or F64).  (search, :42-61)
  * out_idx  [nq, k] int32 row ids, best first; unused slots = -1
  * out_sims [nq, k] float64 similarities; unused slots = NaN
- * Each query returns min(k, size) matches.  Ties in similarity are ordered
- * by DESCENDING row id (what np.argsort(sim)[::-1] yields for equal keys,
- * nns_matching.py:60).  1 <= k <= 1024.
+ * Each query returns min(k, size) matches.  Exactly equal similarities are
+ * ordered by DESCENDING row id (the reference's np.argsort(sim)[::-1],
+ * nns_matching.py:60, leaves the order of equal keys unspecified).
+ * 1 <= k <= 1024.
  * out_info (optional, may be NULL) [4] int64:
  *   [0] queries answered by the tensor-core coarse pass + exact re-rank
- *   [1] queries that needed a widened re-rank window
+ *   [1] total pool rows that were exactly re-ranked (all queries)
  *   [2] queries re-run through the exact fp64 scan kernel
  *   [3] kernels launched by this call                                   */
 int cslam_nns_search_host(cslam_nns_t* h, const void* queries, int dtype, int nq, int k,
@@ -100,9 +101,9 @@ int cslam_nns_search_device(cslam_nns_t* h, const void* d_queries, int dtype, in
  * escalating to the exact scan only when the error-bound check fails),
  * 1 = force the exact fp64 scan kernel (validation path, still GPU). */
 int cslam_nns_set_mode(cslam_nns_t* h, int mode);
-/* re-rank window k' (default 128), sample rows for the threshold pass
- * (default 16384; pools <= 2*sample are scored exhaustively). */
-int cslam_nns_set_params(cslam_nns_t* h, int rerank_window, int sample_rows);
+/* Rows sampled by the threshold pass (default 32768, multiple of 256); pools of at
+ * most this many rows are scored exhaustively without a threshold. */
+int cslam_nns_set_sample_rows(cslam_nns_t* h, int sample_rows);
 /* Time (ms, CUDA events on the handle's stream) of the coarse kernel launches
  * of the last search call and how many there were. */
 int cslam_nns_last_timing(cslam_nns_t* h, float* coarse_ms, int* coarse_launches,

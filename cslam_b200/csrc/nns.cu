@@ -162,6 +162,60 @@ k_nns_coarse_exact(const float* __restrict__ data, const float* __restrict__ vv,
 }
 
 // ---------------------------------------------------------------------------
+// Block-wide radix select over keys held in shared memory: value of the `kth` largest
+// (1-based) of s_key[0..n).  4 passes of 8 bits, MSB first.  s_hist: 256 counters,
+// s_ctl: 2 words.  All threads of the block must call it.
+// ---------------------------------------------------------------------------
+__device__ uint32_t block_kth_largest_smem(const uint32_t* s_key, int n, int kth,
+                                           uint32_t* s_hist, uint32_t* s_ctl) {
+  uint32_t prefix = 0, mask = 0;
+  int remaining = kth;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t key = s_key[i];
+      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // lane l owns digits [8l, 8l+8); suffix sums locate the digit holding rank `remaining`
+      const int l = threadIdx.x;
+      uint32_t h[8];
+      uint32_t tot = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { h[j] = s_hist[8 * l + j]; tot += h[j]; }
+      // above = number of keys in digits owned by higher lanes
+      uint32_t incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_down_sync(0xffffffffu, incl, o);
+        if (l + o < 32) incl += v;
+      }
+      const uint32_t above = incl - tot;
+      const bool mine = above < static_cast<uint32_t>(remaining) &&
+                        static_cast<uint32_t>(remaining) <= above + tot;
+      if (mine) {
+        uint32_t acc = above;
+        int d = 7;
+        for (; d > 0; --d) {
+          if (acc + h[d] >= static_cast<uint32_t>(remaining)) break;
+          acc += h[d];
+        }
+        s_ctl[0] = static_cast<uint32_t>(8 * l + d);
+        s_ctl[1] = static_cast<uint32_t>(remaining) - acc;
+      }
+    }
+    __syncthreads();
+    prefix |= s_ctl[0] << shift;
+    mask |= 255u << shift;
+    remaining = static_cast<int>(s_ctl[1]);
+    __syncthreads();
+  }
+  return prefix;
+}
+
+// ---------------------------------------------------------------------------
 // k_nns_tau_select: tau[q] = (the `kth` largest of the sampled chunk maxima) - slack.
 // Every chunk maximum is a distinct pool row, so at least `kth` pool rows score
 // >= that value: the pool's kth largest coarse score is >= tau[q] + slack.
@@ -173,28 +227,18 @@ __global__ void __launch_bounds__(kTauThreads)
 k_nns_tau_select(const uint32_t* __restrict__ smax, int stride, int nchunks, int kth,
                  float slack, float* __restrict__ tau) {
   __shared__ uint32_t s[kTauMax];
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_ctl[2];
   const int q = blockIdx.x;
-  int P = 1;
-  while (P < nchunks) P <<= 1;
-  for (int i = threadIdx.x; i < P; i += blockDim.x)
-    s[i] = i < nchunks ? smax[static_cast<size_t>(q) * stride + i] : 0u;
+  for (int i = threadIdx.x; i < nchunks; i += blockDim.x)
+    s[i] = smax[static_cast<size_t>(q) * stride + i];
   __syncthreads();
-  for (int size = 2; size <= P; size <<= 1) {
-    for (int st = size >> 1; st > 0; st >>= 1) {
-      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
-        const int lo = ((t & ~(st - 1)) << 1) | (t & (st - 1));  // st is a power of two
-        const int hi = lo + st;
-        const bool desc = ((lo & size) == 0);
-        const uint32_t a = s[lo], b = s[hi];
-        if (desc ? (a < b) : (a > b)) { s[lo] = b; s[hi] = a; }
-      }
-      __syncthreads();
-    }
-  }
+  uint32_t kth_key = 0u;
+  if (kth <= nchunks) kth_key = block_kth_largest_smem(s, nchunks, kth, s_hist, s_ctl);
   if (threadIdx.x == 0) {
     // round toward -inf: a threshold that is too low only costs candidates
     float t = -INFINITY;
-    if (kth <= nchunks) t = __fsub_rd(key_to_f32(s[kth - 1]), slack);
+    if (kth <= nchunks) t = __fsub_rd(key_to_f32(kth_key), slack);
     tau[q] = t;
   }
 }
@@ -415,31 +459,7 @@ k_nns_select(SelectParams p) {
       }
     }
     __syncthreads();
-    int P = 1;
-    while (P < n_c) P <<= 1;
-    for (int i = n_c + tid; i < P; i += blockDim.x) {
-      s_key[i] = 0u;
-      s_row[i] = -1;
-    }
-    __syncthreads();
-    for (int size = 2; size <= P; size <<= 1) {
-      for (int st = size >> 1; st > 0; st >>= 1) {
-        for (int t = tid; t < (P >> 1); t += blockDim.x) {
-          const int lo = ((t & ~(st - 1)) << 1) | (t & (st - 1));  // st is a power of two
-          const int hi = lo + st;
-          const bool desc = ((lo & size) == 0);
-          const uint32_t ka = s_key[lo], kb = s_key[hi];
-          const int ra = s_row[lo], rb = s_row[hi];
-          const bool a_first = (ka > kb) || (ka == kb && ra > rb);
-          if (desc ? !a_first : a_first) {
-            s_key[lo] = kb; s_key[hi] = ka;
-            s_row[lo] = rb; s_row[hi] = ra;
-          }
-        }
-        __syncthreads();
-      }
-    }
-    c_k = key_to_f32(s_key[kk - 1]);
+    c_k = key_to_f32(block_kth_largest_smem(s_key, n_c, kk, s_hist, s_ctl));
   } else {
     c_k = key_to_f32(block_kth_largest_key(c, s_cnt, nsub, kk, s_hist, s_ctl));
   }
@@ -456,14 +476,16 @@ k_nns_select(SelectParams p) {
   int count;
   if (in_smem) {
     const uint32_t thr_key = f32_to_key(thr);
-    int lo = 0, hi = n_c;  // first index with key < thr_key (list sorted descending)
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (s_key[mid] >= thr_key) lo = mid + 1; else hi = mid;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int i = tid; i < n_c; i += blockDim.x) {
+      if (s_key[i] >= thr_key) {
+        const int pos = atomicAdd(&s_count, 1);
+        if (pos < kRerankMax) out_rows[pos] = s_row[i];
+      }
     }
-    count = lo;
-    if (count <= kRerankMax)
-      for (int i = tid; i < count; i += blockDim.x) out_rows[i] = s_row[i];
+    __syncthreads();
+    count = s_count;
   } else {
     if (tid == 0) s_count = 0;
     __syncthreads();

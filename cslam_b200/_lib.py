@@ -49,6 +49,15 @@ SIGNATURES = {
     "cslam_nns_set_mode": (_i, [_vp, _i]),
     "cslam_nns_set_sample_rows": (_i, [_vp, _i]),
     "cslam_nns_last_timing": (_i, [_vp, _P(_f), _P(_i), _P(_f)]),
+    # A11-A15 MAC
+    "cslam_mac_create": (_i, [_i, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _P(_vp)]),
+    "cslam_mac_destroy": (_i, [_vp]),
+    "cslam_mac_set_options": (_i, [_vp, _d, _i, _i]),
+    "cslam_mac_fiedler": (_i, [_vp, _vp, _P(_d), _vp, _P(_i)]),
+    "cslam_mac_grad": (_i, [_vp, _vp, _vp]),
+    "cslam_mac_fw_subset": (_i, [_vp, _vp, _i, _i, _d, _vp, _vp, _P(_d), _P(_i), _vp, _vp]),
+    "cslam_mac_stats": (_i, [_vp, _P(_i64), _P(_i64), _P(_i)]),
+    "cslam_fiedler_csr": (_i, [_i, _vp, _vp, _vp, _d, _i, _i, _P(_d), _vp, _P(_i)]),
 }
 
 _lib = None

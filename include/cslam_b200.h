@@ -109,6 +109,56 @@ int cslam_nns_set_sample_rows(cslam_nns_t* h, int sample_rows);
 int cslam_nns_last_timing(cslam_nns_t* h, float* coarse_ms, int* coarse_launches,
                           float* total_ms);
 
+/* ---- A11-A15: MAC sparsification (Frank-Wolfe on the Fiedler value) ------ *
+ * Replaces cslam/mac/mac.py:19-233 (class MAC) and the Laplacian assembly of
+ * cslam/mac/utils.py:47-126.  All arithmetic is float64.
+ * Node ids are the rekeyed ids of
+ * cslam/algebraic_connectivity_maximization.py:312-362 (0 <= i < num_poses).
+ * A Laplacian whose graph (fixed + active candidate edges) is disconnected is
+ * reported as CSLAM_ERR_SINGULAR, the condition under which the reference's
+ * SuperLU factorisation raises (mac.py:52-58 -> networkx _LUSolver).          */
+typedef struct cslam_mac cslam_mac_t;
+
+/* MAC(fixed_measurements, candidate_measurements, num_poses)  (mac.py:21-33).
+ * Edge arrays are host pointers (i, j, weight); copied. */
+int cslam_mac_create(int num_poses, int64_t n_fixed, const int32_t* fixed_i,
+                     const int32_t* fixed_j, const double* fixed_w, int64_t n_cand,
+                     const int32_t* cand_i, const int32_t* cand_j, const double* cand_w,
+                     int device, cslam_mac_t** out);
+int cslam_mac_destroy(cslam_mac_t* h);
+/* Eigen-solver options: relative residual tolerance ||Lx - theta x||_1 / ||L||_inf
+ * (default 1e-10; the reference stops at 1e-8, mac.py:35), LOBPCG block size (1 or 2,
+ * default 1) and iteration cap. */
+int cslam_mac_set_options(cslam_mac_t* h, double tol, int block_size, int max_lobpcg_iters);
+/* evaluate_fiedler_pair(w)  (mac.py:79-97, 61-77, 35-59): lambda_2 and the unit-norm
+ * Fiedler vector [num_poses] (sign arbitrary, as in the reference) of
+ * L(w) = L_fixed + sum_{w_e > 1e-10} w_e * weight_e * (e_i - e_j)(e_i - e_j)^T.
+ * w: host [n_cand].  vec_out (host, nullable), iters_out (nullable). */
+int cslam_mac_fiedler(cslam_mac_t* h, const double* w, double* lambda2, double* vec_out,
+                      int* iters_out);
+/* grad_from_fiedler(fiedler_vec)  (mac.py:112-130): grad_e = weight_e * (v_i - v_j)^2.
+ * host in [num_poses], host out [n_cand]. */
+int cslam_mac_grad(cslam_mac_t* h, const double* fiedler_vec, double* grad_out);
+/* fw_subset(w_init, k, max_iters, duality_gap_tol)  (mac.py:191-233).
+ * rounded_out [n_cand] 0/1 (round_solution_tiebreaker, mac.py:168-189), w_out [n_cand]
+ * the unrounded iterate, *u_out the dual upper bound, *iters_out Frank-Wolfe iterations
+ * run.  Optional traces: trace_sel [max_iters, k] the ascending edge ids of every
+ * direction s_i (round_solution, mac.py:132-147; exact ties at the k-th value are taken
+ * in index order), trace_f [max_iters] the objective values. */
+int cslam_mac_fw_subset(cslam_mac_t* h, const double* w_init, int k, int max_iters,
+                        double duality_gap_tol, double* rounded_out, double* w_out,
+                        double* u_out, int* iters_out, int32_t* trace_sel, double* trace_f);
+/* Totals since creation: LOBPCG iterations, SpMV columns applied, and whether the last
+ * solve had to fall back from the tridiagonal to the diagonal preconditioner. */
+int cslam_mac_stats(cslam_mac_t* h, int64_t* lobpcg_iters, int64_t* spmv_columns,
+                    int* jacobi_fallback);
+/* find_fiedler_pair(L)  (mac.py:35-59) for a caller-assembled CSR Laplacian (host
+ * arrays, int32 indices, float64 data; the diagonal entries are ignored and rebuilt as
+ * minus the row sums of the off-diagonals). */
+int cslam_fiedler_csr(int n, const int32_t* indptr, const int32_t* indices, const double* data,
+                      double tol, int block_size, int device, double* lambda2, double* vec_out,
+                      int* iters_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,201 @@
+"""Behaviour of AlgebraicConnectivityMaximization / LoopClosureSparseMatching on the GPU
+path.  Modelled on the reference's property tests (tests/test_algebraic_connectivity.py,
+tests/test_sparse_matching.py of lajoiepy/cslam) plus golden selections produced by the
+reference itself (tests/golden/mac.npz)."""
+import os
+from collections import namedtuple
+
+import numpy as np
+import pytest
+
+from oracle.inputs import MAC_CASES, multi_robot_graph
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "mac.npz"))
+GlobalDescriptor = namedtuple('GlobalDescriptor', ['keyframe_id', 'robot_id', 'descriptor'])
+
+
+def _acm(R, **kw):
+    from cslam_b200.algebraic_connectivity_maximization import AlgebraicConnectivityMaximization
+    return AlgebraicConnectivityMaximization(robot_id=0, max_nb_robots=R, **kw)
+
+
+def _edges(tuples):
+    from cslam_b200.algebraic_connectivity_maximization import EdgeInterRobot
+    return [EdgeInterRobot(*t) for t in tuples]
+
+
+def _graph(R, P, m, seed, unit_weight=False):
+    fixed, cand = multi_robot_graph(R, P, m, seed)
+    if unit_weight:
+        cand = [(a, b, c, d, 1.0) for a, b, c, d, _ in cand]
+    return _edges(fixed), _edges(cand)
+
+
+@pytest.mark.parametrize("tag", list(MAC_CASES))
+def test_select_candidates_matches_reference_selection(tag):
+    R, P, m, k, seed = MAC_CASES[tag]
+    fixed, cand = _graph(R, P, m, seed)
+    ac = _acm(R)
+    ac.set_graph(fixed, cand)
+    sel = ac.select_candidates(k, {r: True for r in range(R)}, greedy_initialization=True)
+    ref = GOLD[f"{tag}_selected"]
+    assert len(sel) == len(ref) == k
+    ours = sorted((e.robot0_id, e.robot0_keyframe_id, e.robot1_id, e.robot1_keyframe_id) for e in sel)
+    theirs = sorted(tuple(int(x) for x in row[:4]) for row in ref)
+    assert ours == theirs
+    assert len(ac.candidate_edges) == int(GOLD[f"{tag}_remaining"])
+    assert ac.last_mac_trials == 0
+
+
+@pytest.mark.parametrize("R", [2, 3, 5])
+def test_budget_respected_unit_weights(R):
+    # reference test_multi_robot_graph*: all-equal weights, only the count is defined
+    fixed, cand = _graph(R, 30, 80, 100 + R, unit_weight=True)
+    ac = _acm(R)
+    ac.set_graph(fixed, cand)
+    sel = ac.select_candidates(20, {r: True for r in range(R)})
+    assert len(sel) == 20
+    assert len({ac.edge_key(e) for e in sel}) == 20
+    keys = {ac.edge_key(e) for e in cand}
+    assert all(ac.edge_key(e) in keys for e in sel)
+    # a second call never returns an edge twice
+    sel2 = ac.select_candidates(20, {r: True for r in range(R)})
+    assert not ({ac.edge_key(e) for e in sel} & {ac.edge_key(e) for e in sel2})
+
+
+def test_budget_larger_than_candidates_and_empty():
+    fixed, cand = _graph(3, 10, 6, 5)
+    ac = _acm(3)
+    ac.set_graph(fixed, cand)
+    assert len(ac.select_candidates(50, {0: True, 1: True, 2: True})) == 6
+    assert ac.select_candidates(5, {0: True, 1: True, 2: True}) == []
+
+
+def test_greedy_initialization_picks_largest_weights():
+    fixed, cand = _graph(2, 50, 40, 6)
+    ac = _acm(2)
+    ac.set_graph(fixed, cand)
+    inc = ac.check_graph_disconnections({0: True, 1: True})
+    ac.compute_offsets(inc)
+    edges = ac.rekey_edges(ac.candidate_edges.values(), inc)
+    w = ac.greedy_initialization(10, edges)
+    weights = np.array([e.weight for e in edges])
+    assert np.isclose(weights[w.astype(bool)].sum(), np.sort(weights)[-10:].sum())
+
+
+def test_incremental_edges_removal_and_fixed_conversion():
+    from cslam_b200.algebraic_connectivity_maximization import EdgeInterRobot
+    fixed, cand = _graph(3, 20, 40, 7)
+    ac = _acm(3)
+    ac.set_graph(fixed, cand[:30])
+    for e in cand[30:]:
+        ac.add_candidate_edge(e)
+    assert len(ac.candidate_edges) == 40
+    ac.add_fixed_edge(EdgeInterRobot(0, 3, 2, 4, 1.0))
+    inc = {0: True, 1: True, 2: True}
+    sel = ac.select_candidates(8, inc)
+    assert len(sel) == 8 and len(ac.candidate_edges) == 32
+    # selected edges are blacklisted: re-adding is a no-op
+    ac.add_candidate_edge(sel[0])
+    assert len(ac.candidate_edges) == 32
+    # success -> fixed (weight replaced), failure -> removed
+    nfixed = len(ac.fixed_edges)
+    ac.candidate_edges_to_fixed(sel[:4])
+    assert len(ac.fixed_edges) == nfixed + 4 and all(e.weight == ac.fixed_weight for e in ac.fixed_edges[-4:])
+    ac.remove_candidate_edges(sel[4:], failed=True)
+    sel2 = ac.select_candidates(8, inc)
+    assert not ({ac.edge_key(e) for e in sel} & {ac.edge_key(e) for e in sel2})
+    # removal ignores direction and weight
+    e = next(iter(ac.candidate_edges.values()))
+    flipped = EdgeInterRobot(e.robot1_id, e.robot1_keyframe_id, e.robot0_id, e.robot0_keyframe_id, 123.0)
+    n = len(ac.candidate_edges)
+    ac.remove_candidate_edges([flipped])
+    assert len(ac.candidate_edges) == n - 1
+
+
+def test_disconnections_offsets_rekey_roundtrip():
+    from cslam_b200.algebraic_connectivity_maximization import EdgeInterRobot
+    ac = _acm(4)
+    fixed = [EdgeInterRobot(0, 9, 1, 9, 1.0)]
+    cand = [EdgeInterRobot(0, 2, 1, 3, 0.4), EdgeInterRobot(1, 5, 3, 7, 0.9), EdgeInterRobot(3, 1, 0, 4, 0.2)]
+    ac.set_graph(fixed, cand)
+    assert ac.nb_poses == {0: 10, 1: 10, 2: 0, 3: 8}
+    inc = ac.check_graph_disconnections({0: True, 1: True, 2: True, 3: True})
+    assert inc == {0: True, 1: True, 2: False, 3: True}
+    inc2 = ac.check_graph_disconnections({0: True, 1: True, 2: True, 3: False})
+    assert inc2 == {0: True, 1: True, 2: False, 3: False}
+    ac.compute_offsets(inc)
+    assert ac.offsets == {0: 0, 1: 10, 2: 0, 3: 20}
+    rk = ac.rekey_edges(cand, inc)
+    assert [(e.i, e.j) for e in rk] == [(2, 13), (15, 27), (21, 4)]
+    back = ac.recover_inter_robot_edges(rk, inc)
+    assert [tuple(e) for e in back] == [tuple(e) for e in cand]
+    ac.compute_offsets(inc2)
+    assert len(ac.rekey_edges(cand, inc2)) == 1
+    odom = ac.fill_odometry()
+    assert len(odom) == 9 + 9 + 0 + 7
+
+
+def test_add_match_keeps_max_weight_and_reference_quirk():
+    from cslam_b200.algebraic_connectivity_maximization import EdgeInterRobot
+    ac = _acm(3)
+    ac.add_match(EdgeInterRobot(0, 1, 2, 3, 0.5))
+    ac.add_match(EdgeInterRobot(0, 1, 2, 3, 0.3))
+    assert ac.candidate_edges[(0, 1, 2, 3)].weight == 0.5
+    ac.add_match(EdgeInterRobot(0, 1, 2, 3, 0.8))
+    assert ac.candidate_edges[(0, 1, 2, 3)].weight == 0.8
+    # robot0_id > robot1_id: un-normalised lookup misses -> overwritten even by a lower weight
+    ac.add_match(EdgeInterRobot(2, 7, 1, 4, 0.9))
+    ac.add_match(EdgeInterRobot(2, 7, 1, 4, 0.2))
+    assert ac.candidate_edges[(1, 4, 2, 7)].weight == 0.2
+
+
+def test_excluded_robot_makes_laplacian_singular_and_falls_back_to_greedy():
+    # robot 2 has poses but is out of range: isolated vertices -> the reference's SuperLU
+    # raises, select_candidates retries k times and returns the greedy guess
+    np.random.seed(0)
+    fixed, cand = _graph(3, 12, 30, 9)
+    ac = _acm(3)
+    ac.set_graph(fixed, cand)
+    inc = {0: True, 1: True, 2: False}
+    k = 5
+    usable = [e for e in cand if e.robot0_id != 2 and e.robot1_id != 2]
+    sel = ac.select_candidates(k, inc)
+    assert ac.last_mac_trials == k
+    top = sorted(usable, key=lambda e: e.weight)[-k:]
+    assert {ac.edge_key(e) for e in sel} == {ac.edge_key(e) for e in top}
+
+
+def test_sparse_matching_facade():
+    from cslam_b200.loop_closure_sparse_matching import LoopClosureSparseMatching
+    params = {'robot_id': 0, 'max_nb_robots': 3, 'frontend.sensor_type': 'stereo',
+              'frontend.similarity_threshold': 0.0, 'frontend.enable_sparsification': True,
+              'evaluation.enable_sparsification_comparison': False,
+              'frontend.nb_best_matches': 10, 'frontend.intra_loop_min_inbetween_keyframes': 5}
+    rng = np.random.default_rng(3)
+    lcsm = LoopClosureSparseMatching(params)
+
+    def unit():
+        d = rng.random(10)
+        return d / np.linalg.norm(d)
+
+    d0 = unit()
+    assert lcsm.add_local_global_descriptor(d0, 1) == []
+    np.testing.assert_allclose(lcsm.local_nnsm.data[0], d0, atol=1e-7)
+    msg = GlobalDescriptor(4, 2, unit().tolist())
+    match = lcsm.add_other_robot_global_descriptor(msg)
+    np.testing.assert_allclose(lcsm.other_robots_nnsm[2].data[0], np.array(msg.descriptor), atol=1e-7)
+    assert tuple(match)[:4] == (0, 1, 2, 4) and (0, 1, 2, 4) in lcsm.candidate_selector.candidate_edges
+    # 100 local + 2 x 100 remote descriptors, threshold 0 -> 20 selected (reference
+    # test_select_candidates*)
+    for i in range(2, 100):
+        lcsm.add_local_global_descriptor(unit(), i)
+    for r in (1, 2):
+        for i in range(100):
+            lcsm.add_other_robot_global_descriptor(GlobalDescriptor(i, r, unit().tolist()))
+    sel = lcsm.select_candidates(20, {0: True, 1: True, 2: True})
+    assert len(sel) == 20
+    # intra-robot matching: too-recent keyframes are skipped
+    kf, kfs = lcsm.match_local_loop_closures(lcsm.local_nnsm.data[50].astype(np.float64), 50)
+    assert kf is None or abs(kf - 50) >= 5

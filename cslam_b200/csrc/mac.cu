@@ -253,13 +253,66 @@ __global__ void k_fac_c(int n, const double* __restrict__ diag, const double* __
 
 // Affine chunk scans for the two triangular solves, m right-hand sides.
 //   forward : y_i = r_i - l_i y_{i-1}          backward: x_i = z_i - l_{i+1} x_{i+1}
-// Chunk aggregate = (A, B[m]) meaning out_last = A * in + B.
-__global__ void k_tri_fwd_a(int n, int m, int ld, const double* __restrict__ lfac,
-                            const double* __restrict__ r, double* __restrict__ aggA,
-                            double* __restrict__ aggB, int T) {
+// An element (A, B[m]) is the map x -> A x + B.  Three levels: each thread owns CH
+// consecutive rows (sequential), a block scans its 256 thread aggregates with warp
+// shuffles, and one small block scans the per-block aggregates.
+template <bool REV>
+__device__ __forceinline__ void block_scan_affine(double& A, double (&B)[MAXM], double* shA,
+                                                  double (*shB)[32]) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double pa = REV ? __shfl_down_sync(0xffffffffu, A, o) : __shfl_up_sync(0xffffffffu, A, o);
+    double pb[MAXM];
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c)
+      pb[c] = REV ? __shfl_down_sync(0xffffffffu, B[c], o) : __shfl_up_sync(0xffffffffu, B[c], o);
+    const bool ok = REV ? (lane + o < 32) : (lane >= o);
+    if (ok) {
+#pragma unroll
+      for (int c = 0; c < MAXM; ++c) B[c] = fma(A, pb[c], B[c]);
+      A = A * pa;
+    }
+  }
+  if (lane == (REV ? 0 : 31)) {
+    shA[warp] = A;
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) shB[c][warp] = B[c];
+  }
+  __syncthreads();
+  double pa = 1.0, pb[MAXM];
+#pragma unroll
+  for (int c = 0; c < MAXM; ++c) pb[c] = 0.0;
+  if (!REV) {
+    for (int w2 = 0; w2 < warp; ++w2) {
+#pragma unroll
+      for (int c = 0; c < MAXM; ++c) pb[c] = fma(shA[w2], pb[c], shB[c][w2]);
+      pa = shA[w2] * pa;
+    }
+  } else {
+    for (int w2 = nw - 1; w2 > warp; --w2) {
+#pragma unroll
+      for (int c = 0; c < MAXM; ++c) pb[c] = fma(shA[w2], pb[c], shB[c][w2]);
+      pa = shA[w2] * pa;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < MAXM; ++c) B[c] = fma(A, pb[c], B[c]);
+  A = A * pa;
+  __syncthreads();
+}
+
+// forward phase A: per-thread chunk aggregate, block-inclusive prefixes, block totals
+__global__ void __launch_bounds__(256)
+k_tri_fwd_a(int n, int m, int ld, const double* __restrict__ lfac, const double* __restrict__ r,
+            double* __restrict__ incA, double* __restrict__ incB, int TP,
+            double* __restrict__ blkA, double* __restrict__ blkB, int NB) {
+  __shared__ double shA[32];
+  __shared__ double shB[MAXM][32];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int i0 = t * CH;
-  if (i0 >= n) return;
   double A = 1.0, B[MAXM];
 #pragma unroll
   for (int c = 0; c < MAXM; ++c) B[c] = 0.0;
@@ -270,78 +323,69 @@ __global__ void k_tri_fwd_a(int n, int m, int ld, const double* __restrict__ lfa
     for (int c = 0; c < MAXM; ++c)
       if (c < m) B[c] = fma(-l, B[c], r[static_cast<size_t>(c) * ld + i]);
   }
-  aggA[t] = A;
-  for (int c = 0; c < m; ++c) aggB[static_cast<size_t>(c) * T + t] = B[c];
+  block_scan_affine<false>(A, B, shA, shB);
+  incA[t] = A;
+#pragma unroll
+  for (int c = 0; c < MAXM; ++c) incB[static_cast<size_t>(c) * TP + t] = B[c];
+  if (threadIdx.x == blockDim.x - 1) {
+    blkA[blockIdx.x] = A;
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) blkB[static_cast<size_t>(c) * NB + blockIdx.x] = B[c];
+  }
 }
 
-// exclusive scan over chunk aggregates: on exit aggB[c][t] = value entering chunk t
-// (y_{i0-1} for the forward solve); zero enters chunk 0.  Single block.
-__global__ void __launch_bounds__(SCAN_B_THREADS)
-k_tri_b(int T, int m, const double* __restrict__ aggA, double* __restrict__ aggB) {
-  __shared__ double shA[SCAN_B_THREADS];
-  __shared__ double shB[MAXM][SCAN_B_THREADS];
-  const int per = (T + SCAN_B_THREADS - 1) / SCAN_B_THREADS;
-  const int t0 = threadIdx.x * per;
+// phase B: exclusive scan over the NB block aggregates (NB <= 1024); on exit
+// blkB[c][b] = value entering block b (zero enters block 0).
+__global__ void __launch_bounds__(1024)
+k_tri_b(int NB, const double* __restrict__ blkA, double* __restrict__ blkB) {
+  __shared__ double shA[32];
+  __shared__ double shB[MAXM][32];
+  const int b = threadIdx.x;
   double A = 1.0, B[MAXM];
 #pragma unroll
   for (int c = 0; c < MAXM; ++c) B[c] = 0.0;
-  for (int t = t0; t < min(T, t0 + per); ++t) {
-    const double a = aggA[t];
+  if (b < NB) {
+    A = blkA[b];
 #pragma unroll
-    for (int c = 0; c < MAXM; ++c)
-      if (c < m) B[c] = fma(a, B[c], aggB[static_cast<size_t>(c) * T + t]);
-    A = a * A;
+    for (int c = 0; c < MAXM; ++c) B[c] = blkB[static_cast<size_t>(c) * NB + b];
   }
-  shA[threadIdx.x] = A;
+  block_scan_affine<false>(A, B, shA, shB);
+  // inclusive -> exclusive: shift by one block through shared memory
+  __shared__ double exB[MAXM][1024];
 #pragma unroll
-  for (int c = 0; c < MAXM; ++c) shB[c][threadIdx.x] = B[c];
+  for (int c = 0; c < MAXM; ++c) exB[c][b] = B[c];
   __syncthreads();
-  for (int o = 1; o < SCAN_B_THREADS; o <<= 1) {
-    double a = shA[threadIdx.x];
-    double b[MAXM];
+  if (b < NB) {
 #pragma unroll
-    for (int c = 0; c < MAXM; ++c) b[c] = shB[c][threadIdx.x];
-    if (threadIdx.x >= o) {
-      const double pa = shA[threadIdx.x - o];
-#pragma unroll
-      for (int c = 0; c < MAXM; ++c) b[c] = fma(a, shB[c][threadIdx.x - o], b[c]);
-      a = a * pa;
-    }
-    __syncthreads();
-    shA[threadIdx.x] = a;
-#pragma unroll
-    for (int c = 0; c < MAXM; ++c) shB[c][threadIdx.x] = b[c];
-    __syncthreads();
-  }
-  double in[MAXM];
-#pragma unroll
-  for (int c = 0; c < MAXM; ++c) in[c] = threadIdx.x > 0 ? shB[c][threadIdx.x - 1] : 0.0;
-  for (int t = t0; t < min(T, t0 + per); ++t) {
-    const double a = aggA[t];
-#pragma unroll
-    for (int c = 0; c < MAXM; ++c)
-      if (c < m) {
-        const double bt = aggB[static_cast<size_t>(c) * T + t];
-        aggB[static_cast<size_t>(c) * T + t] = in[c];
-        in[c] = fma(a, in[c], bt);
-      }
+    for (int c = 0; c < MAXM; ++c) blkB[static_cast<size_t>(c) * NB + b] = b > 0 ? exB[c][b - 1] : 0.0;
   }
 }
 
-// forward re-walk: y, then z = y / d stored in w; also emits the backward chunk aggregates.
-// The backward recurrence runs over i descending; chunk t's backward aggregate maps the
-// value entering from the right (x_{i_end}) to x_{i0}.
-__global__ void k_tri_fwd_c(int n, int m, int ld, const double* __restrict__ lfac,
-                            const double* __restrict__ dpiv, const double* __restrict__ r,
-                            const double* __restrict__ inB, double* __restrict__ w,
-                            double* __restrict__ bagA, double* __restrict__ bagB, int T) {
+// forward phase C: re-walk the chunk from its exact incoming value: y, then z = y / d
+// stored in w; also produces the backward aggregates (reverse block scan).  Backward
+// block totals are stored at the REVERSED block index so phase B stays a forward scan.
+__global__ void __launch_bounds__(256)
+k_tri_fwd_c(int n, int m, int ld, const double* __restrict__ lfac,
+            const double* __restrict__ dpiv, const double* r /* may alias w */,
+            const double* __restrict__ incA, const double* __restrict__ incB, int TP,
+            const double* __restrict__ blkIn, int NB, double* w,
+            double* __restrict__ rincA, double* __restrict__ rincB, double* __restrict__ rblkA,
+            double* __restrict__ rblkB) {
+  __shared__ double shA[32];
+  __shared__ double shB[MAXM][32];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int i0 = t * CH;
-  if (i0 >= n) return;
   const int i1 = min(n, i0 + CH);
   double y[MAXM];
 #pragma unroll
-  for (int c = 0; c < MAXM; ++c) y[c] = c < m ? inB[static_cast<size_t>(c) * T + t] : 0.0;
+  for (int c = 0; c < MAXM; ++c) {
+    y[c] = 0.0;
+    if (c < m) {
+      const double bin = blkIn[static_cast<size_t>(c) * NB + blockIdx.x];
+      y[c] = threadIdx.x == 0 ? bin
+                              : fma(incA[t - 1], bin, incB[static_cast<size_t>(c) * TP + t - 1]);
+    }
+  }
   double z[MAXM][CH];
   for (int i = i0; i < i1; ++i) {
     const double l = lfac[i];
@@ -367,15 +411,23 @@ __global__ void k_tri_fwd_c(int n, int m, int ld, const double* __restrict__ lfa
         w[static_cast<size_t>(c) * ld + i] = z[c][i - i0];
       }
   }
-  // store reversed so that the same exclusive scan kernel can be reused (chunk T-1 first)
-  bagA[T - 1 - t] = A;
-  for (int c = 0; c < m; ++c) bagB[static_cast<size_t>(c) * T + (T - 1 - t)] = B[c];
+  block_scan_affine<true>(A, B, shA, shB);
+  rincA[t] = A;
+#pragma unroll
+  for (int c = 0; c < MAXM; ++c) rincB[static_cast<size_t>(c) * TP + t] = B[c];
+  if (threadIdx.x == 0) {
+    const int rb = NB - 1 - blockIdx.x;
+    rblkA[rb] = A;
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) rblkB[static_cast<size_t>(c) * NB + rb] = B[c];
+  }
 }
 
-// backward re-walk: w holds z on entry, x on exit; per-block column sums for the projection
+// backward phase C: w holds z on entry, x on exit; per-block column sums for the projection
 __global__ void __launch_bounds__(256)
 k_tri_bwd_c(int n, int m, int ld, const double* __restrict__ lfac,
-            const double* __restrict__ inB, double* __restrict__ w, int T,
+            const double* __restrict__ rincA, const double* __restrict__ rincB, int TP,
+            const double* __restrict__ rblkIn, int NB, double* __restrict__ w,
             double* __restrict__ blocksum) {
   __shared__ double sh[MAXM][8];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -386,9 +438,15 @@ k_tri_bwd_c(int n, int m, int ld, const double* __restrict__ lfac,
   if (i0 < n) {
     const int i1 = min(n, i0 + CH);
     double x[MAXM];
+    const bool edge = threadIdx.x == blockDim.x - 1;
 #pragma unroll
-    for (int c = 0; c < MAXM; ++c)
-      x[c] = c < m ? inB[static_cast<size_t>(c) * T + (T - 1 - t)] : 0.0;
+    for (int c = 0; c < MAXM; ++c) {
+      x[c] = 0.0;
+      if (c < m) {
+        const double bin = rblkIn[static_cast<size_t>(c) * NB + (NB - 1 - blockIdx.x)];
+        x[c] = edge ? bin : fma(rincA[t + 1], bin, rincB[static_cast<size_t>(c) * TP + t + 1]);
+      }
+    }
     for (int i = i1 - 1; i >= i0; --i) {
       const double l = (i + 1 < n) ? lfac[i + 1] : 0.0;
 #pragma unroll
@@ -475,8 +533,10 @@ struct BasisOut {
 
 __global__ void __launch_bounds__(256)
 k_gram(int n, int s, BasisPtrs bp, double* __restrict__ part /*[2*NPAIR][grid]*/) {
-  __shared__ double sh[8];
+  __shared__ double sh[8][2 * NPAIR];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   double v[MAXS], av[MAXS];
 #pragma unroll
   for (int a = 0; a < MAXS; ++a) {
@@ -488,20 +548,25 @@ k_gram(int n, int s, BasisPtrs bp, double* __restrict__ part /*[2*NPAIR][grid]*/
   for (int a = 0; a < MAXS; ++a) {
 #pragma unroll
     for (int b = a; b < MAXS; ++b) {
-      for (int which = 0; which < 2; ++which) {
-        double t = which == 0 ? v[a] * av[b] : v[a] * v[b];
-        t = warp_sum(t);
-        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          double acc = 0.0;
-          for (int k = 0; k < (blockDim.x >> 5); ++k) acc += sh[k];
-          part[static_cast<size_t>(which * NPAIR + idx) * gridDim.x + blockIdx.x] = acc;
+      if (b < s) {  // block-uniform
+        const double ta = warp_sum(v[a] * av[b]);
+        const double tb = warp_sum(v[a] * v[b]);
+        if (lane == 0) {
+          sh[warp][idx] = ta;
+          sh[warp][NPAIR + idx] = tb;
         }
-        __syncthreads();
+      } else if (lane == 0) {
+        sh[warp][idx] = 0.0;
+        sh[warp][NPAIR + idx] = 0.0;
       }
       ++idx;
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * NPAIR) {
+    double acc = 0.0;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) acc += sh[k][threadIdx.x];
+    part[static_cast<size_t>(threadIdx.x) * gridDim.x + blockIdx.x] = acc;
   }
 }
 
@@ -852,14 +917,16 @@ struct FiedlerSolver {
   int device = 0;
   int n = 0;
   int ld = 0;
-  int m = 1;
+  int m = 2;
   cudaStream_t stream = nullptr;
   Adj fix, act;
   bool has_act = false;
   double *diag = nullptr, *sup = nullptr, *rowabs = nullptr, *dpiv = nullptr, *lfac = nullptr;
   double *X = nullptr, *AX = nullptr, *W = nullptr, *AW = nullptr, *P = nullptr, *AP = nullptr;
   M2* fagg = nullptr;
-  double *aggA = nullptr, *aggB = nullptr, *bagA = nullptr, *bagB = nullptr;
+  double *aggA = nullptr, *aggB = nullptr, *bagA = nullptr, *bagB = nullptr;  // per-thread prefixes
+  double *blkA = nullptr, *blkB = nullptr, *rblkA = nullptr, *rblkB = nullptr;  // per-block
+  int TP = 0;      // padded thread count of the scan kernels (nblk_t * 256)
   double *part = nullptr, *red = nullptr;  // reduction scratch / results
   double* h_red = nullptr;                 // pinned
   int* d_bad = nullptr;
@@ -890,10 +957,19 @@ struct FiedlerSolver {
       CSLAM_CUDA(cudaMemsetAsync(*p, 0, static_cast<size_t>(MAXM) * ld * sizeof(double), stream));
     }
     CSLAM_TRY(dev_alloc(&fagg, T));
-    CSLAM_TRY(dev_alloc(&aggA, T));
-    CSLAM_TRY(dev_alloc(&aggB, static_cast<size_t>(MAXM) * T));
-    CSLAM_TRY(dev_alloc(&bagA, T));
-    CSLAM_TRY(dev_alloc(&bagB, static_cast<size_t>(MAXM) * T));
+    TP = nblk_t * 256;
+    if (nblk_t > 1024) {
+      set_error("fiedler: graphs above %d vertices are not supported yet", 1024 * 256 * CH);
+      return CSLAM_ERR_LIMIT;
+    }
+    CSLAM_TRY(dev_alloc(&aggA, TP));
+    CSLAM_TRY(dev_alloc(&aggB, static_cast<size_t>(MAXM) * TP));
+    CSLAM_TRY(dev_alloc(&bagA, TP));
+    CSLAM_TRY(dev_alloc(&bagB, static_cast<size_t>(MAXM) * TP));
+    CSLAM_TRY(dev_alloc(&blkA, nblk_t));
+    CSLAM_TRY(dev_alloc(&blkB, static_cast<size_t>(MAXM) * nblk_t));
+    CSLAM_TRY(dev_alloc(&rblkA, nblk_t));
+    CSLAM_TRY(dev_alloc(&rblkB, static_cast<size_t>(MAXM) * nblk_t));
     const size_t nparts = static_cast<size_t>(std::max(nblk, nblk_t));
     CSLAM_TRY(dev_alloc(&part, 2 * NPAIR * nparts));
     CSLAM_TRY(dev_alloc(&red, 2 * NPAIR + 4 * MAXM + 4));
@@ -904,7 +980,7 @@ struct FiedlerSolver {
 
   void release() {
     for (double** p : {&diag, &sup, &rowabs, &dpiv, &lfac, &X, &AX, &W, &AW, &P, &AP, &aggA, &aggB,
-                       &bagA, &bagB, &part, &red})
+                       &bagA, &bagB, &blkA, &blkB, &rblkA, &rblkB, &part, &red})
       dev_free(*p);
     dev_free(fagg);
     dev_free(d_bad);
@@ -991,15 +1067,16 @@ struct FiedlerSolver {
 
   // W <- M^-1 W  (in place), colsum of the result in red[2*NPAIR + c]
   int precondition() {
-    k_tri_fwd_a<<<nblk_t, 256, 0, stream>>>(n, m, ld, lfac, W, aggA, aggB, T);
+    k_tri_fwd_a<<<nblk_t, 256, 0, stream>>>(n, m, ld, lfac, W, aggA, aggB, TP, blkA, blkB, nblk_t);
     CSLAM_LAUNCH_CHECK();
-    k_tri_b<<<1, SCAN_B_THREADS, 0, stream>>>(T, m, aggA, aggB);
+    k_tri_b<<<1, 1024, 0, stream>>>(nblk_t, blkA, blkB);
     CSLAM_LAUNCH_CHECK();
-    k_tri_fwd_c<<<nblk_t, 256, 0, stream>>>(n, m, ld, lfac, dpiv, W, aggB, W, bagA, bagB, T);
+    k_tri_fwd_c<<<nblk_t, 256, 0, stream>>>(n, m, ld, lfac, dpiv, W, aggA, aggB, TP, blkB, nblk_t, W,
+                                            bagA, bagB, rblkA, rblkB);
     CSLAM_LAUNCH_CHECK();
-    k_tri_b<<<1, SCAN_B_THREADS, 0, stream>>>(T, m, bagA, bagB);
+    k_tri_b<<<1, 1024, 0, stream>>>(nblk_t, rblkA, rblkB);
     CSLAM_LAUNCH_CHECK();
-    k_tri_bwd_c<<<nblk_t, 256, 0, stream>>>(n, m, ld, lfac, bagB, W, T, part);
+    k_tri_bwd_c<<<nblk_t, 256, 0, stream>>>(n, m, ld, lfac, bagA, bagB, TP, rblkB, nblk_t, W, part);
     CSLAM_LAUNCH_CHECK();
     k_sum_parts<<<m, 256, 0, stream>>>(nblk_t, m, part, red + 2 * NPAIR);
     CSLAM_LAUNCH_CHECK();

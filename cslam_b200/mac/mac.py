@@ -66,7 +66,7 @@ class MAC:
         except Exception:
             pass
 
-    def set_options(self, tol=1e-10, block_size=1, max_lobpcg_iters=20000):
+    def set_options(self, tol=1e-10, block_size=2, max_lobpcg_iters=20000):
         _lib.check(_lib.load().cslam_mac_set_options(self._h, float(tol), int(block_size),
                                                      int(max_lobpcg_iters)))
 

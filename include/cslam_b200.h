@@ -128,7 +128,7 @@ int cslam_mac_create(int num_poses, int64_t n_fixed, const int32_t* fixed_i,
 int cslam_mac_destroy(cslam_mac_t* h);
 /* Eigen-solver options: relative residual tolerance ||Lx - theta x||_1 / ||L||_inf
  * (default 1e-10; the reference stops at 1e-8, mac.py:35), LOBPCG block size (1 or 2,
- * default 1) and iteration cap. */
+ * default 2) and iteration cap. */
 int cslam_mac_set_options(cslam_mac_t* h, double tol, int block_size, int max_lobpcg_iters);
 /* evaluate_fiedler_pair(w)  (mac.py:79-97, 61-77, 35-59): lambda_2 and the unit-norm
  * Fiedler vector [num_poses] (sign arbitrary, as in the reference) of

@@ -40,3 +40,23 @@ def multi_robot_graph(R, P, m, seed):
         seen.add(key)
         cand.append((r0, k0, r1, k1, float(rng.random())))
     return fixed, cand
+
+
+def mac_scale_graph(R=8, P=12500, m=1000000, seed=0):
+    """BASELINE.json configs[4]: R robots x P poses (odometry
+    chains), R-1 fixed bridges between consecutive robots' last poses, m inter-robot
+    candidates with uniform endpoints and U(0,1) weights.  Returns rekeyed arrays
+    (fixed_i, fixed_j, fixed_w), (cand_i, cand_j, cand_w), n."""
+    rng = np.random.default_rng(seed)
+    n = R * P
+    fi = np.concatenate([np.arange(r * P, r * P + P - 1) for r in range(R)] +
+                        [np.array([(r + 1) * P - 1 for r in range(R - 1)])]).astype(np.int32)
+    fj = np.concatenate([np.arange(r * P + 1, r * P + P) for r in range(R)] +
+                        [np.array([(r + 2) * P - 1 for r in range(R - 1)])]).astype(np.int32)
+    fw = np.ones(len(fi))
+    r0 = rng.integers(0, R, m)
+    r1 = (r0 + rng.integers(1, R, m)) % R
+    ci = (r0 * P + rng.integers(0, P, m)).astype(np.int32)
+    cj = (r1 * P + rng.integers(0, P, m)).astype(np.int32)
+    cw = rng.random(m)
+    return (fi, fj, fw), (ci, cj, cw), n

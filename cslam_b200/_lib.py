@@ -58,6 +58,14 @@ SIGNATURES = {
     "cslam_mac_fw_subset": (_i, [_vp, _vp, _i, _i, _d, _vp, _vp, _P(_d), _P(_i), _vp, _vp]),
     "cslam_mac_stats": (_i, [_vp, _P(_i64), _P(_i64), _P(_i)]),
     "cslam_fiedler_csr": (_i, [_i, _vp, _vp, _vp, _d, _i, _i, _P(_d), _vp, _P(_i)]),
+    # A1-A5 descriptor extraction
+    "cslam_preproc_create": (_i, [_i, _i, _i, _i, _i, _P(_vp)]),
+    "cslam_preproc_destroy": (_i, [_vp]),
+    "cslam_preproc_run": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "cslam_vlad_forward": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "cslam_pca_workspace_floats": (_i64, [_i, _i]),
+    "cslam_pca_project_l2": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "cslam_gem_head_forward": (_i, [_vp, _i, _i, _i, _f, _f, _vp, _vp, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -159,6 +159,45 @@ int cslam_fiedler_csr(int n, const int32_t* indptr, const int32_t* indices, cons
                       double tol, int block_size, int device, double* lambda2, double* vec_out,
                       int* iters_out);
 
+/* ---- A1-A5: descriptor extraction around the PyTorch backbone ------------- *
+ * All pointers are DEVICE pointers (float32 unless noted); `stream` as above. */
+
+/* A1 preprocessing: transforms.Compose([CenterCrop(crop), Resize(out, interpolation=3),
+ * ToTensor(), Normalize(IMAGENET mean/std)]) of cslam/vpr/netvlad.py:202-208 and
+ * cslam/vpr/cosplace.py:73-79, for uint8 HWC RGB keyframes of a fixed size.  The resize
+ * reproduces Pillow's fixed-point antialiased bicubic bit for bit. */
+typedef struct cslam_preproc cslam_preproc_t;
+int cslam_preproc_create(int in_h, int in_w, int crop, int out_size, int device,
+                         cslam_preproc_t** out);
+int cslam_preproc_destroy(cslam_preproc_t* h);
+/* d_images uint8 [batch, in_h, in_w, 3] -> d_out float32 [batch, 3, out, out] */
+int cslam_preproc_run(cslam_preproc_t* h, const uint8_t* d_images, int batch, float* d_out,
+                      void* stream);
+
+/* A3 NetVLADLayer.forward (cslam/vpr/netvlad.py:94-130), vladv2=False:
+ * d_x [batch, 512, locations] (NCHW feature map, locations = H*W <= 224),
+ * d_conv_w [64, 512] (pool.conv.weight), d_centroids [64, 512] (pool.centroids)
+ * -> d_out [batch, 64*512], cluster-major, intra-normalised and L2-normalised. */
+int cslam_vlad_forward(const float* d_x, int batch, int channels, int locations,
+                       const float* d_conv_w, const float* d_centroids, int clusters,
+                       float* d_out, void* stream);
+
+/* A4 sklearn PCA.transform + preprocessing.normalize (cslam/vpr/netvlad.py:234-237):
+ * out = l2_normalise_rows((x @ W^T - bias) * scale), W = components_ [dout, din],
+ * bias = mean_ @ W^T [dout], scale = 1/sqrt(explained_variance_) [dout] when whiten
+ * (NULL otherwise).  d_work: cslam_pca_workspace_floats(min(batch,64), dout) floats. */
+int64_t cslam_pca_workspace_floats(int batch, int dout);
+int cslam_pca_project_l2(const float* d_x, int batch, int din, const float* d_w,
+                         const float* d_bias, const float* d_scale, int dout, float* d_out,
+                         float* d_work, void* stream);
+
+/* A5 CosPlace aggregation (cslam/vpr/cosplace_utils/network.py:23-29, layers.py:8-36):
+ * L2Norm -> GeM(p, eps) -> Flatten -> Linear(channels, dout) -> L2Norm.
+ * d_x [batch, channels, locations], d_fc_w [dout, channels], d_fc_b [dout] -> d_out [batch, dout] */
+int cslam_gem_head_forward(const float* d_x, int batch, int channels, int locations, float p,
+                           float eps, const float* d_fc_w, const float* d_fc_b, int dout,
+                           float* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

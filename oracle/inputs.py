@@ -60,3 +60,41 @@ def mac_scale_graph(R=8, P=12500, m=1000000, seed=0):
     cj = (r1 * P + rng.integers(0, P, m)).astype(np.int32)
     cw = rng.random(m)
     return (fi, fj, fw), (ci, cj, cw), n
+
+
+# ---- descriptor heads ----------------------------------------------------------------
+def keyframe_image(seed=7, h=480, w=640):
+    """Synthetic RGB keyframe (SURVEY.md section 8d, C2 inputs)."""
+    return np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+
+
+def vlad_case(seed=0, n=2, c=512, hw=14, k=64):
+    """Feature map + NetVLADLayer parameters (conv.weight [k,c], centroids [k,c])."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, c, hw, hw)).astype(np.float32)
+    conv_w = (rng.standard_normal((k, c)) * 0.2).astype(np.float32)
+    centroids = rng.random((k, c)).astype(np.float32)
+    return x, conv_w, centroids
+
+
+def gem_case(seed=1, n=3, c=512, hw=7, d=64):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, c, hw, hw)).astype(np.float32)
+    w = (rng.standard_normal((d, c)) / np.sqrt(c)).astype(np.float32)
+    b = (rng.standard_normal(d) * 0.01).astype(np.float32)
+    return x, 3.0, 1e-6, w, b
+
+
+def pca_case(seed=2, n=5, din=2048, dout=96, whiten=True):
+    """Synthetic whitening PCA in the spirit of SURVEY.md section 8d (C2), small."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, din)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    comp = (rng.standard_normal((dout, din)) / np.sqrt(din)).astype(np.float32)
+    mean = (0.01 * rng.standard_normal(din)).astype(np.float32)
+    ev = rng.uniform(0.5, 1.5, dout)
+    return x, comp, mean, ev, whiten
+
+
+def subsample(a, step):
+    return np.ascontiguousarray(np.asarray(a).reshape(-1)[::step])

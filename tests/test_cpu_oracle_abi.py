@@ -118,3 +118,23 @@ def test_edge_inter_robot_equality_and_acm_bookkeeping_on_cpu():
     assert ac.select_candidates(3, {0: True, 1: True, 2: False}) == []
     w = ac.greedy_initialization(1, [type("E", (), {"weight": x})() for x in (0.1, 0.7, 0.3)])
     assert list(w) == [0.0, 1.0, 0.0]
+
+
+# ---- descriptor-head oracles vs the reference's own modules --------------------------------
+def test_head_oracles_match_reference_golden():
+    from oracle import heads
+    from oracle.inputs import gem_case, keyframe_image, pca_case, subsample, vlad_case
+    gold = np.load(os.path.join(GOLD_DIR, "heads.npz"))
+    pre = heads.preprocess(keyframe_image(), 376)
+    assert pre.shape == (3, 224, 224)
+    assert np.array_equal(subsample(pre, 13), gold["pre_sub"])
+    x, conv_w, cent = vlad_case()
+    v = heads.netvlad_layer(x, conv_w, cent)
+    np.testing.assert_allclose(subsample(v, 37), gold["vlad_sub"], atol=1e-7)
+    np.testing.assert_allclose([v.astype(np.float64).sum(), (v.astype(np.float64) ** 2).sum()],
+                               gold["vlad_sum"], rtol=1e-6)
+    px, comp, mean, ev, whiten = pca_case()
+    np.testing.assert_allclose(heads.pca_project_normalize(px, comp, mean, ev, whiten),
+                               gold["pca_out"], atol=2e-6)
+    gx, p, eps, w, b = gem_case()
+    np.testing.assert_allclose(heads.gem_head(gx, p, eps, w, b), gold["gem_out"], atol=1e-6)

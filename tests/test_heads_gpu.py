@@ -1,0 +1,123 @@
+"""GPU parity of the descriptor-extraction kernels (csrc/heads.cu, through the C ABI)
+against the torch-CPU / PIL oracle (oracle/heads.py) and the golden outputs of the
+reference's own modules (tests/golden/heads.npz)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import heads
+from oracle.inputs import gem_case, keyframe_image, pca_case, subsample, vlad_case
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "heads.npz"))
+
+
+def _cuda(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_preprocessing_bit_exact_vs_pil():
+    from cslam_b200.vpr._common import Preprocessor
+    imgs = np.stack([keyframe_image(7), keyframe_image(8), keyframe_image(9)])
+    pre = Preprocessor(376, 224, 0)
+    out = pre(_cuda(imgs)).cpu().numpy()
+    for b in range(3):
+        ref = heads.preprocess(imgs[b], 376)
+        # integer resampling identical to Pillow; float epilogue identical to torchvision
+        assert np.array_equal(out[b], ref), np.abs(out[b] - ref).max()
+    assert np.array_equal(subsample(out[0], 13), GOLD["pre_sub"])
+    # another geometry: 720x1280 frame, crop 500
+    big = np.random.default_rng(3).integers(0, 256, (720, 1280, 3), dtype=np.uint8)
+    out2 = Preprocessor(500, 224, 0)(_cuda(big[None])).cpu().numpy()[0]
+    assert np.array_equal(out2, heads.preprocess(big, 500))
+
+
+def test_vlad_head_matches_reference_layer():
+    from cslam_b200.vpr.netvlad import NetVLADLayer
+    x, conv_w, cent = vlad_case()
+    layer = NetVLADLayer(device=0)
+    layer.load_state(conv_w, cent)
+    v = layer(_cuda(x)).cpu().numpy()
+    ref = heads.netvlad_layer(x, conv_w, cent)
+    # north_star tolerance 1e-3; entries are O(1/sqrt(32768)), we hold 2e-6 absolute
+    assert np.abs(v - ref).max() < 2e-6
+    np.testing.assert_allclose(subsample(v, 37), GOLD["vlad_sub"], atol=2e-6)
+    np.testing.assert_allclose(np.linalg.norm(v, axis=1), 1.0, atol=1e-5)
+    # ragged spatial size (S = 7*9 = 63) and batch 5
+    x2 = np.random.default_rng(5).standard_normal((5, 512, 7, 9)).astype(np.float32)
+    v2 = layer(_cuda(x2)).cpu().numpy()
+    assert np.abs(v2 - heads.netvlad_layer(x2, conv_w, cent)).max() < 2e-6
+    # deterministic
+    assert np.array_equal(v2, layer(_cuda(x2)).cpu().numpy())
+
+
+def test_pca_projection_matches_sklearn():
+    from cslam_b200.vpr.netvlad import PCAProjection
+    px, comp, mean, ev, whiten = pca_case()
+    out = PCAProjection(comp, mean, ev, whiten, device=0)(_cuda(px)).cpu().numpy()
+    np.testing.assert_allclose(out, GOLD["pca_out"], atol=1e-5)
+    out2 = PCAProjection(comp, mean, None, False, device=0)(_cuda(px)).cpu().numpy()
+    np.testing.assert_allclose(out2, heads.pca_project_normalize(px, comp, mean, None, False), atol=1e-5)
+    # batch larger than one GEMM tile (70 rows), odd sizes
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((70, 1000)).astype(np.float32)
+    c = (rng.standard_normal((130, 1000)) / 30).astype(np.float32)
+    m = rng.standard_normal(1000).astype(np.float32) * 0.01
+    out3 = PCAProjection(c, m, device=0)(_cuda(x)).cpu().numpy()
+    np.testing.assert_allclose(out3, heads.pca_project_normalize(x, c, m), atol=1e-5)
+
+
+def test_gem_head_matches_reference_modules():
+    from cslam_b200.vpr.cosplace import GemHead
+    gx, p, eps, w, b = gem_case()
+    head = GemHead(512, 64, device=0)
+    head.load_state(np.array([p], dtype=np.float32), w, b)
+    out = head(_cuda(gx)).cpu().numpy()
+    np.testing.assert_allclose(out, GOLD["gem_out"], atol=2e-6)
+    # 2048-channel trunk (resnet50-style), 512-d output
+    rng = np.random.default_rng(8)
+    x2 = rng.standard_normal((2, 2048, 7, 7)).astype(np.float32)
+    w2 = (rng.standard_normal((512, 2048)) / 45).astype(np.float32)
+    b2 = np.zeros(512, dtype=np.float32)
+    h2 = GemHead(2048, 512, device=0)
+    h2.load_state(np.array([3.0], dtype=np.float32), w2, b2)
+    np.testing.assert_allclose(h2(_cuda(x2)).cpu().numpy(), heads.gem_head(x2, 3.0, 1e-6, w2, b2), atol=2e-6)
+
+
+def test_cosplace_end_to_end_embedding():
+    import torch
+    from cslam_b200.vpr.cosplace import CosPlace
+    trunk, sd = heads.build_cosplace_modules(seed=0, backbone="resnet18", dim=512)
+    params = {'frontend.nn_checkpoint': 'synthetic', 'frontend.image_crop_size': 376,
+              'frontend.cosplace.descriptor_dim': 512, 'frontend.cosplace.backbone': 'resnet18'}
+    net = CosPlace(params, None, state_dict=sd)
+    imgs = np.stack([keyframe_image(20 + i) for i in range(3)])
+    out = net.compute_embeddings(imgs)
+    assert out.shape == (3, 512) and out.dtype == np.float32
+    for i in range(3):
+        ref = heads.cosplace_embedding(imgs[i], 376, trunk, sd)
+        # descriptor values within 1e-3 of the reference's torch-CPU path (north_star)
+        assert np.abs(out[i] - ref).max() < 1e-3
+        assert np.dot(out[i], ref) > 0.9999
+    single = net.compute_embedding(imgs[1])
+    assert np.abs(single - out[1]).max() < 1e-5
+    # disabled backend = the reference's random test descriptors
+    off = CosPlace({'frontend.nn_checkpoint': 'disable', 'frontend.cosplace.descriptor_dim': 64}, None)
+    assert off.compute_embedding(imgs[0]).shape == (64,)
+
+
+def test_netvlad_end_to_end_embedding():
+    from cslam_b200.vpr.netvlad import NetVLAD, PCAProjection
+    encoder, sd = heads.build_netvlad_modules(seed=0)
+    comp, mean, ev = heads.synthetic_pca(32768, 256, seed=1)
+    params = {'frontend.nn_checkpoint': 'synthetic', 'frontend.image_crop_size': 376}
+    net = NetVLAD(params, None, state_dict=sd, pca=PCAProjection(comp, mean, ev, True, device=0))
+    imgs = np.stack([keyframe_image(30 + i) for i in range(2)])
+    out = net.compute_embeddings(imgs)
+    assert out.shape == (2, 256)
+    for i in range(2):
+        ref = heads.netvlad_embedding(imgs[i], 376, encoder, sd, (comp, mean, ev, True))
+        assert np.abs(out[i] - ref).max() < 1e-3
+        assert np.dot(out[i], ref) > 0.9999

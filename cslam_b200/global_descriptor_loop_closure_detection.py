@@ -1,0 +1,383 @@
+"""GlobalDescriptorLoopClosureDetection — the object `loop_closure_detection_node` builds and
+drives (reference cslam/global_descriptor_loop_closure_detection.py:27-484, constructed at
+cslam/loop_closure_detection_node.py:97).  Same constructor, callbacks and topic names; the
+arithmetic behind them (descriptor extraction, cosine NNS, MAC sparsification) runs on the
+GPU through libcslam_b200.
+
+`node` is duck-typed: an `rclpy` node when ROS 2 is installed, or
+`cslam_b200.local_node.LocalNode` (in-process bus) otherwise; message classes come from
+`cslam_b200.msgs`, which re-exports the real ROS types when they are importable.
+
+Batched entry points added for the GPU (`receive_keyframes`, `add_global_descriptors_to_map`)
+process B keyframes with one descriptor forward pass and one search per descriptor pool;
+they produce the same buffers, matches and published messages as B calls of the
+reference's per-keyframe callbacks.
+"""
+import time
+
+import numpy as np
+from sortedcontainers import SortedDict
+
+from . import msgs as M
+from .algebraic_connectivity_maximization import EdgeInterRobot
+from .broker import Broker
+from .loop_closure_sparse_matching import LoopClosureSparseMatching
+from .neighbors_manager import NeighborManager
+from .utils.misc import dict_to_list_chunks
+
+
+def image_from_msg(image):
+    """HxWx3 uint8 array from a keyframe image: already an array (in-process use), or a
+    sensor_msgs/Image (fields height, width, step, data; the reference converts with
+    CvBridge 'passthrough', :397-399, i.e. no channel reordering)."""
+    if isinstance(image, np.ndarray) or hasattr(image, "is_cuda"):
+        return image
+    h, w = int(image.height), int(image.width)
+    step = int(getattr(image, "step", 0)) or 3 * w
+    rows = np.frombuffer(bytes(image.data), dtype=np.uint8).reshape(h, step)
+    return rows[:, :3 * w].reshape(h, w, 3)
+
+
+class GlobalDescriptorLoopClosureDetection(object):
+    """ Global descriptor matching """
+
+    def __init__(self, params, node, global_descriptor=None):
+        """
+        Args:
+            params (dict): the reference's flat parameter dict
+            node: node handle (rclpy node or LocalNode)
+            global_descriptor: optional ready-made NetVLAD / CosPlace object (e.g. built from
+                an in-memory state_dict); by default it is built from `params` like the
+                reference does
+        """
+        self.params = params
+        self.node = node
+        self.lcm = LoopClosureSparseMatching(params)
+
+        technique = self.params['frontend.global_descriptor_technique'].lower()
+        if global_descriptor is not None:
+            self.global_descriptor = global_descriptor
+        elif technique == 'netvlad':
+            from .vpr.netvlad import NetVLAD
+            self.node.get_logger().info('Using NetVLAD.')
+            self.global_descriptor = NetVLAD(self.params, self.node)
+        elif technique == 'scancontext':
+            # lidar modality: out of scope of the GPU front end
+            raise NotImplementedError("cslam_b200 covers the visual place-recognition path; "
+                                      "'scancontext' is not supported")
+        else:
+            from .vpr.cosplace import CosPlace
+            self.node.get_logger().info('Using CosPlace. (default)')
+            self.global_descriptor = CosPlace(self.params, self.node)
+        self.keyframe_type = "rgb"
+
+        # topics (reference :63-107)
+        self.params['frontend.global_descriptors_topic'] = '/cslam/' + self.node.get_parameter(
+            'frontend.global_descriptors_topic').value
+        self.global_descriptor_publisher = self.node.create_publisher(
+            M.GlobalDescriptors, self.params['frontend.global_descriptors_topic'], 100)
+        self.global_descriptor_subscriber = self.node.create_subscription(
+            M.GlobalDescriptors, self.params['frontend.global_descriptors_topic'],
+            self.global_descriptor_callback, 100)
+
+        self.params['frontend.inter_robot_matches_topic'] = '/cslam/' + self.node.get_parameter(
+            'frontend.inter_robot_matches_topic').value
+        self.inter_robot_matches_publisher = self.node.create_publisher(
+            M.InterRobotMatches, self.params['frontend.inter_robot_matches_topic'], 100)
+        self.inter_robot_matches_subscriber = self.node.create_subscription(
+            M.InterRobotMatches, self.params['frontend.inter_robot_matches_topic'],
+            self.inter_robot_matches_callback, 100)
+
+        self.receive_keyframe_subscriber = self.node.create_subscription(
+            M.KeyframeRGB, 'cslam/keyframe_data', self.receive_keyframe, 100)
+        self.local_match_publisher = self.node.create_publisher(
+            M.LocalKeyframeMatch, 'cslam/local_keyframe_match', 100)
+        self.receive_inter_robot_loop_closure_subscriber = self.node.create_subscription(
+            M.InterRobotLoopClosure, '/cslam/inter_robot_loop_closure',
+            self.receive_inter_robot_loop_closure, 100)
+        self.local_descriptors_request_publishers = {
+            i: self.node.create_publisher(M.LocalDescriptorsRequest,
+                                          '/r' + str(i) + '/cslam/local_descriptors_request', 100)
+            for i in range(self.params['max_nb_robots'])}
+
+        self.neighbor_manager = NeighborManager(self.node, self.params)
+
+        # outgoing buffers + their periodic publication (reference :112-126)
+        period = self.params['frontend.detection_publication_period_sec']
+        self.global_descriptors_buffer = SortedDict()
+        self.global_descriptors_timer = self._create_timer(
+            period, self.global_descriptors_timer_callback)
+        self.inter_robot_matches_buffer = SortedDict()
+        self.nb_inter_robot_matches = 0
+        self.inter_robot_matches_timer = self._create_timer(
+            period, self.inter_robot_matches_timer_callback)
+
+        if self.params["evaluation.enable_logs"]:
+            self.log_publisher = self.node.create_publisher(M.KeyValue, 'cslam/log_info', 100)
+            self.log_matches_publisher = self.node.create_publisher(
+                M.InterRobotMatches, 'cslam/log_matches', 100)
+            self.log_total_successful_matches = 0
+            self.log_total_failed_matches = 0
+            self.log_total_vertices_transmitted = 0
+            self.log_total_matches_selected = 0
+            self.log_detection_cumulative_communication = 0
+            self.log_total_sparsification_computation_time = 0.0
+
+        self.gpu_start_time = time.time()
+
+    def _create_timer(self, period, callback):
+        try:  # the reference insists on the system clock (:118-126)
+            from rclpy.clock import Clock
+            return self.node.create_timer(period, callback, clock=Clock())
+        except ImportError:
+            return self.node.create_timer(period, callback)
+
+    def _log(self, key, value):
+        self.log_publisher.publish(M.KeyValue(key=key, value=str(value)))
+
+    # ------------------------------------------------------------------ keyframes in
+    def add_global_descriptor_to_map(self, embedding, kf_id):
+        """Add one global descriptor to the matching lists (reference :148-174)."""
+        self.detect_intra(embedding, kf_id)
+        matches = self.lcm.add_local_global_descriptor(embedding, kf_id)
+        self._buffer_descriptor(embedding, kf_id)
+        self._buffer_matches(matches)
+
+    def add_global_descriptors_to_map(self, embeddings, kf_ids):
+        """Batched `add_global_descriptor_to_map`: embeddings [B, D] (CUDA tensor or array)
+        of consecutive local keyframes."""
+        import torch
+        kf_ids = [int(k) for k in kf_ids]
+        rows_before = self.lcm.local_nnsm.n
+        matches = self.lcm.add_local_global_descriptors(embeddings, kf_ids)
+        if self.params['frontend.enable_intra_robot_loop_closures']:
+            for kf_id, (kf_match, _) in zip(kf_ids, self.lcm.match_local_loop_closures_batch(
+                    embeddings, kf_ids, rows_before)):
+                if kf_match is not None:
+                    self.local_match_publisher.publish(
+                        M.LocalKeyframeMatch(keyframe0_id=kf_id, keyframe1_id=kf_match))
+        host = embeddings.detach().cpu().numpy() if torch.is_tensor(embeddings) \
+            else np.asarray(embeddings)
+        for b, kf_id in enumerate(kf_ids):
+            self._buffer_descriptor(host[b], kf_id)
+        self._buffer_matches(matches)
+        return matches
+
+    def _buffer_descriptor(self, embedding, kf_id):
+        msg = M.GlobalDescriptor()
+        msg.keyframe_id = kf_id
+        msg.robot_id = self.params['robot_id']
+        # a ROS float32[] field needs a list; in process the float32 row is kept as is
+        msg.descriptor = embedding.tolist() if M.HAVE_ROS_MSGS else np.asarray(embedding)
+        self.global_descriptors_buffer[kf_id] = msg
+
+    def _buffer_matches(self, matches):
+        for match in matches:
+            self.inter_robot_matches_buffer[self.nb_inter_robot_matches] = match
+            self.nb_inter_robot_matches += 1
+
+    def receive_keyframe(self, msg):
+        """Keyframe callback: image -> descriptor -> matching (reference :388-405)."""
+        embedding = self.global_descriptor.compute_embedding(image_from_msg(msg.image))
+        self.add_global_descriptor_to_map(embedding, msg.id)
+
+    def receive_keyframes(self, keyframe_msgs):
+        """Batched keyframe callback: one forward pass for all images, descriptors stay on
+        the GPU between the network and the searches."""
+        if len(keyframe_msgs) == 0:
+            return []
+        if not getattr(self.global_descriptor, "enable", False):
+            for m in keyframe_msgs:
+                self.receive_keyframe(m)
+            return []
+        images = [image_from_msg(m.image) for m in keyframe_msgs]
+        if hasattr(images[0], "is_cuda"):
+            import torch
+            batch = torch.stack(images)
+        else:
+            batch = np.stack(images)
+        emb = self.global_descriptor.compute_embeddings_device(batch)
+        return self.add_global_descriptors_to_map(emb, [m.id for m in keyframe_msgs])
+
+    # ------------------------------------------------------------------ periodic publication
+    @staticmethod
+    def _drop_below(buffer, first_kept):
+        if first_kept >= buffer.peekitem(0)[0]:
+            for k in [k for k in buffer.keys() if k < first_kept]:
+                del buffer[k]
+
+    def delete_useless_descriptors(self):
+        """Forget descriptors every other robot has received (reference :176-185)."""
+        self._drop_below(self.global_descriptors_buffer, self.neighbor_manager.useless_descriptors(
+            self.global_descriptors_buffer.peekitem(-1)[0]))
+
+    def delete_useless_inter_robot_matches(self):
+        """Forget matches every other robot has received (reference :187-196)."""
+        self._drop_below(self.inter_robot_matches_buffer, self.neighbor_manager.useless_matches(
+            self.inter_robot_matches_buffer.peekitem(-1)[0]))
+
+    def global_descriptors_timer_callback(self):
+        """Broadcast the descriptors some neighbour in range has not seen (reference :198-227)."""
+        if len(self.global_descriptors_buffer) == 0:
+            return
+        from_kf_id = self.neighbor_manager.select_from_which_kf_to_send(
+            self.global_descriptors_buffer.peekitem(-1)[0])
+        chunks = dict_to_list_chunks(
+            self.global_descriptors_buffer,
+            from_kf_id - self.global_descriptors_buffer.peekitem(0)[0],
+            self.params['frontend.detection_publication_max_elems_per_msg'])
+        for chunk in chunks:
+            out = M.GlobalDescriptors()
+            out.descriptors = chunk
+            self.global_descriptor_publisher.publish(out)
+            if self.params["evaluation.enable_logs"]:
+                self.log_detection_cumulative_communication += len(chunk) * len(
+                    chunk[0].descriptor) * 4
+        self.delete_useless_descriptors()
+        if self.params["evaluation.enable_logs"]:
+            self._log("detection_cumulative_communication",
+                      self.log_detection_cumulative_communication)
+
+    def edge_to_match(self, edge):
+        """EdgeInterRobot -> InterRobotMatch message (reference :229-239)."""
+        msg = M.InterRobotMatch()
+        msg.robot0_id = edge.robot0_id
+        msg.robot0_keyframe_id = edge.robot0_keyframe_id
+        msg.robot1_id = edge.robot1_id
+        msg.robot1_keyframe_id = edge.robot1_keyframe_id
+        msg.weight = edge.weight
+        return msg
+
+    def inter_robot_matches_timer_callback(self):
+        """Broadcast the matches some neighbour in range has not seen (reference :241-289)."""
+        if len(self.inter_robot_matches_buffer) == 0:
+            return
+        from_match_idx = self.neighbor_manager.select_from_which_match_to_send(
+            self.inter_robot_matches_buffer.peekitem(-1)[0])
+        chunks = dict_to_list_chunks(
+            self.inter_robot_matches_buffer,
+            from_match_idx - self.inter_robot_matches_buffer.peekitem(0)[0],
+            self.params['frontend.detection_publication_max_elems_per_msg'])
+        # with exactly two robots in range, a match between those two was detected on both
+        # sides already: not transmitted (reference :254-263)
+        _, in_range = self.neighbor_manager.check_neighbors_in_range()
+        if len(in_range) == 2:
+            chunks = [[m for m in c if not (m.robot0_id in in_range and m.robot1_id in in_range)]
+                      for c in chunks]
+            chunks = [c for c in chunks if len(c) > 0]
+        for chunk in chunks:
+            out = M.InterRobotMatches()
+            out.robot_id = self.params['robot_id']
+            out.matches = [self.edge_to_match(m) for m in chunk]
+            self.inter_robot_matches_publisher.publish(out)
+            if self.params["evaluation.enable_logs"]:
+                self.log_detection_cumulative_communication += len(out.matches) * 20
+        self.delete_useless_inter_robot_matches()
+        if self.params["evaluation.enable_logs"]:
+            self._log("detection_cumulative_communication",
+                      self.log_detection_cumulative_communication)
+
+    # ------------------------------------------------------------------ detection
+    def detect_intra(self, embedding, kf_id):
+        """Intra-robot loop closure for one keyframe (reference :291-307)."""
+        if self.params['frontend.enable_intra_robot_loop_closures']:
+            kf_match, _ = self.lcm.match_local_loop_closures(embedding, kf_id)
+            if kf_match is not None:
+                self.local_match_publisher.publish(
+                    M.LocalKeyframeMatch(keyframe0_id=kf_id, keyframe1_id=kf_match))
+
+    def detect_inter(self):
+        """Broker only: choose the budgeted candidates that maximise the algebraic
+        connectivity, then ask the robots to ship the covering vertices (reference :309-363).
+
+        Returns:
+            list(EdgeInterRobot): the selection (the reference returns None; handy for tests)
+        """
+        neighbors_is_in_range, neighbors_in_range_list = \
+            self.neighbor_manager.check_neighbors_in_range()
+        if not (len(neighbors_in_range_list) > 0 and self.neighbor_manager.local_robot_is_broker()):
+            return []
+        logs = self.params["evaluation.enable_logs"]
+        start_time = time.time()
+        selection = self.lcm.select_candidates(
+            self.params["frontend.inter_robot_loop_closure_budget"], neighbors_is_in_range)
+
+        vertices_info = self.edge_list_to_vertices(selection)
+        broker = Broker(selection, neighbors_in_range_list)
+        for vertices in broker.brokerage(self.params["frontend.use_vertex_cover_selection"]):
+            for v in vertices:
+                req = M.LocalDescriptorsRequest()
+                req.keyframe_id = v[1]
+                req.matches_robot_id = vertices_info[v][0]
+                req.matches_keyframe_id = vertices_info[v][1]
+                self.local_descriptors_request_publishers[v[0]].publish(req)
+            if logs:
+                self.log_total_vertices_transmitted += len(vertices)
+        if logs:
+            self.log_total_sparsification_computation_time += time.time() - start_time
+            self.log_total_matches_selected += len(selection)
+            self._log("sparsification_cumulative_computation_time",
+                      self.log_total_sparsification_computation_time)
+            self._log("nb_vertices_transmitted", self.log_total_vertices_transmitted)
+            self._log("nb_matches_selected", self.log_total_matches_selected)
+            if self.params["evaluation.enable_sparsification_comparison"]:
+                out = M.InterRobotMatches()
+                out.robot_id = self.params["robot_id"]
+                out.matches = [self.edge_to_match(e)
+                               for e in self.lcm.candidate_selector.log_mac_edges]
+                self.log_matches_publisher.publish(out)
+        return selection
+
+    def edge_list_to_vertices(self, selection):
+        """{(robot, keyframe): [[matched robot ids], [matched keyframe ids]]} (reference :365-386)."""
+        vertices = {}
+        for s in selection:
+            a = (s.robot0_id, s.robot0_keyframe_id)
+            b = (s.robot1_id, s.robot1_keyframe_id)
+            for x, y in ((a, b), (b, a)):
+                entry = vertices.setdefault(x, [[], []])
+                entry[0].append(y[0])
+                entry[1].append(y[1])
+        return vertices
+
+    # ------------------------------------------------------------------ messages from other robots
+    def global_descriptor_callback(self, msg):
+        """Descriptors received from another robot (reference :407-422)."""
+        if len(msg.descriptors) == 0 or msg.descriptors[0].robot_id == self.params['robot_id']:
+            return
+        unknown = self.neighbor_manager.get_unknown_range(msg.descriptors)
+        new = [msg.descriptors[i] for i in unknown]
+        for match in self.lcm.add_other_robot_global_descriptors(new):
+            if match is not None:
+                self._buffer_matches([match])
+
+    def inter_robot_matches_callback(self, msg):
+        """Matches detected by other robots (reference :424-433)."""
+        if msg.robot_id != self.params['robot_id']:
+            for m in msg.matches:
+                self.lcm.candidate_selector.add_match(EdgeInterRobot(
+                    m.robot0_id, m.robot0_keyframe_id, m.robot1_id, m.robot1_keyframe_id, m.weight))
+
+    def inter_robot_loop_closure_msg_to_edge(self, msg):
+        """InterRobotLoopClosure -> edge carrying the fixed weight (reference :435-447)."""
+        return EdgeInterRobot(msg.robot0_id, msg.robot0_keyframe_id, msg.robot1_id,
+                              msg.robot1_keyframe_id, self.lcm.candidate_selector.fixed_weight)
+
+    def receive_inter_robot_loop_closure(self, msg):
+        """Geometric verification result: success turns the candidate into a fixed edge,
+        failure removes it (reference :449-484)."""
+        edge = self.inter_robot_loop_closure_msg_to_edge(msg)
+        what = 'New' if msg.success else 'Failed'
+        self.node.get_logger().info(
+            f'{what} inter-robot loop closure measurement: ({msg.robot0_id},'
+            f'{msg.robot0_keyframe_id}) -> ({msg.robot1_id},{msg.robot1_keyframe_id})')
+        if msg.success:
+            self.lcm.candidate_selector.candidate_edges_to_fixed([edge])
+            if self.params["evaluation.enable_logs"]:
+                self.log_total_successful_matches += 1
+                self._log("nb_matches", self.log_total_successful_matches)
+        else:
+            self.lcm.candidate_selector.remove_candidate_edges([edge], failed=True)
+            if self.params["evaluation.enable_logs"]:
+                self.log_total_failed_matches += 1
+                self._log("nb_failed_matches", self.log_total_failed_matches)

@@ -98,3 +98,44 @@ def pca_case(seed=2, n=5, din=2048, dout=96, whiten=True):
 
 def subsample(a, step):
     return np.ascontiguousarray(np.asarray(a).reshape(-1)[::step])
+
+
+# ---- front-end scenario (A7/A17): a seeded stream of local and remote keyframe descriptors ----
+FRONTEND_PARAMS = {
+    'robot_id': 0, 'max_nb_robots': 3, 'frontend.sensor_type': 'stereo',
+    'frontend.similarity_threshold': 0.8, 'frontend.enable_sparsification': True,
+    'evaluation.enable_sparsification_comparison': False, 'frontend.nb_best_matches': 10,
+    'frontend.intra_loop_min_inbetween_keyframes': 5,
+    'frontend.enable_intra_robot_loop_closures': True,
+    'frontend.inter_robot_loop_closure_budget': 5,
+}
+
+
+def frontend_scenario(seed=11, dim=32, n_local=48, n_remote=40, block=8):
+    """Events in arrival order: ('local', [kf ids], desc [b, dim]) blocks of `block` local
+    keyframes alternating with ('remote', robot, [kf ids], desc) blocks of remote
+    descriptors from robots 1 and 2.  Descriptors are unit-norm float32 drawn around a
+    few shared 'places' so that a useful fraction of similarities clears the 0.8
+    threshold and some do not."""
+    rng = np.random.default_rng(seed)
+    places = rng.random((12, dim))
+
+    def draw(m):
+        base = places[rng.integers(0, len(places), m)]
+        x = base + 0.35 * rng.random((m, dim))
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+        return x.astype(np.float32)
+
+    events = []
+    next_local, next_remote = 0, {1: 0, 2: 0}
+    while next_local < n_local or any(v < n_remote for v in next_remote.values()):
+        if next_local < n_local:
+            ids = list(range(next_local, min(n_local, next_local + block)))
+            events.append(('local', ids, draw(len(ids))))
+            next_local += len(ids)
+        for r in (1, 2):
+            if next_remote[r] < n_remote:
+                ids = list(range(next_remote[r], min(n_remote, next_remote[r] + block)))
+                events.append(('remote', r, ids, draw(len(ids))))
+                next_remote[r] += len(ids)
+    return events

@@ -99,7 +99,47 @@ def gen_mac():
     np.savez_compressed(os.path.join(GOLD, "mac.npz"), **out)
 
 
-GENERATORS = {"nns": gen_nns, "mac": gen_mac}
+def gen_frontend():
+    """Drives the reference LoopClosureSparseMatching with the call sequence of the ROS
+    wrapper (global_descriptor_loop_closure_detection.py:148-174 for local keyframes,
+    :407-422 for remote descriptors, :309-325 for the periodic selection) on the seeded
+    stream of oracle.inputs.frontend_scenario."""
+    import collections
+    import contextlib
+    import io
+    from cslam.loop_closure_sparse_matching import LoopClosureSparseMatching
+    from cslam.algebraic_connectivity_maximization import EdgeInterRobot
+    from oracle.inputs import FRONTEND_PARAMS, frontend_scenario
+    Msg = collections.namedtuple("GlobalDescriptor", ["keyframe_id", "robot_id", "descriptor"])
+    lcm = LoopClosureSparseMatching(dict(FRONTEND_PARAMS))
+    intra, matches = [], []
+    for ev in frontend_scenario():
+        if ev[0] == 'local':
+            for kf, d in zip(ev[1], ev[2]):
+                kf_match, _ = lcm.match_local_loop_closures(d, kf)      # detect_intra
+                intra.append((kf, -1 if kf_match is None else kf_match))
+                matches.extend(lcm.add_local_global_descriptor(d, kf))
+        else:
+            for kf, d in zip(ev[2], ev[3]):
+                m = lcm.add_other_robot_global_descriptor(Msg(kf, ev[1], d.tolist()))
+                if m is not None:
+                    matches.append(m)
+    out = {"intra": np.array(intra), "matches": np.array([tuple(m) for m in matches])}
+    cand = lcm.candidate_selector.candidate_edges
+    out["cand_keys"] = np.array(sorted(cand.keys()))
+    out["cand_weights"] = np.array([cand[k].weight for k in sorted(cand.keys())])
+    # geometric verification feedback: one fixed edge per robot pair so that MAC runs
+    for r0, r1 in ((0, 1), (1, 2)):
+        lcm.candidate_selector.add_fixed_edge(EdgeInterRobot(r0, 0, r1, 0, 1.0))
+    with contextlib.redirect_stdout(io.StringIO()):
+        sel = lcm.select_candidates(FRONTEND_PARAMS['frontend.inter_robot_loop_closure_budget'],
+                                    {0: True, 1: True, 2: True})
+    out["selected"] = np.array([tuple(e) for e in sel])
+    out["remaining"] = np.array(len(lcm.candidate_selector.candidate_edges))
+    np.savez_compressed(os.path.join(GOLD, "frontend.npz"), **out)
+
+
+GENERATORS = {"nns": gen_nns, "mac": gen_mac, "frontend": gen_frontend}
 
 
 def main(argv):

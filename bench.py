@@ -4,31 +4,35 @@ descriptor + NNS + sparsify at a 1M-keyframe pool).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload at N=1 (BASELINE.json configs[2], the configuration the metric is quoted on
-that fits one GPU): CosPlace 512-d descriptors + cosine NNS over a 1M-keyframe pool,
-top-k=30, batch of 64 keyframes per step.  A step = one batch of 64 synthetic 640x480
-RGB keyframes through  preprocess -> ResNet-18 trunk (PyTorch/cuDNN fp32) -> GeM head
--> top-30 search against the resident pool -> similarity threshold -> candidate edges,
-plus one MAC sparsification of the accumulated candidates every `--sparsify-every`
-steps.  Stages whose kernels are not built yet are reported in config["stages"].
+Workload (BASELINE.json configs[2] at N=1, configs[3] under torchrun):
+a step is one round of the front end for a batch of 64 synthetic 640x480 RGB keyframes per
+robot (one robot per GPU):
 
-  value : keyframes/s with the step's inputs already resident in HBM
-  e2e   : same through the public host API (pinned host images in, host results out)
-  roofline : the dominant hand-written kernel (k_nns_coarse_tc), algorithmic bytes
-             = pool_rows * dim_pad * 2 B (fp16 shadow) + query tile, per launch, over its
-             CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline : the oracle port of the reference path timed on host cores (bounded sample)
+  descriptor  preprocess (CUDA) -> ResNet-18 trunk (PyTorch/cuDNN) -> GeM head (CUDA) -> [64, 512]
+  nns         N=1: append to the local 1M x 512 pool, top-30 cosine search (intra-robot
+              loop closures, `GlobalDescriptorLoopClosureDetection.receive_keyframes`)
+              N>1: all-gather the robots' descriptors, each rank searches its own shard
+              (1M / N rows) for all N*64 descriptors, all-gather of the per-shard top-k,
+              candidate edges on every rank (`SwarmLoopClosureMatching.step`)
+  sparsify    the broker (rank 0) runs one MAC Frank-Wolfe selection (`MAC.fw_subset`,
+              20 iterations) on the configs[4] graph: 8 x 12 500 poses, 1M candidate edges,
+              budget 1000 - once per step, i.e. one sparsification per 64 keyframes per robot
+              (the reference sparsifies every 5 s, more often than that per keyframe)
 
-Under torchrun (N>1) every rank holds one robot's pool shard (1M/N rows... weak scaling:
-1M rows per GPU) and processes its own batch; there is no data-path collective in this
-metric except the all-gather of per-shard top-k on the multi-robot path (config 4).
+  value : whole-job keyframes/s with the images already resident in HBM
+  e2e   : same through the same public calls with the images in pinned HOST memory
+          (H2D of 64 x 480 x 640 x 3 bytes per rank and step inside the timed region; the
+          results - matches, selected edges - always come back to the host)
+  roofline : k_nns_coarse_tc, the HBM-bound pool sweep; algorithmic bytes per launch
+          = pool rows x dim_pad x 2 B (fp16 shadow) + the query tile, over its CUDA-event
+          duration measured inside the library on the launching stream
+  cpu_baseline : the oracle port of the reference timed on the host cores (bounded sample)
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -36,207 +40,371 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+METRIC = "keyframes/s descriptor+NNS+sparsify @1M-pool"
+IMG_H, IMG_W = 480, 640
+
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pool", type=int, default=1000000)
+    ap.add_argument("--pool", type=int, default=1000000, help="keyframes in the swarm's pools (total)")
     ap.add_argument("--dim", type=int, default=512)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--k", type=int, default=30)
-    ap.add_argument("--sparsify-every", type=int, default=0)
+    ap.add_argument("--backbone", default="resnet18")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--sparsify-every", type=int, default=1)
+    ap.add_argument("--mac-robots", type=int, default=8)
+    ap.add_argument("--mac-poses", type=int, default=12500)
+    ap.add_argument("--mac-candidates", type=int, default=1000000)
+    ap.add_argument("--mac-budget", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="only the device-resident timed loop (for ncu launch lists; prints no bench line)")
     return ap.parse_args()
 
 
 # --------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-    QUERIES = [
-        "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-        "clocks_event_reasons.sw_power_cap",
-        "clocks.sm,clocks.max.sm,power.draw,clocks_throttle_reasons.hw_slowdown,"
-        "clocks_throttle_reasons.hw_thermal_slowdown,clocks_throttle_reasons.sw_thermal_slowdown,"
-        "clocks_throttle_reasons.sw_power_cap",
-        "clocks.sm,clocks.max.sm,power.draw",
-    ]
+class ClockSampler(object):
+    """`nvidia-smi -lms` running beside the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ["clocks.sm", "clocks.max.sm", "power.draw", "clocks_event_reasons.hw_slowdown",
+              "clocks_event_reasons.hw_thermal_slowdown", "clocks_event_reasons.sw_thermal_slowdown",
+              "clocks_event_reasons.sw_power_cap"]
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
-        self.stop_flag = False
-
-    def _query(self, q):
-        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                              "-i", str(self.index)], capture_output=True, text=True, timeout=5)
-        parts = [p.strip() for p in out.stdout.strip().split(",")]
-        float(parts[0])  # raises if the query was rejected
-        return parts
-
-    def run(self):
-        q = None
-        for cand in self.QUERIES:
+        self.proc, self.fields = None, self.FIELDS
+        for fields in (self.FIELDS, [f.replace("clocks_event_reasons", "clocks_throttle_reasons")
+                                     for f in self.FIELDS], self.FIELDS[:3]):
             try:
-                self._query(cand)
-                q = cand
-                break
+                probe = subprocess.run(["nvidia-smi", "--query-gpu=" + ",".join(fields),
+                                        "--format=csv,noheader,nounits", "-i", str(index)],
+                                       capture_output=True, text=True, timeout=20)
+                float(probe.stdout.strip().split(",")[0])
             except Exception:
                 continue
-        while q is not None and not self.stop_flag:
-            try:
-                parts = self._query(q)
-                parts += ["n/a"] * (7 - len(parts))
-                self.samples.append(parts)
-            except Exception:
-                pass
-            time.sleep(0.1)
+            self.fields = fields
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + ",".join(fields),
+                                          "--format=csv,noheader,nounits", "-i", str(index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            break
+        self.t_marks = []
 
     def summary(self):
-        self.stop_flag = True
-        if not self.samples:
+        if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        reasons = []
-        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
-                          ("sw_power_cap", 6)):
-            if any(s[col].lower().startswith("active") for s in self.samples):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(self.samples)}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=10)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        rows = []
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                float(parts[0])
+                rows.append(parts + ["n/a"] * (7 - len(parts)))
+            except Exception:
+                pass
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        power = [float(r[2]) for r in rows if r[2].replace(".", "", 1).isdigit()]
+        # "under load" = samples drawing at least half of the run's peak power
+        load = [r for r in rows if not power or float(r[2]) >= 0.5 * max(power)] or rows
+        sm = sorted(float(r[0]) for r in load)
+        reasons = [name for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4),
+                                          ("sw_thermal_slowdown", 5), ("sw_power_cap", 6))
+                   if any(r[col].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "samples_under_load": len(load),
+                "power_w_max": max(power) if power else None}
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        if "hbm_gbs" in d:
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy: the kernel is timed alone)"
+    return 6550.0, "fallback (B200_PROFILING.md measured copy bandwidth)"
 
 
-# --------------------------------------------------------------------------
-def cpu_reference_nns(pool_rows, dim, k, seconds, batch):
-    """Oracle port of NearestNeighborsMatching.search (cslam/nns_matching.py:42-61) on host
-    cores.  The reference's per-row Python loop is far slower than this vectorised float64
-    restatement (oracle/nns.py: search_vec, numpy/BLAS with all host threads); we time the
-    faster one, on a bounded sample: a pool of `sample_rows` rows, scaled linearly to
-    `pool_rows` (the scan is O(N))."""
+# -------------------------------------------------------------------------- synthetic inputs
+def mac_graph(R, P, m, seed=0):
+    """BASELINE.json configs[4]: R odometry chains of P poses, R-1 fixed bridges between
+    consecutive robots' last poses, m inter-robot candidates with uniform endpoints and
+    U(0,1) weights.  Rekeyed (i, j, w) arrays."""
+    rng = np.random.default_rng(seed)
+    fi = np.concatenate([np.arange(r * P, r * P + P - 1) for r in range(R)] +
+                        [np.array([(r + 1) * P - 1 for r in range(R - 1)])]).astype(np.int32)
+    fj = np.concatenate([np.arange(r * P + 1, r * P + P) for r in range(R)] +
+                        [np.array([(r + 2) * P - 1 for r in range(R - 1)])]).astype(np.int32)
+    r0 = rng.integers(0, R, m)
+    r1 = (r0 + rng.integers(1, R, m)) % R
+    ci = (r0 * P + rng.integers(0, P, m)).astype(np.int32)
+    cj = (r1 * P + rng.integers(0, P, m)).astype(np.int32)
+    return (fi, fj, np.ones(len(fi))), (ci, cj, rng.random(m)), R * P
+
+
+def greedy_w_init(weights, k):
+    """cslam/algebraic_connectivity_maximization.py:205-218"""
+    w = np.zeros(len(weights))
+    w[np.argpartition(weights, -k)[-k:]] = 1.0
+    return w
+
+
+def cosplace_state_dict(backbone, dim, seed=0):
+    import torch
+    from cslam_b200.vpr.cosplace import get_backbone
+    torch.manual_seed(seed)
+    trunk, feat = get_backbone(backbone)
+    lin = torch.nn.Linear(feat, dim)
+    sd = {"backbone." + k: v for k, v in trunk.state_dict().items()}
+    sd["aggregation.1.p"] = torch.ones(1) * 3
+    sd["aggregation.3.weight"] = lin.weight.detach()
+    sd["aggregation.3.bias"] = lin.bias.detach()
+    return sd
+
+
+def centre_head_bias(net, dev, n_images=16):
+    """Randomly initialised trunks map every image to almost the same GeM feature (measured:
+    pairwise descriptor cosine 0.998), which would make all synthetic keyframes near-duplicates
+    of each other - nothing like trained descriptors.  The head's bias is a model parameter:
+    set it to -W g0 (g0 = mean GeM feature of a few synthetic images) so that descriptors of
+    different keyframes spread over the sphere.  Setup only; plain torch ops."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator(device=dev).manual_seed(99)
+    imgs = torch.randint(0, 256, (n_images, IMG_H, IMG_W, 3), generator=g, device=dev, dtype=torch.uint8)
+    with torch.no_grad():
+        feat = net.backbone(net.transform(imgs))
+        x = F.normalize(feat, p=2.0, dim=1)
+        gem = x.clamp(min=net.aggregation.eps).pow(net.aggregation.p).mean(dim=(2, 3)).pow(1.0 / net.aggregation.p)
+        net.aggregation.bias.copy_(-(net.aggregation.weight.double() @ gem.mean(0).double()).float())
+
+
+def frontend_params(args, rank, world):
+    return {
+        'robot_id': rank, 'max_nb_robots': world, 'frontend.sensor_type': 'stereo',
+        'frontend.similarity_threshold': 0.9, 'frontend.enable_sparsification': True,
+        'evaluation.enable_sparsification_comparison': False, 'evaluation.enable_logs': False,
+        'frontend.nb_best_matches': args.k, 'frontend.intra_loop_min_inbetween_keyframes': 10,
+        'frontend.enable_intra_robot_loop_closures': True,
+        'frontend.inter_robot_loop_closure_budget': args.mac_budget,
+        'frontend.global_descriptor_technique': 'cosplace', 'frontend.nn_checkpoint': 'synthetic',
+        'frontend.cosplace.descriptor_dim': args.dim, 'frontend.cosplace.backbone': args.backbone,
+        'frontend.image_crop_size': 376, 'frontend.backbone_precision': args.precision,
+        'frontend.detection_publication_period_sec': 1.0,
+        'frontend.detection_publication_max_elems_per_msg': 10,
+        'frontend.use_vertex_cover_selection': True,
+        'neighbor_management.enable_neighbor_monitoring': False,
+        'neighbor_management.init_delay_sec': 0.0,
+        'neighbor_management.max_heartbeat_delay_sec': 5.0,
+    }
+
+
+# -------------------------------------------------------------------------- CPU reference leg
+def cpu_reference(args, seconds):
+    """The reference's path restated on the host (oracle port, `kind: port`), bounded sample:
+    descriptor = torch-CPU ResNet-18 + reference-style head on a few images (all host
+    threads); NNS = vectorised float64 scan (numpy/BLAS, faster than the reference's per-row
+    Python loop) of a 100k-row sample scaled linearly to the pool; sparsify = oracle
+    fw_subset (scipy TraceMIN/SuperLU) on a graph 1/10 of configs[4] with 2 of 20 iterations,
+    scaled x10 (edges) x10 (iterations).  Returns (keyframes/s of one full step, description)."""
+    import torch
+    from oracle import heads
+    from oracle.mac import MACOracle
     from oracle.nns import NNSOracle
     rng = np.random.default_rng(2)
-    sample_rows = min(pool_rows, 100000)
-    pool = rng.random((sample_rows, dim), dtype=np.float32)
+    budget = max(2.0, seconds / 3)
+    # descriptor
+    trunk, sd = heads.build_cosplace_modules(seed=0, backbone=args.backbone, dim=args.dim)
+    imgs = rng.integers(0, 256, (64, IMG_H, IMG_W, 3), dtype=np.uint8)
+    heads.cosplace_embedding(imgs[0], 376, trunk, sd)
+    t0, n_img = time.time(), 0
+    while time.time() - t0 < budget and n_img < 64:
+        heads.cosplace_embedding(imgs[n_img], 376, trunk, sd)
+        n_img += 1
+    t_img = (time.time() - t0) / n_img
+    # NNS
+    sample_rows = min(args.pool, 100000)
+    pool = rng.random((sample_rows, args.dim), dtype=np.float32)
     pool /= np.linalg.norm(pool, axis=1, keepdims=True)
-    orc = NNSOracle(dim)
-    orc.data = pool
-    orc.n = sample_rows
+    orc = NNSOracle(args.dim)
+    orc.data, orc.n = pool, sample_rows
     orc.items = dict((i, i) for i in range(sample_rows))
     orc._vv = np.einsum("ij,ij->i", pool, pool)
-    qs = rng.random((batch, dim))
-    orc.search_vec(qs[0], k)
+    qs = rng.random((64, args.dim))
+    orc.search_vec(qs[0], args.k)
+    t0, n_q = time.time(), 0
+    while time.time() - t0 < budget and n_q < 256:
+        orc.search_vec(qs[n_q % 64], args.k)
+        n_q += 1
+    t_query = (time.time() - t0) / n_q * (args.pool / sample_rows)
+    # sparsify
+    shrink = 10
+    fixed, cand, n = mac_graph(args.mac_robots, max(2, args.mac_poses // shrink),
+                               max(100, args.mac_candidates // shrink))
+    k = max(1, args.mac_budget // shrink)
     t0 = time.time()
-    done = 0
-    while time.time() - t0 < seconds and done < 4 * batch:
-        orc.search_vec(qs[done % batch], k)
-        done += 1
-    dt = time.time() - t0
-    per_query = dt / done * (pool_rows / sample_rows)
-    return 1.0 / per_query, f"{done} queries against a {sample_rows}x{dim} pool, scaled x{pool_rows // sample_rows} to {pool_rows} rows"
+    mac = MACOracle.from_arrays(fixed, cand, n)
+    iters = 2
+    mac.fw_subset(greedy_w_init(cand[2], k), k, max_iters=iters)
+    t_mac = (time.time() - t0) * shrink * (20 / iters)
+    t_step = args.batch * (t_img + t_query) + t_mac / max(1, args.sparsify_every)
+    sample = (f"descriptor {n_img} images ({t_img * 1e3:.0f} ms/img, torch {torch.get_num_threads()} threads); "
+              f"NNS {n_q} queries x {sample_rows} rows scaled x{args.pool // sample_rows} "
+              f"({t_query:.2f} s/query at {args.pool} rows, numpy float64); "
+              f"sparsify oracle fw_subset {iters}/20 iterations on 1/{shrink} of the graph scaled x{shrink * 20 // iters} "
+              f"({t_mac:.0f} s per selection); step = {args.batch} keyframes + 1/{args.sparsify_every} selection")
+    return args.batch / t_step, sample, {"ms_per_image": t_img * 1e3, "s_per_query": t_query, "s_per_selection": t_mac}
+
+
+def workload_name(args, world):
+    shard = args.pool // world
+    if world == 1:
+        nns = f"cosine NNS top-{args.k} over a {args.pool}x{args.dim} pool"
+    else:
+        nns = (f"{world} robots, one pool shard of {shard}x{args.dim} per GPU, all-gather of per-shard "
+               f"top-{args.k}")
+    return (f"CosPlace {args.backbone} {args.dim}-d on 640x480 RGB, batch {args.batch}/GPU + {nns} + MAC "
+            f"fw_subset {args.mac_robots}x{args.mac_poses} poses / {args.mac_candidates} candidates / budget "
+            f"{args.mac_budget} every {args.sparsify_every} step(s)")
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count()
     t0 = time.time()
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):
-        v, sample = cpu_reference_nns(args.pool, args.dim, args.k, max(2.0, args.cpu_seconds / 3), args.batch)
+    vals, sample, parts = [], "", {}
+    reps = max(1, min(args.steps, 2))
+    for _ in range(reps):
+        v, sample, parts = cpu_reference(args, max(6.0, args.cpu_seconds / reps))
         vals.append(v)
     v = float(np.median(vals))
-    line = {
-        "impl": "reference", "metric": "keyframes/s (NNS stage of descriptor+NNS+sparsify @1M-pool)",
-        "value": v, "unit": "keyframes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * args.batch / v, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C3: cosine NNS top-{args.k} over {args.pool}x{args.dim} pool, batch {args.batch}",
-                   "stages": ["nns"]},
-        "cpu_baseline": {"value": v, "unit": "keyframes/s", "cores": cores, "kind": "port", "sample": sample},
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "keyframes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.batch / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 descriptors, f64 scores",
+        "data": "synthetic", "config": {"workload": workload_name(args, 1)},
+        "cpu_baseline": {"value": v, "unit": "keyframes/s", "cores": cores, "kind": "port", "sample": sample,
+                         "parts": parts},
         "e2e": {"value": v, "unit": "keyframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "wall_s": time.time() - t0,
-    }
-    print(json.dumps(line))
+        "wall_s": time.time() - t0}))
 
 
-# --------------------------------------------------------------------------
+# -------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from cslam_b200 import _lib
-    from cslam_b200.nns_matching import NearestNeighborsMatching
+    from cslam_b200 import _lib, msgs as M
+    from cslam_b200.mac.mac import MAC
+    from cslam_b200.vpr.cosplace import CosPlace
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+        raise SystemExit("bench.py needs a CUDA device (cslam_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    B, K = args.batch, args.k
+    params = frontend_params(args, rank, world)
+    net = CosPlace(params, None, state_dict=cosplace_state_dict(args.backbone, args.dim), device=local)
+    centre_head_bias(net, dev)
 
-    # ---- resident pool: this rank's robot, `pool` rows (weak scaling) ----
+    # ---- front end of this rank's robot, with its pool shard resident in HBM ----
+    shard = args.pool // world
     g = torch.Generator(device=dev).manual_seed(2 + rank)
-    nn = NearestNeighborsMatching(device=local)
-    for s in range(0, args.pool, 100000):
-        m = min(100000, args.pool - s)
+    if world == 1:
+        from cslam_b200.global_descriptor_loop_closure_detection import GlobalDescriptorLoopClosureDetection
+        from cslam_b200.local_node import LocalNode
+        node = LocalNode(None, "/r0", {'frontend.global_descriptors_topic': 'global_descriptors',
+                                       'frontend.inter_robot_matches_topic': 'inter_robot_matches'})
+        glcd = GlobalDescriptorLoopClosureDetection(params, node, global_descriptor=net)
+        pool = glcd.lcm.local_nnsm
+        swarm = None
+    else:
+        from cslam_b200.swarm import SwarmExchange, SwarmLoopClosureMatching
+        swarm = SwarmLoopClosureMatching(params, SwarmExchange(), exchange_k=K)
+        pool = swarm.local_nnsm
+    for s in range(0, shard, 100000):
+        m = min(100000, shard - s)
         x = torch.rand((m, args.dim), generator=g, device=dev)
         x = x / x.norm(dim=1, keepdim=True)
-        nn.add_items_device(x)
+        pool.add_items_device(x, range(s, s + m))
+        if swarm is not None:
+            swarm._append_ids(range(s, s + m), dev)
     del x
-    B, K = args.batch, args.k
-    # distinct query batches per step (descriptors of new keyframes)
-    nb = 8
-    q_dev = torch.rand((nb, B, args.dim), generator=g, device=dev, dtype=torch.float32)
-    q_dev = q_dev / q_dev.norm(dim=2, keepdim=True)
-    q_host = q_dev.cpu().pin_memory()
-    out_idx = torch.empty((B, K), dtype=torch.int32, device=dev)
-    out_sims = torch.empty((B, K), dtype=torch.float64, device=dev)
-    h_idx = torch.empty((B, K), dtype=torch.int32).pin_memory()
-    h_sims = torch.empty((B, K), dtype=torch.float64).pin_memory()
+    next_kf = [shard]
 
-    def step_device(i):
-        nn.search_batch_device(q_dev[i % nb], K, out=(out_idx, out_sims))
+    # ---- sparsification problem on the broker ----
+    mac = w_init = None
+    if rank == 0 and args.sparsify_every > 0:
+        fixed, cand, n = mac_graph(args.mac_robots, args.mac_poses, args.mac_candidates)
+        mac = MAC(fixed, cand, n, device=local)
+        w_init = greedy_w_init(cand[2], args.mac_budget)
 
-    def step_e2e(i):
-        q = q_host[i % nb].to(dev, non_blocking=True)
-        nn.search_batch_device(q, K, out=(out_idx, out_sims))
-        h_idx.copy_(out_idx, non_blocking=True)
-        h_sims.copy_(out_sims, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        # similarity threshold -> candidate edge count (host side of the path)
-        return int((h_sims[:, 0] >= 0.0).sum())
+    # ---- keyframes: `nb` distinct batches, resident (value) and in pinned host memory (e2e) ----
+    nb = 4
+    img_dev = torch.randint(0, 256, (nb, B, IMG_H, IMG_W, 3), generator=g, device=dev, dtype=torch.uint8)
+    img_host = img_dev.cpu().pin_memory()
+    img_host_np = img_host.numpy()
+    stage_ms = {"descriptor": 0.0, "nns": 0.0, "sparsify": 0.0}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    result = {}
+    steps_run = [0]
+
+    def step(i, images, split=False):
+        kf_ids = list(range(next_kf[0], next_kf[0] + B))
+        next_kf[0] += B
+        steps_run[0] += 1
+        if split:
+            ev[0].record()
+        if world == 1:
+            if split:   # same calls as receive_keyframes, with events between the stages
+                emb = net.compute_embeddings_device(images)
+                ev[1].record()
+                result["matches"] = glcd.add_global_descriptors_to_map(emb, kf_ids)
+            else:
+                result["matches"] = glcd.receive_keyframes(
+                    [M.KeyframeRGB(id=k, image=images[b]) for b, k in enumerate(kf_ids)])
+        else:
+            emb = net.compute_embeddings_device(images)
+            if split:
+                ev[1].record()
+            result["matches"], result["intra"] = swarm.step(emb, kf_ids)
+        if split:
+            ev[2].record()
+        if mac is not None and (i + 1) % args.sparsify_every == 0:
+            rounded, _, u = mac.fw_subset(w_init, args.mac_budget, max_iters=20)
+            result["selected"] = int(rounded.sum())
+        if split:
+            ev[3].record()
+            torch.cuda.synchronize()
+            for name, a, b in (("descriptor", 0, 1), ("nns", 1, 2), ("sparsify", 2, 3)):
+                stage_ms[name] += ev[a].elapsed_time(ev[b])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(images_of, steps, warmup):
         for i in range(warmup):
-            fn(i)
+            step(i, images_of(i))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        coarse = []
         e0.record()
         for i in range(steps):
-            fn(warmup + i)
-            coarse.append(i)
+            step(warmup + i, images_of(warmup + i))
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -247,48 +415,88 @@ def run_ours(args):
         return ms
 
     sampler = ClockSampler(local)
-    sampler.start()
     launches0 = _lib.launch_count()
-    ms_dev = timed(step_device, args.steps, args.warmup)
+    ms_dev = timed(lambda i: img_dev[i % nb], args.steps, args.warmup)
+    if args.profile_mode:
+        print(json.dumps({"profile_mode": True, "ms_per_step_under_profiler": ms_dev / args.steps,
+                          "launches": _lib.launch_count() - launches0}))
+        return
     launches = (_lib.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
-    # per-launch duration of the dominant kernel, CUDA events inside the library
-    coarse_ms = []
-    for i in range(args.steps):
-        step_device(i)
-        torch.cuda.synchronize()
-        coarse_ms.append(nn.last_timing()[0])
-    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e = timed(lambda i: img_host_np[i % nb] if world == 1 else img_host[i % nb], args.steps, args.warmup)
     clocks = sampler.summary()
+    # stage breakdown and the dominant kernel's launch duration: separate, untimed passes
+    n_split = max(3, min(args.steps, 10))
+    coarse_ms = []
+    for i in range(n_split):
+        step(i, img_dev[i % nb], split=True)
+        coarse_ms.append(pool.last_timing()[0])
+    stages = {k_: v / n_split for k_, v in stage_ms.items()}
 
     value = world * B * args.steps / (ms_dev * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     dim_pad = (args.dim + 63) // 64 * 64
-    alg_bytes = args.pool * dim_pad * 2 + 128 * dim_pad * 2
-    c_ms = float(np.mean(coarse_ms))
+    alg_bytes = pool.n * dim_pad * 2 + 128 * dim_pad * 2
+    c_ms = float(np.median(coarse_ms))
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (c_ms * 1e-3) / 1e9
-
+    traffic = {}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):   # dram bytes per launch from one `ncu --set full` capture of the same kernels
+        try:
+            traffic = json.load(open(tr))
+        except Exception:
+            traffic = {}
+    roof_nns = {"bound": "hbm", "kernel": "k_nns_coarse_tc", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("k_nns_coarse_tc"),
+                "peak_source": peak_src, "launch_us": c_ms * 1e3, "algorithmic_bytes": int(alg_bytes),
+                "share_of_step": c_ms / (ms_dev / args.steps)}
+    # the kernel with the largest share of the step: the persistent eigen-solver of the MAC stage
+    # (one launch per Fiedler solve).  Its working set (~25 MB) is L2 resident and every LOBPCG
+    # iteration is a chain of 4 grid barriers + a 6x6 eigen-solve, so it is latency-bound: the
+    # HBM fraction below is reported for completeness, us per iteration is the figure that matters.
+    roofline = roof_nns
+    if mac is not None:
+        st = mac.solver_timing()
+        if st["launches"] > 0 and st["kernel_ms"] > 0:
+            per_launch_bytes = st["algorithmic_bytes"] / st["launches"]
+            per_launch_ms = st["kernel_ms"] / st["launches"]
+            ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "k_lobpcg_persist", "achieved": ach, "peak": peak,
+                        "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get("k_lobpcg_persist"),
+                        "peak_source": peak_src, "launch_us": per_launch_ms * 1e3,
+                        "algorithmic_bytes": int(per_launch_bytes),
+                        "us_per_lobpcg_iteration": 1e3 * st["kernel_ms"] / max(1, st["iterations"]),
+                        "share_of_step": (st["kernel_ms"] / max(1, steps_run[0])) / (ms_dev / args.steps),
+                        "note": "L2-resident, barrier/latency-bound sequential solver; see DESIGN.md section 4"}
+    d2h = (B * (K + B) * 12 if world == 1 else world * world * B * K * 16) + B * args.dim * 4
+    if mac is not None:
+        d2h += 2 * args.mac_candidates * 8 // args.sparsify_every
     line = {
-        "metric": "keyframes/s (NNS stage of descriptor+NNS+sparsify @1M-pool)",
-        "value": value, "unit": "keyframes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 coarse (tcgen05, fp32 acc) + f64 exact re-rank", "data": "synthetic",
-        "config": {"workload": f"C3: cosine NNS top-{K} over {args.pool}x{args.dim} pool per GPU, batch {B}",
-                   "stages": ["nns"], "l2": "inputs larger than L2 (pool shadow %.2f GB)" % (alg_bytes / 1e9),
-                   "parallelism": f"{world} robot shard(s), one per GPU"},
+        "metric": METRIC, "value": value, "unit": "keyframes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": f"{args.precision} backbone (cuDNN), f32 heads, f16 coarse scores (tcgen05, f32 acc) + f64 exact re-rank, f64 MAC",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args, world),
+                   "l2": "inputs larger than L2 (fp16 pool shadow %.2f GB, 4 rotating image batches of %.0f MB)"
+                         % (alg_bytes / 1e9, B * IMG_H * IMG_W * 3 / 1e6),
+                   "parallelism": f"{world} robot(s), one per GPU; sparsification on the broker (rank 0)",
+                   "stage_ms": stages},
         "clocks": clocks,
-        "e2e": {"value": e2e, "unit": "keyframes/s", "h2d_bytes_per_step": B * args.dim * 4,
-                "d2h_bytes_per_step": B * K * 12, "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e, "unit": "keyframes/s", "h2d_bytes_per_step": B * IMG_H * IMG_W * 3,
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_nns_coarse_tc", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "launch_us": c_ms * 1e3, "algorithmic_bytes": alg_bytes},
-        "nns_info": nn.last_info.tolist(),
+        "roofline": roofline,
+        "roofline_nns": roof_nns,
+        "nns_info": pool.last_info.tolist(),
+        "results": {k_: (len(v) if hasattr(v, "__len__") else v) for k_, v in result.items()},
     }
+    if mac is not None:
+        line["mac_stats"] = mac.stats()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sample = cpu_reference_nns(args.pool, args.dim, K, args.cpu_seconds, B)
+        v, sample, parts = cpu_reference(args, args.cpu_seconds)
         line["cpu_baseline"] = {"value": v, "unit": "keyframes/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": sample}
+                                "sample": sample, "parts": parts}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -29,11 +29,16 @@
 #include <math.h>
 
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 #include <random>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace cslam {
 namespace {
@@ -92,17 +97,27 @@ __global__ void k_lap_diag(int n, const int* __restrict__ ip0, const int* __rest
   rowabs[r] = -2.0 * s;  // off-diagonals are all <= 0: |diag| + sum|off| = 2 * degree
 }
 
-__global__ void k_max_reduce(const double* __restrict__ x, int n, double* __restrict__ out) {
-  __shared__ double sh[32];
+// out = max(out, max_i x[i]) for non-negative x (their bit patterns order like integers);
+// `out` must be zeroed before the launch.  Multi-block, 8 independent loads per thread.
+__global__ void __launch_bounds__(256)
+k_max_reduce(const double* __restrict__ x, int n, double* __restrict__ out) {
+  __shared__ double sh[8];
   double m = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, x[i]);
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 8 * stride) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (i0 + u * stride < n) ? x[i0 + u * stride] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) m = fmax(m, v[u]);
+  }
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    m = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (threadIdx.x == 0) *out = m;
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (blockDim.x >> 5); ++k) m = fmax(m, sh[k]);
+    atomicMax(reinterpret_cast<unsigned long long*>(out),
+              static_cast<unsigned long long>(__double_as_longlong(m)));
   }
 }
 
@@ -178,8 +193,14 @@ __device__ __forceinline__ M2 m2_mul(const M2& x, const M2& y) {  // x * y
   r.b = x.a * y.b + x.b * y.d;
   r.c = x.c * y.a + x.d * y.c;
   r.d = x.c * y.b + x.d * y.d;
+  // projective map: renormalise by a power of two (exact, and no fp64 division on the scan path)
   const double s = fmax(fmax(fabs(r.a), fabs(r.b)), fmax(fabs(r.c), fabs(r.d)));
-  if (s > 0.0) { const double inv = 1.0 / s; r.a *= inv; r.b *= inv; r.c *= inv; r.d *= inv; }
+  if (s > 0.0 && isfinite(s)) {
+    int ex;
+    (void)frexp(s, &ex);
+    const double inv = ldexp(1.0, -ex);
+    r.a *= inv; r.b *= inv; r.c *= inv; r.d *= inv;
+  }
   return r;
 }
 
@@ -660,20 +681,50 @@ k_sel_hist(int64_t n, const double* __restrict__ g, SelCtl* ctl, int shift) {
     if (sh[i]) atomicAdd(&ctl->hist[i], sh[i]);
 }
 
+// Digit of the k-th largest key in this pass: the largest d >= 1 with
+// (#keys in bins > d) + hist[d] >= remaining, else 0.  One 256-thread block: bins in shared
+// memory, per-thread chunks of 8 bins, suffix sums over the chunks.
 template <int BITS>
-__global__ void k_sel_pick(SelCtl* ctl, int shift) {
+__global__ void __launch_bounds__(256) k_sel_pick(SelCtl* ctl, int shift) {
+  constexpr int NB = 1 << BITS;
+  constexpr int PER = NB / 256;
+  static_assert(NB % 256 == 0, "bins must split evenly over the block");
+  __shared__ unsigned int sh[NB];
+  __shared__ long long chunk_sum[256];
+  __shared__ int best_d;
+  __shared__ long long best_acc;
+  for (int i = threadIdx.x; i < NB; i += 256) sh[i] = ctl->hist[i];
+  if (threadIdx.x == 0) { best_d = 0; best_acc = -1; }
+  __syncthreads();
+  long long mine = 0;
+  for (int j = 0; j < PER; ++j) mine += sh[threadIdx.x * PER + j];
+  chunk_sum[threadIdx.x] = mine;
+  __syncthreads();
+  // suffix (exclusive) over chunks: keys in bins above this thread's chunk
+  long long above = 0;
+  for (int t = threadIdx.x + 1; t < 256; ++t) above += chunk_sum[t];
+  const long long remaining = ctl->remaining;
+  long long acc = above;
+  int found = -1;
+  long long found_acc = 0;
+  for (int j = PER - 1; j >= 0; --j) {
+    const int d = threadIdx.x * PER + j;
+    const long long hcount = sh[d];
+    if (found < 0 && d > 0 && acc + hcount >= remaining) { found = d; found_acc = acc; }
+    acc += hcount;
+  }
+  if (found > 0) atomicMax(&best_d, found);
+  __syncthreads();
+  if (found > 0 && found == best_d) best_acc = found_acc;
+  if (threadIdx.x == 0 && best_d == 0) best_acc = above + mine - sh[0];   // all keys in bins > 0
+  __syncthreads();
   if (threadIdx.x == 0) {
-    long long acc = 0;
-    int d = (1 << BITS) - 1;
-    for (; d > 0; --d) {
-      const long long h = ctl->hist[d];
-      if (acc + h >= ctl->remaining) break;
-      acc += h;
-    }
+    const int d = best_d;
+    const long long acc_gt = best_acc;
     ctl->prefix |= static_cast<uint64_t>(d) << shift;
     ctl->mask |= static_cast<uint64_t>((1u << BITS) - 1u) << shift;
-    ctl->remaining -= acc;
-    ctl->n_gt += acc;
+    ctl->remaining -= acc_gt;
+    ctl->n_gt += acc_gt;
     if (shift == 0) ctl->need_eq = ctl->remaining;
   }
   __syncthreads();
@@ -815,17 +866,20 @@ __global__ void k_gather(int cnt, const int* __restrict__ idx, const double* __r
   if (i < cnt) dst[i] = src[idx[i]];
 }
 
-// ------------------------------------------------------------------ host: small dense math
+// ------------------------------------------------------------------ small dense math
 // Symmetric generalized eigenproblem GA y = theta GB y for s <= MAXS, smallest m pairs.
 // Column-scaled Cholesky of GB + cyclic Jacobi.  Returns false if GB is (numerically)
-// singular, i.e. the basis is rank deficient.
-bool rayleigh_ritz(int s, int m, const double* GA, const double* GB, double C[MAXS][MAXM],
-                   double* theta) {
-  double ds[MAXS], A[MAXS][MAXS], B[MAXS][MAXS], Lc[MAXS][MAXS] = {}, Li[MAXS][MAXS] = {};
+// singular, i.e. the basis is rank deficient.  Runs on the host (multi-kernel solver) and on
+// the device (one thread per CTA of the persistent solver), same arithmetic.
+__host__ __device__ inline bool rayleigh_ritz(int s, int m, const double* GA, const double* GB,
+                                              double C[MAXS][MAXM], double* theta) {
+  double ds[MAXS], A[MAXS][MAXS], B[MAXS][MAXS], Lc[MAXS][MAXS], Li[MAXS][MAXS];
+  for (int a = 0; a < MAXS; ++a)
+    for (int b = 0; b < MAXS; ++b) Lc[a][b] = Li[a][b] = 0.0;
   for (int a = 0; a < s; ++a) {
     const double d = GB[a * MAXS + a];
-    if (!(d > 0.0) || !std::isfinite(d)) return false;
-    ds[a] = 1.0 / std::sqrt(d);
+    if (!(d > 0.0) || !isfinite(d)) return false;
+    ds[a] = 1.0 / sqrt(d);
   }
   for (int a = 0; a < s; ++a)
     for (int b = 0; b < s; ++b) {
@@ -836,7 +890,7 @@ bool rayleigh_ritz(int s, int m, const double* GA, const double* GB, double C[MA
     double d = B[j][j];
     for (int k = 0; k < j; ++k) d -= Lc[j][k] * Lc[j][k];
     if (!(d > 1e-14)) return false;
-    Lc[j][j] = std::sqrt(d);
+    Lc[j][j] = sqrt(d);
     if (Lc[j][j] < 1e-7) return false;
     for (int i = j + 1; i < s; ++i) {
       double v = B[i][j];
@@ -867,19 +921,23 @@ bool rayleigh_ritz(int s, int m, const double* GA, const double* GB, double C[MA
     }
   for (int i = 0; i < s; ++i)
     for (int j = i + 1; j < s; ++j) T[i][j] = T[j][i] = 0.5 * (T[i][j] + T[j][i]);
-  double V[MAXS][MAXS] = {};
-  for (int i = 0; i < s; ++i) V[i][i] = 1.0;
+  double V[MAXS][MAXS];
+  for (int i = 0; i < MAXS; ++i)
+    for (int j = 0; j < MAXS; ++j) V[i][j] = i == j ? 1.0 : 0.0;
   for (int sweep = 0; sweep < 60; ++sweep) {
-    double off = 0.0;
-    for (int i = 0; i < s; ++i)
+    double off = 0.0, dia = 0.0;
+    for (int i = 0; i < s; ++i) {
+      dia += T[i][i] * T[i][i];
       for (int j = i + 1; j < s; ++j) off += T[i][j] * T[i][j];
-    if (off < 1e-300) break;
+    }
+    // off-diagonal mass below the rounding level of the diagonal: converged
+    if (off <= 1e-36 * dia || off < 1e-300) break;
     for (int p = 0; p < s; ++p)
       for (int q = p + 1; q < s; ++q) {
-        if (std::fabs(T[p][q]) < 1e-300) continue;
+        if (fabs(T[p][q]) < 1e-300) continue;
         const double tau = (T[q][q] - T[p][p]) / (2.0 * T[p][q]);
-        const double t = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
-        const double c = 1.0 / std::sqrt(1.0 + t * t), sn = t * c;
+        const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+        const double c = 1.0 / sqrt(1.0 + t * t), sn = t * c;
         for (int k = 0; k < s; ++k) {
           const double kp = T[k][p], kq = T[k][q];
           T[k][p] = c * kp - sn * kq;
@@ -898,8 +956,16 @@ bool rayleigh_ritz(int s, int m, const double* GA, const double* GB, double C[MA
       }
   }
   int order[MAXS];
-  std::iota(order, order + s, 0);
-  std::sort(order, order + s, [&](int a, int b) { return T[a][a] < T[b][b]; });
+  for (int i = 0; i < s; ++i) order[i] = i;
+  for (int i = 1; i < s; ++i) {  // insertion sort by eigenvalue
+    const int o = order[i];
+    int j = i - 1;
+    while (j >= 0 && T[order[j]][order[j]] > T[o][o]) {
+      order[j + 1] = order[j];
+      --j;
+    }
+    order[j + 1] = o;
+  }
   for (int c = 0; c < m; ++c) {
     const int col = order[c];
     theta[c] = T[col][col];
@@ -910,6 +976,847 @@ bool rayleigh_ritz(int s, int m, const double* GA, const double* GB, double C[MA
     }
   }
   return true;
+}
+
+// ------------------------------------------------------------------ warp-parallel Rayleigh-Ritz
+// Same problem as rayleigh_ritz() above (GA y = theta GB y, s <= MAXS, smallest m pairs), solved
+// by ONE WARP on matrices in shared memory: right-looking Cholesky of the column-scaled GB, two
+// triangular solves for T = L^-1 A L^-T, cyclic Jacobi with the round-robin parallel ordering
+// (s/2 disjoint rotations per round), back-substitution for the m wanted vectors.  A serial
+// version on one GPU thread costs ~130 us per call (fp64 latency chains through local memory);
+// this one a few microseconds.  All lanes of the warp must call it; returns a warp-uniform flag.
+struct RRShared {
+  double A[MAXS][MAXS], B[MAXS][MAXS], L[MAXS][MAXS], Y[MAXS][MAXS], T[MAXS][MAXS], V[MAXS][MAXS];
+  double ds[MAXS], invd[MAXS], rc[MAXS / 2], rs[MAXS / 2];
+  int rp[MAXS / 2], rq[MAXS / 2], order[MAXS];
+  int fail;
+};
+
+__device__ __forceinline__ bool rr_warp(RRShared& S, int s, int m, const double* GA /*[MAXS*MAXS]*/,
+                                        const double* GB, double (*C)[MAXM], double* theta,
+                                        int max_sweeps, long long* rrprof = nullptr) {
+  const int lane = threadIdx.x & 31;
+  long long tq = clock64();
+  auto sect = [&](int k) {
+    if (rrprof && lane == 0) {
+      const long long t = clock64();
+      rrprof[k] += t - tq;
+      tq = t;
+    }
+  };
+  const unsigned full = 0xffffffffu;
+  if (lane == 0) S.fail = 0;
+  __syncwarp();
+  if (lane < s) {
+    const double d = GB[lane * MAXS + lane];
+    if (!(d > 0.0) || !isfinite(d)) S.fail = 1;
+    S.ds[lane] = rsqrt(d);
+  }
+  __syncwarp();
+  if (S.fail) return false;
+  for (int e = lane; e < MAXS * MAXS; e += 32) {
+    const int i = e / MAXS, j = e % MAXS;
+    const bool in = i < s && j < s;
+    const double sc = in ? S.ds[i] * S.ds[j] : 0.0;
+    S.A[i][j] = in ? 0.5 * (GA[i * MAXS + j] + GA[j * MAXS + i]) * sc : 0.0;
+    S.B[i][j] = in ? 0.5 * (GB[i * MAXS + j] + GB[j * MAXS + i]) * sc : 0.0;
+    S.L[i][j] = 0.0;
+    S.V[i][j] = i == j ? 1.0 : 0.0;
+  }
+  __syncwarp();
+  sect(0);
+  // Cholesky B = L L^T, right-looking
+  for (int j = 0; j < s; ++j) {
+    // every lane computes the pivot redundantly (same shared value): one rsqrt gives both
+    // L[j][j] = d * rsqrt(d) and its reciprocal, and no broadcast step is needed
+    const double d = S.B[j][j];
+    if (!(d > 1e-14)) return false;   // warp-uniform
+    const double inv = rsqrt(d);
+    if (lane == 0) {
+      S.L[j][j] = d * inv;
+      S.invd[j] = inv;
+    }
+    if (lane > j && lane < s) S.L[lane][j] = S.B[lane][j] * inv;
+    __syncwarp();
+    for (int e = lane; e < MAXS * MAXS; e += 32) {
+      const int i = e / MAXS, k = e % MAXS;
+      if (k > j && i >= k && i < s) S.B[i][k] -= S.L[i][j] * S.L[k][j];
+    }
+    __syncwarp();
+  }
+  sect(1);
+  // Y = L^-1 A (row by row), T = Y L^-T (column by column)
+  for (int i = 0; i < s; ++i) {
+    if (lane < s) {
+      double v = S.A[i][lane];
+      for (int k = 0; k < i; ++k) v -= S.L[i][k] * S.Y[k][lane];
+      S.Y[i][lane] = v * S.invd[i];
+    }
+    __syncwarp();
+  }
+  for (int j = 0; j < s; ++j) {
+    if (lane < s) {
+      double v = S.Y[lane][j];
+      for (int k = 0; k < j; ++k) v -= S.T[lane][k] * S.L[j][k];
+      S.T[lane][j] = v * S.invd[j];
+    }
+    __syncwarp();
+  }
+  for (int e = lane; e < MAXS * MAXS; e += 32) {
+    const int i = e / MAXS, j = e % MAXS;
+    if (i < j && j < s) {
+      const double v = 0.5 * (S.T[i][j] + S.T[j][i]);
+      S.T[i][j] = v;
+      S.T[j][i] = v;
+    }
+  }
+  __syncwarp();
+  sect(2);
+  // cyclic Jacobi, round-robin ordering over se = s rounded up to even players
+  const int se = s + (s & 1);
+  const int npair = se / 2;
+  // At most 5 sweeps: LOBPCG only needs a basis of the Ritz subspace that is diagonal to working
+  // precision near convergence, where T starts out almost diagonal and 1-2 sweeps suffice; early
+  // iterations tolerate a slightly under-rotated basis (theta stays the exact Rayleigh quotient
+  // of the returned vectors because V is orthogonal).
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    // converged when every off-diagonal entry is below the rounding level of its diagonal pair
+    bool big = false;
+    for (int e = lane; e < MAXS * MAXS; e += 32) {
+      const int i = e / MAXS, j = e % MAXS;
+      if (i < j && j < s) {
+        const double v = S.T[i][j];
+        big = big || (v * v > 1e-32 * fabs(S.T[i][i] * S.T[j][j]) && fabs(v) > 1e-150);
+      }
+    }
+    if (!__any_sync(full, big)) break;
+    for (int r = 0; r < se - 1; ++r) {
+      if (lane < npair) {
+        // circle method: player se-1 is fixed, the others rotate
+        int p, q;
+        if (lane == 0) {
+          p = se - 1;
+          q = r;
+        } else {
+          p = (r + lane) % (se - 1);
+          q = (r - lane + (se - 1)) % (se - 1);
+        }
+        if (p > q) { const int t = p; p = q; q = t; }
+        double c = 1.0, sn = 0.0;
+        if (q < s) {
+          const double apq = S.T[p][q], app = S.T[p][p], aqq = S.T[q][q];
+          if (apq * apq > 1e-40 * fabs(app * aqq) && fabs(apq) > 1e-150) {
+            // same rotation as tau = (aqq - app) / (2 apq), t = sgn(tau) / (|tau| + sqrt(1 + tau^2)),
+            // c = 1 / sqrt(1 + t^2), s = t c, written with two dependent special-function
+            // stages instead of four: r = hypot(h, 2 apq), c = sqrt((|h| + r) / 2r),
+            // s = sgn |2 apq| / sqrt(2 r (|h| + r))
+            // The ANGLE only needs single precision (a slightly inexact angle leaves a 1e-7
+            // relative off-diagonal remainder for the next sweep); what must hold to double
+            // precision is c^2 + s^2 = 1, restored with two Newton steps of 1/sqrt near 1.
+            const double h = aqq - app, bb = 2.0 * apq;
+            int ex;
+            (void)frexp(fmax(fabs(h), fabs(bb)), &ex);   // power-of-two scaling: no fp32 under/overflow
+            const float hf = static_cast<float>(ldexp(h, -ex)), bf = static_cast<float>(ldexp(bb, -ex));
+            const float r2 = fmaf(hf, hf, bf * bf);
+            const float inv_r = rsqrtf(r2);
+            const float rr = r2 * inv_r;
+            const float u = fabsf(hf) + rr;
+            const float cf = sqrtf(0.5f * u * inv_r);
+            const float sf = ((hf >= 0.f) == (bf >= 0.f) ? 1.f : -1.f) * fabsf(bf) * rsqrtf(2.f * rr * u);
+            double cd = cf, sd = sf;
+            double nrm = fma(cd, cd, sd * sd);
+            double fix = fma(-0.5, nrm, 1.5);
+            cd *= fix; sd *= fix;
+            nrm = fma(cd, cd, sd * sd);
+            fix = fma(-0.5, nrm, 1.5);
+            c = cd * fix;
+            sn = sd * fix;
+          }
+        }
+        S.rc[lane] = c;
+        S.rs[lane] = sn;
+        S.rp[lane] = p;
+        S.rq[lane] = q < s ? q : p;   // dummy opponent: identity rotation on (p, p) is skipped below
+      }
+      __syncwarp();
+      // column rotations on T and V: items (pair t, row k, matrix)
+      for (int e = lane; e < npair * MAXS * 2; e += 32) {
+        const int t = e / (MAXS * 2), k = (e / 2) % MAXS, which = e & 1;
+        const int p = S.rp[t], q = S.rq[t];
+        if (p != q && k < s) {
+          double(*Mx)[MAXS] = which ? S.V : S.T;
+          const double c = S.rc[t], sn = S.rs[t];
+          const double kp = Mx[k][p], kq = Mx[k][q];
+          Mx[k][p] = c * kp - sn * kq;
+          Mx[k][q] = sn * kp + c * kq;
+        }
+      }
+      __syncwarp();
+      for (int e = lane; e < npair * MAXS; e += 32) {
+        const int t = e / MAXS, k = e % MAXS;
+        const int p = S.rp[t], q = S.rq[t];
+        if (p != q && k < s) {
+          const double c = S.rc[t], sn = S.rs[t];
+          const double pk = S.T[p][k], qk = S.T[q][k];
+          S.T[p][k] = c * pk - sn * qk;
+          S.T[q][k] = sn * pk + c * qk;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  sect(3);
+  if (lane == 0) {
+    for (int i = 0; i < s; ++i) S.order[i] = i;
+    for (int i = 1; i < s; ++i) {
+      const int o = S.order[i];
+      int j = i - 1;
+      while (j >= 0 && S.T[S.order[j]][S.order[j]] > S.T[o][o]) {
+        S.order[j + 1] = S.order[j];
+        --j;
+      }
+      S.order[j + 1] = o;
+    }
+  }
+  __syncwarp();
+  // C[:, c] = diag(ds) L^-T V[:, order[c]]  (back substitution, one lane per wanted vector)
+  if (lane < m) {
+    const int col = S.order[lane];
+    theta[lane] = S.T[col][col];
+    double z[MAXS];
+#pragma unroll
+    for (int a2 = MAXS - 1; a2 >= 0; --a2) {
+      z[a2] = 0.0;
+      if (a2 < s) {
+        double v = S.V[a2][col];
+#pragma unroll
+        for (int k = MAXS - 1; k > a2; --k)
+          if (k < s) v -= S.L[k][a2] * z[k];
+        z[a2] = v * S.invd[a2];
+      }
+    }
+#pragma unroll
+    for (int a2 = 0; a2 < MAXS; ++a2) C[a2][lane] = a2 < s ? z[a2] * S.ds[a2] : 0.0;
+  }
+  __syncwarp();
+  sect(4);
+  return true;
+}
+
+// Grid-wide barrier for a co-resident (cooperatively launched) grid: one arrival per CTA on a
+// monotonically increasing counter, release/acquire at GPU scope.  `epoch` is the CTA-uniform
+// number of barriers passed so far.  (cooperative_groups' grid.sync() measured ~11 us per call
+// here; this one is bounded by one L2 atomic round trip.)
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch,
+                                             unsigned int nblocks) {
+  __syncthreads();
+  ++epoch;
+  if (threadIdx.x == 0) {
+    const unsigned int target = epoch * nblocks;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ persistent LOBPCG
+// The whole LOBPCG iteration as ONE cooperative kernel: one CTA per SM, every thread owns CH
+// consecutive rows and keeps its rows of X, AX, W, AW, P, AP in REGISTERS for the entire
+// solve; the only vector that travels through global memory is W (the SpMM gathers
+// neighbours' entries).  Four grid barriers per iteration:
+//   1  residual + forward substitution (thread / CTA aggregates)      | barrier
+//   2  CTA-prefix, exact forward re-walk, z = y / d, backward aggregates | barrier
+//   3  CTA-prefix, exact backward re-walk -> W, column sums             | barrier
+//   4  AW = L (W - mean), W -= mean, Gram partial sums                   | barrier
+//   5  every CTA reduces the Gram partials in the same fixed order, thread 0 solves the
+//      (<= 6x6) Rayleigh-Ritz problem, all threads update X, AX, P, AP in registers
+// The multi-kernel path above needs ~13 launches and one host round trip per iteration
+// (~140 us at n = 100k); this kernel needs neither.
+constexpr bool kUseWCache = false;   // shared copy of the CTA's own W rows (measured slower: see DESIGN.md)
+struct PersistArgs {
+  int n, m, rpb;         // rows, block size of the eigen-solver, rows per CTA
+  int ld;
+  const int *ip0, *c0;   // fixed adjacency
+  const double* v0;
+  const int *ip1, *c1;   // active adjacency (ip1 == nullptr: none)
+  const double* v1;
+  const double *diag, *dpiv, *lfac;
+  double *X, *AX, *W, *P, *AP;     // global copies: X/AX in and out, W exchange buffer
+  double *fA, *fB, *bA, *bB;       // [grid], [MAXM][grid] CTA aggregates of the two scans
+  double *pres, *pcs, *pgram;      // [MAXM][grid], [MAXM][grid], [2*NPAIR][grid] partial sums
+  double theta0[MAXM];
+  double tol, lnorm;
+  int max_iters, have_p;
+  double* out;           // [0..MAXM) theta, [MAXM] iterations, [MAXM+1] status, [MAXM+2] res
+  int rr_sweeps;         // Jacobi sweep cap of the Rayleigh-Ritz solve
+  int cap0, cap1;        // shared-memory capacity (entries) for the CTA's slice of each adjacency
+  unsigned int* barrier; // grid barrier counter, zero at launch
+  long long* prof;       // optional [8] cycle counters of CTA 0 (phases 1-5, RR, barriers)
+};
+
+template <int CH, int T>
+__global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
+  constexpr int NW = T / 32;
+  __shared__ double shA[32];
+  __shared__ double shB[MAXM][32];
+  __shared__ double s_incA[T];
+  __shared__ double s_incB[MAXM][T];
+  __shared__ double s_red[NW][2 * NPAIR];
+  __shared__ double s_in[MAXM];
+  __shared__ double s_mu[MAXM];
+  __shared__ double s_res[MAXM];
+  __shared__ double s_G[2 * NPAIR];
+  __shared__ double s_C[MAXS][MAXM];
+  __shared__ double s_theta[MAXM];
+  __shared__ int s_ok;
+  __shared__ RRShared s_rr;
+  __shared__ double s_GA[MAXS * MAXS], s_GB[MAXS * MAXS];
+  __shared__ double s_th2[MAXM];
+  unsigned int epoch = 0;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x, nb_grid = gridDim.x;
+  const int n = a.n, m = a.m, ld = a.ld;
+  const int row0 = b * a.rpb + tid * CH;
+  const int row_end = min(n, (b + 1) * a.rpb);
+  // The matrix does not change during the solve: stage this CTA's (contiguous) slice of both
+  // CSR adjacencies in shared memory so that the SpMM only goes to L2 for the W gathers.
+  // (Every grid barrier invalidates L1, so global CSR reads would pay L2 latency each time.)
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  double* s_v0 = reinterpret_cast<double*>(dyn_smem);
+  double* s_v1 = s_v0 + a.cap0;
+  int* s_c0 = reinterpret_cast<int*>(s_v1 + a.cap1);
+  int* s_c1 = s_c0 + a.cap0;
+  double* s_w = reinterpret_cast<double*>(s_c1 + a.cap1);   // [MAXM][rpb] this CTA's rows of W
+  const int r_lo_cta = min(n, b * a.rpb);
+  const int* C0 = a.c0;
+  const double* V0 = a.v0;
+  const int* C1 = a.c1;
+  const double* V1 = a.v1;
+  {
+    const int r_lo = min(n, b * a.rpb);
+    const int base0 = a.ip0[r_lo], cnt0 = a.ip0[row_end > r_lo ? row_end : r_lo] - base0;
+    if (cnt0 <= a.cap0) {
+      for (int q = tid; q < cnt0; q += T) {
+        s_c0[q] = a.c0[base0 + q];
+        s_v0[q] = a.v0[base0 + q];
+      }
+      C0 = s_c0 - base0;
+      V0 = s_v0 - base0;
+    }
+    if (a.ip1) {
+      const int base1 = a.ip1[r_lo], cnt1 = a.ip1[row_end > r_lo ? row_end : r_lo] - base1;
+      if (cnt1 <= a.cap1) {
+        for (int q = tid; q < cnt1; q += T) {
+          s_c1[q] = a.c1[base1 + q];
+          s_v1[q] = a.v1[base1 + q];
+        }
+        C1 = s_c1 - base1;
+        V1 = s_v1 - base1;
+      }
+    }
+    __syncthreads();
+  }
+  int q0s[CH], q0e[CH], q1s[CH], q1e[CH];
+  bool valid[CH];
+  double x[CH][MAXM], ax[CH][MAXM], w[CH][MAXM], aw[CH][MAXM], p[CH][MAXM], ap[CH][MAXM];
+  double lf[CH], lf_next[CH], dp[CH], dg[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) {
+    const int i = row0 + j;
+    valid[j] = i < row_end;
+    lf[j] = valid[j] ? a.lfac[i] : 0.0;
+    lf_next[j] = (valid[j] && i + 1 < n) ? a.lfac[i + 1] : 0.0;
+    dp[j] = valid[j] ? 1.0 / a.dpiv[i] : 1.0;   // reciprocal pivot
+    dg[j] = valid[j] ? a.diag[i] : 0.0;
+    q0s[j] = valid[j] ? a.ip0[i] : 0;
+    q0e[j] = valid[j] ? a.ip0[i + 1] : 0;
+    q1s[j] = (valid[j] && a.ip1) ? a.ip1[i] : 0;
+    q1e[j] = (valid[j] && a.ip1) ? a.ip1[i + 1] : 0;
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) {
+      const bool on = valid[j] && c < m;
+      x[j][c] = on ? a.X[static_cast<size_t>(c) * ld + i] : 0.0;
+      ax[j][c] = on ? a.AX[static_cast<size_t>(c) * ld + i] : 0.0;
+      p[j][c] = (on && a.have_p) ? a.P[static_cast<size_t>(c) * ld + i] : 0.0;
+      ap[j][c] = (on && a.have_p) ? a.AP[static_cast<size_t>(c) * ld + i] : 0.0;
+      w[j][c] = aw[j][c] = 0.0;
+    }
+  }
+  double theta[MAXM];
+#pragma unroll
+  for (int c = 0; c < MAXM; ++c) theta[c] = a.theta0[c];
+  bool have_p = a.have_p != 0;
+  int status = 1;  // 0 converged, 1 iteration cap, 2 basis rank deficient (converged as far as fp64 allows)
+  double res_out = 0.0;
+  int it = 0;
+
+  // value entering this CTA from the CTAs before (forward) / after (backward) it
+  auto cta_prefix = [&](const double* gA, const double* gB, bool rev) {
+    double A = 1.0, B[MAXM];
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) B[c] = 0.0;
+    if (tid < nb_grid) {
+      A = __ldcg(gA + tid);
+#pragma unroll
+      for (int c = 0; c < MAXM; ++c) B[c] = __ldcg(gB + static_cast<size_t>(c) * nb_grid + tid);
+    }
+    if (rev) block_scan_affine<true>(A, B, shA, shB);
+    else block_scan_affine<false>(A, B, shA, shB);
+    const int src = rev ? b + 1 : b - 1;
+    if (tid == 0 && (src < 0 || src >= nb_grid)) {
+#pragma unroll
+      for (int c = 0; c < MAXM; ++c) s_in[c] = 0.0;
+    }
+    if (tid == src) {
+#pragma unroll
+      for (int c = 0; c < MAXM; ++c) s_in[c] = B[c];
+    }
+    __syncthreads();
+  };
+  // CTA-level sums of MAXM per-thread values -> gdst[c][b]  (fixed order: deterministic)
+  auto block_sum2 = [&](const double (&vals)[MAXM], double* gdst) {
+#pragma unroll
+    for (int k = 0; k < MAXM; ++k) {
+      const double sres = warp_sum(vals[k]);
+      if (lane == 0) s_red[warp][k] = sres;
+    }
+    __syncthreads();
+    if (tid < MAXM) {
+      double acc = 0.0;
+      for (int k = 0; k < NW; ++k) acc += s_red[k][tid];
+      gdst[static_cast<size_t>(tid) * nb_grid + b] = acc;
+    }
+    __syncthreads();
+  };
+  // every CTA: out_s[k] = sum over CTAs of gsrc[k][*] in a fixed order.  All loads of a thread
+  // are issued before the first use (fully unrolled, predicated), so a reduction costs one L2
+  // round trip instead of one per loop iteration.
+  constexpr int MAXG = 192;                 // upper bound on the grid size (one CTA per SM)
+  auto grid_sum2 = [&](const double* gsrc, double* out_s) {   // MAXM values, one warp each
+    constexpr int PER = MAXG / 32;
+    if (warp < MAXM) {
+      double vals[PER];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int q = lane + 32 * i;
+        vals[i] = q < nb_grid ? __ldcg(gsrc + static_cast<size_t>(warp) * nb_grid + q) : 0.0;
+      }
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) acc += vals[i];
+      acc = warp_sum(acc);
+      if (lane == 0) out_s[warp] = acc;
+    }
+    __syncthreads();
+  };
+  auto grid_sum_gram = [&](const double* gsrc, double* out_s) {   // 2 * NPAIR values
+    constexpr int PARTS = 6, PER = MAXG / PARTS;
+    static_assert(2 * NPAIR * PARTS <= T, "needs one thread per (value, part)");
+    const int k = tid / PARTS, part = tid % PARTS;
+    double acc = 0.0;
+    if (k < 2 * NPAIR) {
+      double vals[PER];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int q = part + PARTS * i;
+        vals[i] = q < nb_grid ? __ldcg(gsrc + static_cast<size_t>(k) * nb_grid + q) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < PER; ++i) acc += vals[i];
+    }
+    __syncthreads();
+    // combine the PARTS partial sums of each value in a fixed order through shared memory
+    double* tmp = &s_red[0][0];           // NW * 2 * NPAIR doubles >= 2 * NPAIR * PARTS
+    if (k < 2 * NPAIR) tmp[k * PARTS + part] = acc;
+    __syncthreads();
+    if (tid < 2 * NPAIR) {
+      double t2 = 0.0;
+#pragma unroll
+      for (int i = 0; i < PARTS; ++i) t2 += tmp[tid * PARTS + i];
+      out_s[tid] = t2;
+    }
+    __syncthreads();
+  };
+
+  long long t_prev = clock64();
+  long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  __shared__ long long rrprof_acc[8];
+  if (tid < 8) rrprof_acc[tid] = 0;
+  __syncthreads();
+  const bool do_prof = a.prof != nullptr && b == 0 && tid == 0;
+  auto tick = [&](int slot) {
+    if (do_prof) {
+      const long long t = clock64();
+      prof_acc[slot] += t - t_prev;
+      t_prev = t;
+    }
+  };
+  for (; it < a.max_iters; ++it) {
+    // ---- phase 1: residual, forward aggregates -------------------------------------------
+    double loc[MAXM];
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) loc[c] = 0.0;
+    double A = 1.0, B[MAXM];
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) B[c] = 0.0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      if (valid[j]) {
+        A = -lf[j] * A;
+#pragma unroll
+        for (int c = 0; c < MAXM; ++c)
+          if (c < m) {
+            const double r = fma(-theta[c], x[j][c], ax[j][c]);
+            w[j][c] = r;
+            loc[c] += fabs(r);
+            B[c] = fma(-lf[j], B[c], r);
+          }
+      }
+    }
+    block_sum2(loc, a.pres);
+    block_scan_affine<false>(A, B, shA, shB);
+    s_incA[tid] = A;
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) s_incB[c][tid] = B[c];
+    if (tid == T - 1) {
+      a.fA[b] = A;
+#pragma unroll
+      for (int c = 0; c < MAXM; ++c) a.fB[static_cast<size_t>(c) * nb_grid + b] = B[c];
+    }
+    tick(0);
+    grid_barrier(a.barrier, epoch, nb_grid);
+    tick(6);
+    // ---- phase 2: convergence test, exact forward walk, backward aggregates ----------------
+    grid_sum2(a.pres, s_res);
+    res_out = s_res[0] / a.lnorm;
+    if (res_out < a.tol) { status = 0; break; }
+    cta_prefix(a.fA, a.fB, false);
+    double y[MAXM];
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c)
+      y[c] = tid == 0 ? s_in[c] : fma(s_incA[tid - 1], s_in[c], s_incB[c][tid - 1]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (valid[j]) {
+#pragma unroll
+        for (int c = 0; c < MAXM; ++c)
+          if (c < m) {
+            y[c] = fma(-lf[j], y[c], w[j][c]);
+            w[j][c] = y[c] * dp[j];  // z = y / d
+          }
+      }
+    A = 1.0;
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) B[c] = 0.0;
+#pragma unroll
+    for (int j = CH - 1; j >= 0; --j)
+      if (valid[j]) {
+        A = -lf_next[j] * A;
+#pragma unroll
+        for (int c = 0; c < MAXM; ++c)
+          if (c < m) B[c] = fma(-lf_next[j], B[c], w[j][c]);
+      }
+    block_scan_affine<true>(A, B, shA, shB);
+    s_incA[tid] = A;
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) s_incB[c][tid] = B[c];
+    if (tid == 0) {
+      a.bA[b] = A;
+#pragma unroll
+      for (int c = 0; c < MAXM; ++c) a.bB[static_cast<size_t>(c) * nb_grid + b] = B[c];
+    }
+    tick(1);
+    grid_barrier(a.barrier, epoch, nb_grid);
+    tick(6);
+    // ---- phase 3: exact backward walk -> W = M^-1 r, column sums ------------------------------
+    cta_prefix(a.bA, a.bB, true);
+    double xb[MAXM];
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c)
+      xb[c] = tid == T - 1 ? s_in[c] : fma(s_incA[tid + 1], s_in[c], s_incB[c][tid + 1]);
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) loc[c] = 0.0;
+#pragma unroll
+    for (int j = CH - 1; j >= 0; --j)
+      if (valid[j]) {
+#pragma unroll
+        for (int c = 0; c < MAXM; ++c)
+          if (c < m) {
+            xb[c] = fma(-lf_next[j], xb[c], w[j][c]);
+            w[j][c] = xb[c];
+            loc[c] += xb[c];
+            a.W[static_cast<size_t>(c) * ld + row0 + j] = xb[c];
+            if (kUseWCache) s_w[c * a.rpb + (row0 + j - r_lo_cta)] = xb[c];
+          }
+      }
+    block_sum2(loc, a.pcs);
+    tick(2);
+    grid_barrier(a.barrier, epoch, nb_grid);
+    tick(6);
+    // ---- phase 4: AW = L (W - mean), centre W, Gram partial sums ------------------------------
+    grid_sum2(a.pcs, s_mu);
+    tick(8);
+    double mu[MAXM];
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) mu[c] = c < m ? s_mu[c] / n : 0.0;
+    __syncthreads();
+    // W entries of this CTA's own row range (the odometry neighbours) come from shared memory,
+    // the rest (loop closures, range boundaries) from L2.  Branch-free: both loads are
+    // predicated so that a thread's remote gathers are all in flight together.
+    auto w_at = [&](int c, int col, bool on) -> double {
+      const bool loc = kUseWCache && col >= r_lo_cta && col < row_end;
+      const int li = loc ? col - r_lo_cta : 0;
+      const double vs = s_w[c * a.rpb + li];
+      double vg = 0.0;
+      if (on && !loc) vg = __ldcg(a.W + static_cast<size_t>(c) * ld + col);
+      return loc ? vs : vg;
+    };
+    {
+      // gathers of all rows of the thread are issued before any is consumed: the first two
+      // fixed entries (odometry neighbours) and the first active entry of each row are
+      // predicated, longer rows continue in the loops below
+      constexpr int PF = 2, PA = 1;
+      double gv[CH][PF + PA], gw[CH][PF + PA][MAXM];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+#pragma unroll
+        for (int e = 0; e < PF + PA; ++e) {
+          const int q = e < PF ? q0s[j] + e : q1s[j] + (e - PF);
+          const bool on = valid[j] && (e < PF ? q < q0e[j] : q < q1e[j]);
+          gv[j][e] = 0.0;
+          int col = 0;
+          if (on) {
+            gv[j][e] = e < PF ? V0[q] : V1[q];
+            col = e < PF ? C0[q] : C1[q];
+          }
+#pragma unroll
+          for (int c = 0; c < MAXM; ++c)
+            gw[j][e][c] = (on && c < m) ? w_at(c, col, on && c < m) : mu[c];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        if (valid[j]) {
+          double acc[MAXM];
+#pragma unroll
+          for (int c = 0; c < MAXM; ++c) acc[c] = 0.0;
+#pragma unroll
+          for (int e = 0; e < PF + PA; ++e)
+#pragma unroll
+            for (int c = 0; c < MAXM; ++c)
+              if (c < m) acc[c] = fma(gv[j][e], gw[j][e][c] - mu[c], acc[c]);
+          for (int q = q0s[j] + PF; q < q0e[j]; ++q) {
+            const double v = V0[q];
+            const int col = C0[q];
+#pragma unroll
+            for (int c = 0; c < MAXM; ++c)
+              if (c < m) acc[c] = fma(v, w_at(c, col, true) - mu[c], acc[c]);
+          }
+          for (int q = q1s[j] + PA; q < q1e[j]; ++q) {
+            const double v = V1[q];
+            const int col = C1[q];
+#pragma unroll
+            for (int c = 0; c < MAXM; ++c)
+              if (c < m) acc[c] = fma(v, w_at(c, col, true) - mu[c], acc[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < MAXM; ++c)
+            if (c < m) {
+              w[j][c] -= mu[c];
+              aw[j][c] = fma(dg[j], w[j][c], acc[c]);
+            }
+        }
+      }
+    }
+    tick(9);
+    const int nbas = have_p ? 3 : 2;
+    const int sdim = nbas * m;
+    {
+      // basis values of this thread's rows: S = [X | W | P], AS = [AX | AW | AP]
+      double v[CH][MAXS], av[CH][MAXS];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        // column order of the basis: b * m + c (b = 0 X, 1 W, 2 P); static register indices
+        static_assert(MAXM == 2 && MAXS == 6, "basis packing below is written for MAXM == 2");
+        const bool two = m == 2;
+        const double p0 = have_p ? p[j][0] : 0.0, p1 = have_p ? p[j][1] : 0.0;
+        const double ap0 = have_p ? ap[j][0] : 0.0, ap1 = have_p ? ap[j][1] : 0.0;
+        v[j][0] = x[j][0];                 av[j][0] = ax[j][0];
+        v[j][1] = two ? x[j][1] : w[j][0]; av[j][1] = two ? ax[j][1] : aw[j][0];
+        v[j][2] = two ? w[j][0] : p0;      av[j][2] = two ? aw[j][0] : ap0;
+        v[j][3] = two ? w[j][1] : 0.0;     av[j][3] = two ? aw[j][1] : 0.0;
+        v[j][4] = two ? p0 : 0.0;          av[j][4] = two ? ap0 : 0.0;
+        v[j][5] = two ? p1 : 0.0;          av[j][5] = two ? ap1 : 0.0;
+      }
+      int idx = 0;
+#pragma unroll
+      for (int k = 0; k < MAXS; ++k)
+#pragma unroll
+        for (int l = k; l < MAXS; ++l) {
+          double ga = 0.0, gb = 0.0;
+          if (l < sdim) {   // CTA-uniform
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+              ga = fma(v[j][k], av[j][l], ga);
+              gb = fma(v[j][k], v[j][l], gb);
+            }
+            ga = warp_sum(ga);
+            gb = warp_sum(gb);
+          }
+          if (lane == 0) {
+            s_red[warp][idx] = ga;
+            s_red[warp][NPAIR + idx] = gb;
+          }
+          ++idx;
+        }
+      __syncthreads();
+      if (tid < 2 * NPAIR) {
+        double acc = 0.0;
+        for (int k = 0; k < NW; ++k) acc += s_red[k][tid];
+        a.pgram[static_cast<size_t>(tid) * nb_grid + b] = acc;
+      }
+      __syncthreads();
+    }
+    tick(3);
+    grid_barrier(a.barrier, epoch, nb_grid);
+    tick(6);
+    // ---- phase 5: Rayleigh-Ritz (redundantly per CTA), basis update in registers --------------
+    grid_sum_gram(a.pgram, s_G);
+    tick(4);
+    if (tid < MAXS * MAXS) {
+      s_GA[tid] = 0.0;
+      s_GB[tid] = 0.0;
+    }
+    __syncthreads();
+    if (tid < 2 * NPAIR) {   // unpack the upper triangles
+      int idx = tid % NPAIR, k = 0, l = 0, run = 0;
+      for (int kk = 0; kk < MAXS; ++kk) {
+        if (idx < run + (MAXS - kk)) { k = kk; l = kk + (idx - run); break; }
+        run += MAXS - kk;
+      }
+      double* dst = tid < NPAIR ? s_GA : s_GB;
+      if (k < sdim && l < sdim) {
+        dst[k * MAXS + l] = s_G[tid];
+        dst[l * MAXS + k] = s_G[tid];
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int use = sdim;
+      bool ok = rr_warp(s_rr, sdim, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps, (a.prof && b == 0) ? rrprof_acc : nullptr);
+      if (!ok && have_p) {  // drop P (restart) and solve in span[X W]
+        use = 2 * m;
+        for (int e = lane; e < MAXS * MAXS; e += 32) {
+          const int i = e / MAXS, j = e % MAXS;
+          if (i >= use || j >= use) { s_GA[e] = 0.0; s_GB[e] = 0.0; }
+        }
+        __syncwarp();
+        ok = rr_warp(s_rr, use, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps);
+      }
+      if (lane == 0) s_ok = ok ? 1 : 0;
+      if (lane < MAXM) s_theta[lane] = lane < m ? s_th2[lane] : 0.0;
+      __syncwarp();
+    }
+    tick(5);
+    __syncthreads();
+    if (!s_ok) { status = 2; break; }  // W numerically inside span(X)
+    // X' = X C_x + P',  P' = W C_w + P C_p  (and the same for AX, AP); C_p = 0 when P is unused
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      double nx[MAXM], nax[MAXM], np_[MAXM], nap[MAXM];
+#pragma unroll
+      for (int c = 0; c < MAXM; ++c) {
+        nx[c] = nax[c] = np_[c] = nap[c] = 0.0;
+        if (c < m) {
+#pragma unroll
+          for (int k = 0; k < MAXM; ++k)
+            if (k < m) {
+              nx[c] = fma(x[j][k], s_C[k][c], nx[c]);
+              nax[c] = fma(ax[j][k], s_C[k][c], nax[c]);
+              np_[c] = fma(w[j][k], s_C[m + k][c], np_[c]);
+              nap[c] = fma(aw[j][k], s_C[m + k][c], nap[c]);
+              np_[c] = fma(p[j][k], s_C[2 * m + k][c], np_[c]);
+              nap[c] = fma(ap[j][k], s_C[2 * m + k][c], nap[c]);
+            }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < MAXM; ++c)
+        if (c < m) {
+          x[j][c] = nx[c] + np_[c];
+          ax[j][c] = nax[c] + nap[c];
+          p[j][c] = np_[c];
+          ap[j][c] = nap[c];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) theta[c] = s_theta[c];
+    have_p = true;
+    tick(4);
+    if (it % 50 == 49) {
+      // refresh AX = L X against drift: X through global memory
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (valid[j])
+#pragma unroll
+          for (int c = 0; c < MAXM; ++c)
+            if (c < m) a.X[static_cast<size_t>(c) * ld + row0 + j] = x[j][c];
+      grid_barrier(a.barrier, epoch, nb_grid);
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (valid[j]) {
+          const int i = row0 + j;
+          double acc[MAXM];
+#pragma unroll
+          for (int c = 0; c < MAXM; ++c) acc[c] = 0.0;
+          for (int q = q0s[j]; q < q0e[j]; ++q)
+#pragma unroll
+            for (int c = 0; c < MAXM; ++c)
+              if (c < m) acc[c] = fma(V0[q], __ldcg(a.X + static_cast<size_t>(c) * ld + C0[q]), acc[c]);
+          for (int q = q1s[j]; q < q1e[j]; ++q)
+#pragma unroll
+            for (int c = 0; c < MAXM; ++c)
+              if (c < m) acc[c] = fma(V1[q], __ldcg(a.X + static_cast<size_t>(c) * ld + C1[q]), acc[c]);
+          (void)i;
+#pragma unroll
+          for (int c = 0; c < MAXM; ++c)
+            if (c < m) ax[j][c] = fma(dg[j], x[j][c], acc[c]);
+        }
+    }
+  }
+  // ---- epilogue: X, AX, P, AP back to global (warm start of the next solve) --------------------
+#pragma unroll
+  for (int j = 0; j < CH; ++j)
+    if (valid[j])
+#pragma unroll
+      for (int c = 0; c < MAXM; ++c)
+        if (c < m) {
+          const size_t o = static_cast<size_t>(c) * ld + row0 + j;
+          a.X[o] = x[j][c];
+          a.AX[o] = ax[j][c];
+          a.P[o] = p[j][c];
+          a.AP[o] = ap[j][c];
+        }
+  if (do_prof) {
+    for (int k = 0; k < 8; ++k) a.prof[k] += prof_acc[k];
+    for (int k = 0; k < 5; ++k) a.prof[8 + k] += rrprof_acc[k];
+    a.prof[13] += it;
+    a.prof[14] += prof_acc[8];
+    a.prof[15] += prof_acc[9];
+  }
+  if (b == 0 && tid == 0) {
+    for (int c = 0; c < MAXM; ++c) a.out[c] = theta[c];
+    a.out[MAXM] = static_cast<double>(it);
+    a.out[MAXM + 1] = static_cast<double>(status);
+    a.out[MAXM + 2] = res_out;
+  }
 }
 
 // ------------------------------------------------------------------ solver object
@@ -933,6 +1840,18 @@ struct FiedlerSolver {
   int T = 0;       // chunks
   int nblk = 0;    // 256-thread blocks over n
   int nblk_t = 0;  // 256-thread blocks over T
+  // persistent solver (k_lobpcg_persist)
+  double *pfA = nullptr, *pfB = nullptr, *pbA = nullptr, *pbB = nullptr;
+  double *ppres = nullptr, *ppcs = nullptr, *ppgram = nullptr, *pout = nullptr;
+  int num_sms = 0;
+  int persist_variant = -1;   // -1 auto, 0 off (multi-kernel path), else rows per thread
+  int last_path = 0;          // 1 = persistent kernel ran
+  unsigned int* pbar = nullptr;
+  cudaEvent_t pev0 = nullptr, pev1 = nullptr;   // around every k_lobpcg_persist launch
+  double persist_ms = 0.0;                      // summed CUDA-event durations
+  int64_t persist_launches = 0, persist_iters = 0, persist_bytes = 0;
+  double t_prepare = 0, t_prologue = 0, t_loop = 0;   // CSLAM_MAC_PROF
+  long long* pprof = nullptr; // cycle counters (CSLAM_LOBPCG_PROF=1)
   bool warm = false;
   double lnorm = 0.0;
   int last_iters = 0;
@@ -975,13 +1894,129 @@ struct FiedlerSolver {
     CSLAM_TRY(dev_alloc(&red, 2 * NPAIR + 4 * MAXM + 4));
     CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_red), (2 * NPAIR + 4 * MAXM + 4) * sizeof(double)));
     CSLAM_TRY(dev_alloc(&d_bad, 1));
+    int coop = 0;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if (!coop) persist_variant = 0;
+    if (const char* e = getenv("CSLAM_LOBPCG_VARIANT")) persist_variant = atoi(e);
+    const size_t g = static_cast<size_t>(std::max(num_sms, 1));
+    CSLAM_TRY(dev_alloc(&pfA, g));
+    CSLAM_TRY(dev_alloc(&pfB, MAXM * g));
+    CSLAM_TRY(dev_alloc(&pbA, g));
+    CSLAM_TRY(dev_alloc(&pbB, MAXM * g));
+    CSLAM_TRY(dev_alloc(&ppres, MAXM * g));
+    CSLAM_TRY(dev_alloc(&ppcs, MAXM * g));
+    CSLAM_TRY(dev_alloc(&ppgram, 2 * NPAIR * g));
+    CSLAM_TRY(dev_alloc(&pout, MAXM + 4));
+    CSLAM_TRY(dev_alloc(&pbar, 1));
+    if (getenv("CSLAM_LOBPCG_PROF")) {
+      CSLAM_TRY(dev_alloc(&pprof, 16));
+      CSLAM_CUDA(cudaMemsetAsync(pprof, 0, 16 * sizeof(long long), stream));
+    }
+    return CSLAM_OK;
+  }
+
+  static int persist_threads(int ch) {
+    return ch == 1 ? 1024 : ch == 2 ? 512 : (ch == 4 || ch == 8) ? 256 : 0;
+  }
+  // rows per thread of the persistent kernel for this problem size (0 = not applicable)
+  int persist_rows_per_thread() const {
+    if (persist_variant == 0 || num_sms <= 0 || num_sms > 192) return 0;   // MAXG in the kernel
+    const int64_t rows = (static_cast<int64_t>(n) + num_sms - 1) / num_sms;
+    if (persist_variant > 0) {
+      const int t = persist_threads(persist_variant);
+      return (t > 0 && rows <= static_cast<int64_t>(t) * persist_variant) ? persist_variant : 0;
+    }
+    if (rows <= 256 * 4) return 4;
+    if (rows <= 256 * 8) return 8;
+    return 0;
+  }
+
+  // LOBPCG main loop in one cooperative kernel; theta in/out, *iters, *status out
+  int persist_loop(int ch, double tol, int max_iters, double* theta, bool have_p, int* iters,
+                   int* status) {
+    PersistArgs pa;
+    pa.n = n;
+    pa.m = m;
+    pa.ld = ld;
+    const int rows = (n + num_sms - 1) / num_sms;
+    pa.rpb = (rows + ch - 1) / ch * ch;
+    pa.ip0 = fix.indptr; pa.c0 = fix.cols; pa.v0 = fix.vals;
+    pa.ip1 = has_act ? act.indptr : nullptr; pa.c1 = act.cols; pa.v1 = act.vals;
+    pa.diag = diag; pa.dpiv = dpiv; pa.lfac = lfac;
+    pa.X = X; pa.AX = AX; pa.W = W; pa.P = P; pa.AP = AP;
+    pa.fA = pfA; pa.fB = pfB; pa.bA = pbA; pa.bB = pbB;
+    pa.pres = ppres; pa.pcs = ppcs; pa.pgram = ppgram;
+    for (int c = 0; c < MAXM; ++c) pa.theta0[c] = theta[c];
+    pa.tol = tol;
+    pa.lnorm = lnorm;
+    pa.max_iters = max_iters;
+    pa.have_p = have_p ? 1 : 0;
+    pa.out = pout;
+    pa.barrier = pbar;
+    CSLAM_CUDA(cudaMemsetAsync(pbar, 0, sizeof(unsigned int), stream));
+    pa.prof = pprof;
+    void* args[] = {&pa};
+    const void* fn = nullptr;
+    int threads = 0;
+    switch (ch) {
+      case 1: fn = reinterpret_cast<const void*>(&k_lobpcg_persist<1, 1024>); threads = 1024; break;
+      case 2: fn = reinterpret_cast<const void*>(&k_lobpcg_persist<2, 512>); threads = 512; break;
+      case 4: fn = reinterpret_cast<const void*>(&k_lobpcg_persist<4, 256>); threads = 256; break;
+      case 8: fn = reinterpret_cast<const void*>(&k_lobpcg_persist<8, 256>); threads = 256; break;
+      default: set_error("fiedler: bad persistent variant %d", ch); return CSLAM_ERR_INVALID;
+    }
+    pa.cap0 = pa.cap1 = 6144;
+    pa.rr_sweeps = getenv("CSLAM_RR_SWEEPS") ? atoi(getenv("CSLAM_RR_SWEEPS")) : 3;
+    const size_t dyn = static_cast<size_t>(pa.cap0 + pa.cap1) * (sizeof(double) + sizeof(int)) +
+                       static_cast<size_t>(MAXM) * pa.rpb * sizeof(double);
+    CSLAM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+    if (!pev0) {
+      CSLAM_CUDA(cudaEventCreate(&pev0));
+      CSLAM_CUDA(cudaEventCreate(&pev1));
+    }
+    CSLAM_CUDA(cudaEventRecord(pev0, stream));
+    CSLAM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms), dim3(threads), args, dyn, stream));
+    CSLAM_CUDA(cudaEventRecord(pev1, stream));
+    count_launch();
+    CSLAM_CUDA(cudaMemcpyAsync(h_red, pout, (MAXM + 3) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaStreamSynchronize(stream));
+    for (int c = 0; c < MAXM; ++c) theta[c] = h_red[c];
+    *iters = static_cast<int>(h_red[MAXM]);
+    *status = static_cast<int>(h_red[MAXM + 1]);
+    spmv_count += static_cast<int64_t>(*iters) * m;
+    {
+      float ms = 0.f;
+      CSLAM_CUDA(cudaEventElapsedTime(&ms, pev0, pev1));
+      persist_ms += ms;
+      persist_launches += 1;
+      persist_iters += *iters;
+      // one SpMM per iteration reads nnz*(8+4) + n*4 and moves m*n*16
+      const int64_t nnz = fix.nnz + (has_act ? act.nnz : 0);
+      persist_bytes += static_cast<int64_t>(*iters) * (nnz * 12 + static_cast<int64_t>(n) * 4 +
+                                                       static_cast<int64_t>(m) * n * 16);
+    }
     return CSLAM_OK;
   }
 
   void release() {
     for (double** p : {&diag, &sup, &rowabs, &dpiv, &lfac, &X, &AX, &W, &AW, &P, &AP, &aggA, &aggB,
-                       &bagA, &bagB, &blkA, &blkB, &rblkA, &rblkB, &part, &red})
+                       &bagA, &bagB, &blkA, &blkB, &rblkA, &rblkB, &part, &red, &pfA, &pfB, &pbA,
+                       &pbB, &ppres, &ppcs, &ppgram, &pout})
       dev_free(*p);
+    if (pprof) {
+      long long hp[16] = {};
+      cudaMemcpy(hp, pprof, sizeof(hp), cudaMemcpyDeviceToHost);
+      const double it_ = static_cast<double>(std::max<long long>(hp[13], 1));
+      fprintf(stderr, "[cslam lobpcg prof] cycles/iter over %lld iters: p1 %.0f p2 %.0f p3 %.0f p4 %.0f p5 %.0f rr %.0f barriers %.0f | rr: setup %.0f chol %.0f tri %.0f jacobi %.0f back %.0f | p4: gridsum %.0f spmm %.0f (gram = p4)\n",
+              hp[13], hp[0] / it_, hp[1] / it_, hp[2] / it_, hp[3] / it_, hp[4] / it_, hp[5] / it_, hp[6] / it_,
+              hp[8] / it_, hp[9] / it_, hp[10] / it_, hp[11] / it_, hp[12] / it_, hp[14] / it_, hp[15] / it_);
+      dev_free(pprof);
+    }
+    dev_free(pbar);
+    if (pev0) cudaEventDestroy(pev0);
+    if (pev1) cudaEventDestroy(pev1);
+    pev0 = pev1 = nullptr;
     dev_free(fagg);
     dev_free(d_bad);
     if (h_red) cudaFreeHost(h_red);
@@ -1040,7 +2075,8 @@ struct FiedlerSolver {
                                          has_act ? act.indptr : nullptr, act.cols, act.vals, diag,
                                          sup, rowabs);
     CSLAM_LAUNCH_CHECK();
-    k_max_reduce<<<1, 1024, 0, stream>>>(rowabs, n, red);
+    CSLAM_CUDA(cudaMemsetAsync(red, 0, sizeof(double), stream));
+    k_max_reduce<<<std::min(64, (n + 2047) / 2048), 256, 0, stream>>>(rowabs, n, red);
     CSLAM_LAUNCH_CHECK();
     CSLAM_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), stream));
     k_fac_a<<<nblk_t, 256, 0, stream>>>(n, diag, sup, fagg);
@@ -1148,7 +2184,15 @@ struct FiedlerSolver {
 
   // Solve for the Fiedler pair of the current matrix.  X keeps the result (column 0).
   int solve(double tol, int max_iters, double* lambda2) {
+    const bool prof = getenv("CSLAM_MAC_PROF") != nullptr;
+    auto now = [&]() {
+      if (prof) cudaStreamSynchronize(stream);
+      return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    const double tp0 = prof ? now() : 0;
     CSLAM_TRY(prepare_matrix());
+    const double tp1 = prof ? now() : 0;
+    t_prepare += tp1 - tp0;
     if (n < 2) {
       set_error("fiedler: need at least 2 vertices");
       return CSLAM_ERR_INVALID;
@@ -1180,6 +2224,23 @@ struct FiedlerSolver {
     }
     bool have_p = false;
     int it = 0;
+    last_path = 0;
+    const double tp2 = prof ? now() : 0;
+    t_prologue += tp2 - tp1;
+    if (const int ch = persist_rows_per_thread()) {
+      int status = 1;
+      CSLAM_TRY(persist_loop(ch, tol, max_iters, theta, false, &it, &status));
+      if (prof) t_loop += now() - tp2;
+      last_path = 1;
+      last_iters = it;
+      if (status == 1) {
+        set_error("fiedler: LOBPCG did not reach tol %.1e in %d iterations", tol, max_iters);
+        return CSLAM_ERR_NOCONV;
+      }
+      *lambda2 = theta[0];
+      warm = true;
+      return CSLAM_OK;
+    }
     for (; it < max_iters; ++it) {
       Theta th;
       for (int c = 0; c < MAXM; ++c) th.v[c] = theta[c];
@@ -1352,13 +2413,15 @@ namespace cslam {
 namespace {
 
 int mac_set_active(cslam_mac* h, const std::vector<int>& support) {
-  // connectivity of fixed + active edges (reference: singular factorisation -> exception)
-  UnionFind uf(h->n);
-  int comps = h->n;
-  for (int64_t e = 0; e < h->nf; ++e)
-    if (uf.unite(h->fi[e], h->fj[e])) --comps;
-  for (int e : support)
-    if (uf.unite(h->ci[e], h->cj[e])) --comps;
+  // connectivity of fixed + active edges (reference: singular factorisation -> exception).
+  // The components of the fixed graph are computed once (mac_create); here only the
+  // active edges are merged over those component labels.
+  int comps = h->fixed_components;
+  if (comps > 1) {
+    UnionFind uf(h->fixed_components);
+    for (int e : support)
+      if (uf.unite(h->fixed_root[h->ci[e]], h->fixed_root[h->cj[e]])) --comps;
+  }
   if (comps != 1) {
     set_error("Laplacian is singular: graph of fixed + selected edges has %d connected components",
               comps);
@@ -1473,6 +2536,21 @@ int cslam_mac_create(int num_poses, int64_t n_fixed, const int32_t* fi, const in
     st = h->fs.upload(h->fs.fix, indptr, cols, nullptr, &vals);
     if (st != CSLAM_OK) return fail(st);
   }
+  {
+    // connected components of the fixed graph, labelled 0..c-1
+    UnionFind uf(h->n);
+    h->fixed_components = h->n;
+    for (int64_t e = 0; e < n_fixed; ++e)
+      if (uf.unite(h->fi[e], h->fj[e])) --h->fixed_components;
+    h->fixed_root.assign(static_cast<size_t>(h->n), 0);
+    std::vector<int> label(static_cast<size_t>(h->n), -1);
+    int next = 0;
+    for (int v = 0; v < h->n; ++v) {
+      const int r = uf.find(v);
+      if (label[r] < 0) label[r] = next++;
+      h->fixed_root[v] = label[r];
+    }
+  }
   const size_t mc = static_cast<size_t>(std::max<int64_t>(n_cand, 1));
   h->sel_per_block = 4096;
   h->sel_blocks = static_cast<int>((mc + h->sel_per_block - 1) / h->sel_per_block);
@@ -1581,11 +2659,22 @@ int cslam_mac_fw_subset(cslam_mac_t* h, const double* w_init, int k, int max_ite
   int it = 0;
   bool gap_reached = false;
   const int blocks_m = static_cast<int>((mc + 255) / 256);
+  const bool prof = getenv("CSLAM_MAC_PROF") != nullptr;
+  double t_act = 0, t_solve = 0, t_sel = 0, t_host = 0;
+  auto now = [&]() {
+    if (prof) cudaStreamSynchronize(s);
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  };
   for (; it < max_iters; ++it) {
     // f_i, vec_i = evaluate_fiedler_pair(w_i)                               (mac.py:211)
+    double t0 = prof ? now() : 0;
     CSLAM_TRY(mac_set_active(h, support));
     double f = 0.0;
+    double t1 = prof ? now() : 0;
     CSLAM_TRY(h->fs.solve(h->tol, h->max_lobpcg_iters, &f));
+    double t2 = prof ? now() : 0;
+    t_act += t1 - t0;
+    t_solve += t2 - t1;
     h->total_lobpcg_iters += h->fs.last_iters;
     // grad_i = grad_from_fiedler(vec_i)                                     (mac.py:212)
     k_grad<<<blocks_m, 256, 0, s>>>(mc, h->d_ci, h->d_cj, h->d_cw, h->fs.X, h->d_g);
@@ -1602,6 +2691,8 @@ int cslam_mac_fw_subset(cslam_mac_t* h, const double* w_init, int k, int max_ite
     if (k > 0)
       CSLAM_CUDA(cudaMemcpyAsync(slist.data(), h->d_slist, k * sizeof(int), cudaMemcpyDeviceToHost, s));
     CSLAM_CUDA(cudaStreamSynchronize(s));
+    double t3 = prof ? now() : 0;
+    t_sel += t3 - t2;
     u = std::min(u, f + dual);
     if (trace_f) trace_f[it] = f;
     if (trace_sel)
@@ -1624,7 +2715,11 @@ int cslam_mac_fw_subset(cslam_mac_t* h, const double* w_init, int k, int max_ite
         support.push_back(slist[t]);
       }
     std::sort(support.begin(), support.end());
+    if (prof) t_host += now() - t3;
   }
+  if (prof)
+    fprintf(stderr, "[cslam mac prof] set_active %.2f ms, solve %.2f ms (prepare %.2f, prologue %.2f, loop %.2f), grad+topk+dual %.2f ms, host update %.2f ms\n",
+            t_act, t_solve, h->fs.t_prepare, h->fs.t_prologue, h->fs.t_loop, t_sel, t_host);
   (void)gap_reached;
   if (iters_out) *iters_out = it + (gap_reached ? 1 : 0);
   CSLAM_CUDA(cudaMemcpyAsync(w_out, h->d_w, mc * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1656,6 +2751,16 @@ int cslam_mac_fw_subset(cslam_mac_t* h, const double* w_init, int k, int max_ite
     std::partial_sort(keys.begin(), keys.begin() + k, keys.end(), better);
     for (int t = 0; t < k; ++t) rounded_out[keys[t].e] = 1.0;
   }
+  return CSLAM_OK;
+}
+
+int cslam_mac_solver_timing(cslam_mac_t* h, double* kernel_ms, int64_t* launches, int64_t* iterations,
+                            int64_t* algorithmic_bytes) {
+  CSLAM_REQUIRE(h, "mac_solver_timing: NULL handle");
+  if (kernel_ms) *kernel_ms = h->fs.persist_ms;
+  if (launches) *launches = h->fs.persist_launches;
+  if (iterations) *iterations = h->fs.persist_iters;
+  if (algorithmic_bytes) *algorithmic_bytes = h->fs.persist_bytes;
   return CSLAM_OK;
 }
 

@@ -191,11 +191,20 @@ class GlobalDescriptorLoopClosureDetection(object):
                 self.receive_keyframe(m)
             return []
         images = [image_from_msg(m.image) for m in keyframe_msgs]
+        import torch
         if hasattr(images[0], "is_cuda"):
-            import torch
             batch = torch.stack(images)
         else:
-            batch = np.stack(images)
+            # gather the images in a persistent pinned buffer: one asynchronous H2D copy
+            shape = (len(images),) + tuple(images[0].shape)
+            buf = getattr(self, "_pinned_images", None)
+            if buf is None or tuple(buf.shape[1:]) != shape[1:] or buf.shape[0] < shape[0]:
+                buf = torch.empty(shape, dtype=torch.uint8).pin_memory()
+                self._pinned_images = buf
+            view = buf[:shape[0]].numpy()
+            for b, img in enumerate(images):
+                view[b] = img
+            batch = buf[:shape[0]]
         emb = self.global_descriptor.compute_embeddings_device(batch)
         return self.add_global_descriptors_to_map(emb, [m.id for m in keyframe_msgs])
 

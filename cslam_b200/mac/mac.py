@@ -75,6 +75,15 @@ class MAC:
         _lib.check(_lib.load().cslam_mac_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return {"lobpcg_iters": a.value, "spmv_columns": b.value, "jacobi_fallback": bool(c.value)}
 
+    def solver_timing(self):
+        """Cumulative CUDA-event time / launches / iterations / algorithmic bytes of the
+        persistent eigen-solver kernel (for the bench roofline)."""
+        ms, a, b, c = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(_lib.load().cslam_mac_solver_timing(self._h, ctypes.byref(ms), ctypes.byref(a),
+                                                       ctypes.byref(b), ctypes.byref(c)))
+        return {"kernel_ms": ms.value, "launches": a.value, "iterations": b.value,
+                "algorithmic_bytes": c.value}
+
     # ---- reference API -----------------------------------------------------
     @property
     def L_odom(self):

@@ -89,4 +89,4 @@ def as_uint8_cuda(keyframes, device):
         return t.to(device, non_blocking=True)
     if keyframes.dim() == 3:
         keyframes = keyframes[None]
-    return keyframes.to(device)
+    return keyframes.to(device, non_blocking=True)   # async when the source is pinned

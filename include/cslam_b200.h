@@ -152,6 +152,12 @@ int cslam_mac_fw_subset(cslam_mac_t* h, const double* w_init, int k, int max_ite
  * solve had to fall back from the tridiagonal to the diagonal preconditioner. */
 int cslam_mac_stats(cslam_mac_t* h, int64_t* lobpcg_iters, int64_t* spmv_columns,
                     int* jacobi_fallback);
+/* Totals since creation for the persistent eigen-solver kernel (k_lobpcg_persist): summed
+ * CUDA-event durations of its launches on the handle's stream, launches, LOBPCG iterations and
+ * the algorithmic bytes of those iterations (one SpMM each: nnz*12 + n*4 + m*n*16, SURVEY.md
+ * section 8d).  Used by bench.py for the roofline entry. */
+int cslam_mac_solver_timing(cslam_mac_t* h, double* kernel_ms, int64_t* launches,
+                            int64_t* iterations, int64_t* algorithmic_bytes);
 /* find_fiedler_pair(L)  (mac.py:35-59) for a caller-assembled CSR Laplacian (host
  * arrays, int32 indices, float64 data; the diagonal entries are ignored and rebuilt as
  * minus the row sums of the off-diagonals). */

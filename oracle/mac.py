@@ -86,6 +86,16 @@ class MACOracle:
         self.weights = np.array([e.weight for e in candidate_measurements])
         self.edge_list = np.array([(e.i, e.j) for e in candidate_measurements])
 
+    @classmethod
+    def from_arrays(cls, fixed, cand, num_poses):
+        """Same object from (i, j, weight) array triples (large synthetic graphs)."""
+        self = cls.__new__(cls)
+        self.L_odom = laplacian_from_arrays(*fixed, num_poses)
+        self.num_poses = num_poses
+        self.weights = np.asarray(cand[2], dtype=np.float64)
+        self.edge_list = np.stack([cand[0], cand[1]], axis=1)
+        return self
+
     def find_fiedler_pair(self, L, method='tracemin_lu', tol=1e-8):
         return tracemin_fiedler_lu(L, tol=tol, seed=7)  # mac.py:52-58
 

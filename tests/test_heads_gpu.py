@@ -121,3 +121,23 @@ def test_netvlad_end_to_end_embedding():
         ref = heads.netvlad_embedding(imgs[i], 376, encoder, sd, (comp, mean, ev, True))
         assert np.abs(out[i] - ref).max() < 1e-3
         assert np.dot(out[i], ref) > 0.9999
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("tf32", None), ("bf16", None)])
+def test_backbone_precision_modes(precision, tol):
+    """fp32 (the default, strict cuDNN/cuBLAS math) must meet the 1e-3 descriptor bound of
+    north_star; tf32 / bf16 are opt-in and their deviation is only reported (pytest -s)."""
+    from cslam_b200.vpr.cosplace import CosPlace
+    trunk, sd = heads.build_cosplace_modules(seed=0, backbone="resnet18", dim=512)
+    params = {'frontend.nn_checkpoint': 'synthetic', 'frontend.image_crop_size': 376,
+              'frontend.cosplace.descriptor_dim': 512, 'frontend.cosplace.backbone': 'resnet18',
+              'frontend.backbone_precision': precision}
+    net = CosPlace(params, None, state_dict=sd)
+    imgs = np.stack([keyframe_image(40 + i) for i in range(4)])
+    out = net.compute_embeddings(imgs)
+    ref = np.stack([heads.cosplace_embedding(im, 376, trunk, sd) for im in imgs])
+    err = float(np.abs(out - ref).max())
+    cos = float(np.min(np.sum(out * ref, axis=1)))
+    print(f"\n[precision {precision}] max|d| {err:.3e}  min cosine {cos:.7f}")
+    if tol is not None:
+        assert err < tol and cos > 0.9999

@@ -608,7 +608,8 @@ struct cslam_nns {
   float* d_data = nullptr;
   __half* d_shadow = nullptr;
   float* d_vv = nullptr;
-  TensorMapBlob tmap_p;
+  TensorMapBlob tmap_p[3];   // pool tile maps with box rows 256, 128, 64 (cluster size 1, 2, 4)
+  int max_clusters[3] = {0, 0, 0};   // co-resident clusters of size 1, 2, 4
   cudaStream_t stream = nullptr;
 
   // host -> device staging for add_host
@@ -687,7 +688,8 @@ int nns_reserve_rows(cslam_nns* h, int64_t need) {
   h->d_shadow = ns;
   h->d_vv = nv;
   h->cap = ncap;
-  CSLAM_TRY(make_fp16_rowmajor_tmap(&h->tmap_p, h->d_shadow, h->cap, h->dim_pad, kCoarseBN));
+  for (int c = 0; c < 3; ++c)
+    CSLAM_TRY(make_fp16_rowmajor_tmap(&h->tmap_p[c], h->d_shadow, h->cap, h->dim_pad, kCoarseBN >> c));
   return CSLAM_OK;
 }
 
@@ -730,42 +732,57 @@ int nns_reserve_queries(cslam_nns* h, int nq, int k) {
     CSLAM_TRY(make_fp16_rowmajor_tmap(&h->tmap_q, h->d_qh, need, h->dim_pad, kCoarseBM));
   }
   if (!h->d_tau) {
-    CSLAM_TRY(dev_alloc(&h->d_tau, kCoarseBM));
-    CSLAM_TRY(dev_alloc(&h->d_flags, kCoarseBM));
-    CSLAM_TRY(dev_alloc(&h->d_sel_rows, static_cast<size_t>(kCoarseBM) * kRerankMax));
-    CSLAM_TRY(dev_alloc(&h->d_sel_cnt, kCoarseBM));
-    CSLAM_TRY(dev_alloc(&h->d_sel_sims, static_cast<size_t>(kCoarseBM) * kRerankMax));
-    CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), 2 * kCoarseBM * sizeof(int)));
+    CSLAM_TRY(dev_alloc(&h->d_tau, kGroupMax));
+    CSLAM_TRY(dev_alloc(&h->d_flags, kGroupMax));
+    CSLAM_TRY(dev_alloc(&h->d_sel_rows, static_cast<size_t>(kGroupMax) * kRerankMax));
+    CSLAM_TRY(dev_alloc(&h->d_sel_cnt, kGroupMax));
+    CSLAM_TRY(dev_alloc(&h->d_sel_sims, static_cast<size_t>(kGroupMax) * kRerankMax));
+    CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), 2 * kGroupMax * sizeof(int)));
   }
   (void)k;
   return CSLAM_OK;
 }
 
-// One query tile (<= kCoarseBM queries starting at q0) through candidate
-// generation + re-rank.  `exact` selects the fp64 scan instead of the tensor
-// cores.  Results land in out_idx/out_sims (device, [*, k], already offset).
+// One query GROUP (nqt <= kGroupMax queries starting at q0; <= kCoarseBM for the exact scan)
+// through candidate generation + re-rank.  Groups wider than one tile run the tensor-core
+// pass as clusters of 2 or 4 CTAs that share every pool tile (TMA multicast), so the pool is
+// swept once per group.  `exact` selects the fp64 scan instead of the tensor cores.  Results
+// land in out_idx/out_sims (device, [*, k], already offset).
 int nns_run_tile(cslam_nns* h, int q0, int nqt, int k, bool exact, int32_t* out_idx,
                  double* out_sims, cudaStream_t s, bool time_it) {
   const int n_rows = static_cast<int>(h->n);
   const int num_tiles = (n_rows + kCoarseBN - 1) / kCoarseBN;
   const bool exhaustive = n_rows <= h->sample_rows;
   const int sample_tiles = h->sample_rows / kCoarseBN;
-  // dump passes (tau = -inf, small pools) give every CTA exactly one tile, i.e. each
-  // sub-segment exactly kSegCap entries; the filtered pass runs one CTA per SM.
+  const int q_tiles = (nqt + kCoarseBM - 1) / kCoarseBM;
+  int cl = exact ? 0 : (q_tiles <= 1 ? 0 : (q_tiles <= 2 ? 1 : 2));   // log2(cluster size)
+  const int C = 1 << cl;
+  CSLAM_REQUIRE(nqt <= (exact ? kCoarseBM : kGroupMax), "nns: query group of %d too wide", nqt);
+  if (!exact && h->max_clusters[cl] == 0) {
+    if (C == 1) h->max_clusters[0] = h->num_sms;
+    else CSLAM_TRY(coarse_tc_max_clusters(C, &h->max_clusters[cl]));
+    CSLAM_REQUIRE(h->max_clusters[cl] > 0, "nns: no co-resident cluster of %d CTAs", C);
+    if (getenv("CSLAM_NNS_DEBUG"))
+      fprintf(stderr, "[cslam nns] cluster size %d: %d co-resident clusters (%d SMs)\n", C,
+              h->max_clusters[cl], h->num_sms);
+  }
+  const int resident = exact ? h->num_sms : h->max_clusters[cl];   // clusters (C = 1: CTAs)
+  // dump passes (tau = -inf, small pools) give every cluster exactly one tile, i.e. each
+  // sub-segment exactly kSegCap entries; the filtered pass runs as many clusters as fit.
   const int max_grid = std::max(h->num_sms, sample_tiles);
   const int nsub_needed = 2 * max_grid;
   if (nsub_needed > h->nsub) {
     CSLAM_REQUIRE(nsub_needed <= kMaxSub, "nns: %d sub-segments exceed the limit %d", nsub_needed,
                   kMaxSub);
     CSLAM_CUDA(cudaStreamSynchronize(s));
-    CSLAM_TRY(h->cand.reserve(cand_slots(nsub_needed) * kCoarseBM));
+    CSLAM_TRY(h->cand.reserve(cand_slots(nsub_needed) * kGroupMax));
     dev_free(h->d_cnt);
-    CSLAM_TRY(dev_alloc(&h->d_cnt, static_cast<size_t>(kCoarseBM) * (nsub_needed + 1)));
+    CSLAM_TRY(dev_alloc(&h->d_cnt, static_cast<size_t>(kGroupMax) * (nsub_needed + 1)));
     h->nsub = nsub_needed;
   }
   const int smax_stride = sample_tiles * (kCoarseBN / kChunk);
   CSLAM_REQUIRE(smax_stride <= kTauMax, "nns: sample_rows too large");
-  CSLAM_TRY(h->smax.reserve(static_cast<size_t>(kCoarseBM) * smax_stride));
+  CSLAM_TRY(h->smax.reserve(static_cast<size_t>(kGroupMax) * smax_stride));
   // fp16 rounding of both unit-norm operands (2 * 2^-11), fp32 accumulation over
   // dim_pad terms, fp16 subnormal flush; exact scan only rounds the score to fp32.
   const float eps = exact ? 1.0e-6f
@@ -778,11 +795,21 @@ int nns_run_tile(cslam_nns* h, int q0, int nqt, int k, bool exact, int32_t* out_
   cp.n_rows = n_rows;
   cp.nq = nqt;
   cp.q_row0 = q0;
+  cp.cluster = C;
+  cp.l2_prefetch = getenv("CSLAM_NNS_PF") ? atoi(getenv("CSLAM_NNS_PF")) : (C > 1 ? 3 : 0);
+  cp.a_resident = (C > 1 && h->dim_pad <= 512 && !getenv("CSLAM_NNS_NO_ARES")) ? 1 : 0;
   cp.cnt = h->d_cnt;
   cp.cand = h->cand.p;
   cp.nsub = h->nsub;
   cp.smax = h->smax.p;
   cp.smax_stride = smax_stride;
+  cp.dbg = nullptr;
+  static long long* s_dbg = nullptr;
+  if (getenv("CSLAM_NNS_DEBUG")) {
+    if (!s_dbg) { cudaMalloc(&s_dbg, 8 * sizeof(long long)); }
+    cudaMemsetAsync(s_dbg, 0, 8 * sizeof(long long), s);
+    cp.dbg = s_dbg;
+  }
 
   auto launch_coarse = [&](int mode, int tiles, int stride, const float* tau, bool timed) -> int {
     cp.mode = mode;
@@ -791,20 +818,21 @@ int nns_run_tile(cslam_nns* h, int q0, int nqt, int k, bool exact, int32_t* out_
     cp.tau = tau;
     if (mode == 0) {
       CSLAM_CUDA(cudaMemsetAsync(
-          h->d_cnt, 0, static_cast<size_t>(kCoarseBM) * (h->nsub + 1) * sizeof(unsigned int), s));
+          h->d_cnt, 0, static_cast<size_t>(nqt) * (h->nsub + 1) * sizeof(unsigned int), s));
     } else if (exact) {
       CSLAM_CUDA(cudaMemsetAsync(h->smax.p, 0,
-                                 static_cast<size_t>(kCoarseBM) * smax_stride * sizeof(uint32_t),
+                                 static_cast<size_t>(nqt) * smax_stride * sizeof(uint32_t),
                                  s));
     }
     if (timed) CSLAM_CUDA(cudaEventRecord(h->ev_c0, s));
-    // unfiltered passes: one tile per CTA; filtered full pass: persistent, one CTA per SM
-    const int grid = tau == nullptr ? std::min(tiles, max_grid) : std::min(tiles, h->num_sms);
+    // unfiltered passes: one tile per cluster; filtered full pass: persistent, one cluster per
+    // co-resident slot
+    const int clusters = tau == nullptr ? std::min(tiles, max_grid) : std::min(tiles, resident);
     if (exact) {
-      k_nns_coarse_exact<<<grid, 256, 0, s>>>(h->d_data, h->d_vv, h->dim, h->d_q64, h->d_uu, cp);
+      k_nns_coarse_exact<<<clusters, 256, 0, s>>>(h->d_data, h->d_vv, h->dim, h->d_q64, h->d_uu, cp);
       CSLAM_LAUNCH_CHECK();
     } else {
-      CSLAM_TRY(launch_coarse_tc(&h->tmap_q, &h->tmap_p, cp, grid, s));
+      CSLAM_TRY(launch_coarse_tc(&h->tmap_q, &h->tmap_p[cl], cp, clusters * C, s));
     }
     if (timed) CSLAM_CUDA(cudaEventRecord(h->ev_c1, s));
     h->last_coarse_launches++;
@@ -829,6 +857,13 @@ int nns_run_tile(cslam_nns* h, int q0, int nqt, int k, bool exact, int32_t* out_
     CSLAM_TRY(launch_coarse(0, num_tiles, 1, tau, time_it));
   }
 
+  if (cp.dbg) {
+    long long hd[8];
+    cudaMemcpyAsync(hd, cp.dbg, sizeof(hd), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    fprintf(stderr, "[cslam nns] CTA0 cycles: producer wait-empty %lld | mma wait-full %lld wait-acc %lld | epilogue wait-acc %lld scan %lld | tiles %lld\n",
+            hd[0], hd[1], hd[2], hd[3], hd[4], hd[5]);
+  }
   SelectParams sp;
   sp.cand = h->cand.p;
   sp.cnt = h->d_cnt;
@@ -902,22 +937,24 @@ int nns_search_impl(cslam_nns* h, const void* d_queries, int dtype, int nq, int 
   }
   CSLAM_CUDA(cudaEventRecord(h->ev_t0, s));
   const bool exact = (h->mode == 1);
-  for (int q0 = 0; q0 < nq; q0 += kCoarseBM) {
-    const int nqt = std::min(kCoarseBM, nq - q0);
+  int group = exact ? kCoarseBM : kGroupMax;
+  if (!exact && getenv("CSLAM_NNS_GROUP")) group = std::max(kCoarseBM, std::min(kGroupMax, atoi(getenv("CSLAM_NNS_GROUP"))));
+  for (int q0 = 0; q0 < nq; q0 += group) {
+    const int nqt = std::min(group, nq - q0);
     int32_t* oi = d_out_idx + static_cast<size_t>(q0) * k;
     double* os = d_out_sims + static_cast<size_t>(q0) * k;
-    CSLAM_TRY(nns_run_tile(h, q0, nqt, k, exact, oi, os, s, /*time_it=*/q0 + kCoarseBM >= nq));
+    CSLAM_TRY(nns_run_tile(h, q0, nqt, k, exact, oi, os, s, /*time_it=*/q0 + group >= nq));
     // escalation check: read the per-query flags
     CSLAM_CUDA(cudaMemcpyAsync(h->h_flags, h->d_flags, nqt * sizeof(int), cudaMemcpyDeviceToHost,
                                s));
-    CSLAM_CUDA(cudaMemcpyAsync(h->h_flags + kCoarseBM, h->d_sel_cnt, nqt * sizeof(int),
+    CSLAM_CUDA(cudaMemcpyAsync(h->h_flags + kGroupMax, h->d_sel_cnt, nqt * sizeof(int),
                                cudaMemcpyDeviceToHost, s));
     CSLAM_CUDA(cudaStreamSynchronize(s));
     std::vector<int> redo;
     for (int i = 0; i < nqt; ++i) {
       if (h->h_flags[i] == 2) redo.push_back(i);
       else info[0]++;
-      info[1] += h->h_flags[kCoarseBM + i];
+      info[1] += h->h_flags[kGroupMax + i];
     }
     for (int i : redo) {
       if (exact) {

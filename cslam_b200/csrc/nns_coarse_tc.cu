@@ -15,6 +15,11 @@
 //   * Ph  [cap,   dim_pad] fp16, rows L2-normalised, zero padded   (B operand, K-major)
 //   * TMEM: 2 accumulator buffers x 256 fp32 columns = all 512 columns; TMEM lane m
 //     holds query m, column j holds pool row (tile_row0 + j).
+// Query batches wider than 128 run as thread-block CLUSTERS of C = 2 or 4 CTAs: CTA r of a
+// cluster owns query tile r of the group, all CTAs of a cluster walk the same pool tiles, and
+// every pool tile is fetched from HBM ONCE per cluster: each CTA loads 256/C of its rows and
+// TMA-multicasts them into the shared memory of all C CTAs.  A 512-query batch then costs one
+// pool sweep instead of four and the kernel moves from the HBM roofline to the tensor pipe.
 // Warp roles (384 threads, 1 CTA / SM, persistent over pool tiles):
 //   warp 0    TMA producer (one lane)       warp 1  MMA issuer (one lane)
 //   warp 2    TMEM allocator                warp 3  idle
@@ -43,6 +48,15 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_THREADS = 384;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// "A-resident" mode (clusters, dim_pad <= 512): the query tile stays in shared memory for the
+// whole kernel (num_kb x 16 KiB) and only pool tiles stream through a 3-stage ring, which cuts
+// the bytes every SM has to ingest per MMA by a third (the chip-wide TMA/L2 delivery rate, not
+// HBM, is what bounds the cluster kernel).
+constexpr int RES_MAX_KB = 8;
+constexpr int RES_STAGES = 3;
+constexpr int RES_DATA_BYTES = RES_MAX_KB * A_BYTES + RES_STAGES * B_BYTES;   // 224 KiB
+constexpr int SMEM_BYTES_RES = RES_DATA_BYTES + 1024 + 256;
+static_assert(SMEM_BYTES_RES <= 232448, "A-resident layout exceeds the 227 KiB CTA limit");
 
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
@@ -92,6 +106,40 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                               int c0, int c1, uint16_t cta_mask, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      ".multicast::cluster.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5, %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask), "l"(policy)
+      : "memory");
+}
+// Pull a tile into L2 ahead of time (no shared memory, no barrier).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(map), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) = 1 | SBO>>4 [32,46) = 1024>>4 | version=1 [46,48) |
 // layout_type=SWIZZLE_128B(2) [61,64).
@@ -127,6 +175,13 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                ::"r"(bar)
                : "memory");
 }
+// commit that arrives on the same barrier offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -154,25 +209,41 @@ __device__ __forceinline__ void tmem_ld_wait() {
 struct PipeState {
   int stage = 0;
   uint32_t phase = 0;
-  __device__ __forceinline__ void advance() {
-    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+  __device__ __forceinline__ void advance(int nst) {
+    if (++stage == nst) { stage = 0; phase ^= 1; }
   }
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
                 const __grid_constant__ CUtensorMap tmap_p, CoarseParams prm) {
+  // cluster geometry: C CTAs, rank r owns query tile r of the group; C == 1 is the plain kernel
+  const int C = prm.cluster;
+  const int crank = C > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cid = C > 1 ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
+  const int ncl = C > 1 ? static_cast<int>(num_clusters_x()) : static_cast<int>(gridDim.x);
+  const uint16_t cmask = static_cast<uint16_t>((1u << C) - 1u);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const bool a_res = prm.a_resident != 0;
+  const int nst = a_res ? RES_STAGES : STAGES;
+  const uint32_t bar_base = smem_base + (a_res ? RES_DATA_BYTES : STAGES * STAGE_BYTES);
   // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-  auto smem_a = [&](int s) { return smem_base + s * STAGE_BYTES; };
-  auto smem_b = [&](int s) { return smem_base + s * STAGE_BYTES + A_BYTES; };
+  // streaming layout: stage = [A k-block | B k-block]; resident layout: [A k-blocks 0..7 | B ring]
+  auto smem_a = [&](int s, int kb) {
+    return a_res ? smem_base + kb * A_BYTES : smem_base + s * STAGE_BYTES;
+  };
+  auto smem_b = [&](int s) {
+    return a_res ? smem_base + RES_MAX_KB * A_BYTES + s * B_BYTES
+                 : smem_base + s * STAGE_BYTES + A_BYTES;
+  };
+  // barrier slots: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem slot, a_full
+  const uint32_t afull_bar = bar_base + 8u * (2 * STAGES + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -184,12 +255,13 @@ k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), C);   // one MMA commit per CTA of the cluster frees a slot
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), 256);
     }
+    mbar_init(afull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -200,43 +272,96 @@ k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
   }
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   const int num_kb = prm.num_kb;
-  const int first_tile = blockIdx.x;
-  const int tile_step = gridDim.x;
+  long long* dbg = (prm.dbg != nullptr && blockIdx.x == 0) ? prm.dbg : nullptr;
+  long long w_acc0 = 0, w_acc1 = 0, w_acc2 = 0;
+  auto timed_wait = [&](uint32_t bar, uint32_t parity, long long& acc) {
+    if (dbg) {
+      const long long t0 = clock64();
+      mbar_wait(bar, parity);
+      acc += clock64() - t0;
+    } else {
+      mbar_wait(bar, parity);
+    }
+  };
+  const int first_tile = cid;
+  const int tile_step = ncl;
+  const int q_tile_row0 = prm.q_row0 + crank * BM;
 
   if (warp == 0) {
     if (lane == 0) {
       PipeState ps;
-      for (int tile = first_tile; tile < prm.num_tiles; tile += tile_step) {
-        const int row0 = static_cast<int>(static_cast<int64_t>(tile) * prm.tile_stride * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
-          mbar_expect_tx(full_bar(ps.stage), STAGE_BYTES);
-          tma_load_2d(smem_a(ps.stage), &tmap_q, full_bar(ps.stage), kb * BK, prm.q_row0,
-                      kEvictLast);
-          tma_load_2d(smem_b(ps.stage), &tmap_p, full_bar(ps.stage), kb * BK, row0,
-                      kEvictFirst);
-          ps.advance();
+      if (a_res) {   // the whole query tile, once
+        mbar_expect_tx(afull_bar, static_cast<uint32_t>(num_kb) * A_BYTES);
+        for (int kb = 0; kb < num_kb; ++kb)
+          tma_load_2d(smem_a(0, kb), &tmap_q, afull_bar, kb * BK, q_tile_row0, kEvictLast);
+      }
+      // The ring in shared memory holds well under one bandwidth-delay product of an HBM
+      // stream, so in the cluster kernel (where every SM must ingest a whole pool tile per
+      // 2.2 us of MMA) the tiles are pulled into L2 `pf` tiles ahead and the ring is refilled
+      // at L2 latency.
+      const int pf = prm.l2_prefetch;
+      const int slice_rows = BN / C;
+      for (int t = 0; t < pf; ++t) {
+        const int tl = first_tile + t * tile_step;
+        if (tl < prm.num_tiles) {
+          const int r0 = static_cast<int>(static_cast<int64_t>(tl) * prm.tile_stride * BN);
+          for (int kb = 0; kb < num_kb; ++kb)
+            tma_prefetch_l2_2d(&tmap_p, kb * BK, r0 + crank * slice_rows);
         }
       }
+      for (int tile = first_tile; tile < prm.num_tiles; tile += tile_step) {
+        const int row0 = static_cast<int>(static_cast<int64_t>(tile) * prm.tile_stride * BN);
+        if (pf > 0) {
+          const int tl = tile + pf * tile_step;
+          if (tl < prm.num_tiles) {
+            const int r0 = static_cast<int>(static_cast<int64_t>(tl) * prm.tile_stride * BN);
+            for (int kb = 0; kb < num_kb; ++kb)
+              tma_prefetch_l2_2d(&tmap_p, kb * BK, r0 + crank * slice_rows);
+          }
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          timed_wait(empty_bar(ps.stage), ps.phase ^ 1, w_acc0);
+          mbar_expect_tx(full_bar(ps.stage), a_res ? B_BYTES : STAGE_BYTES);
+          if (!a_res)
+            tma_load_2d(smem_a(ps.stage, kb), &tmap_q, full_bar(ps.stage), kb * BK, q_tile_row0,
+                        kEvictLast);
+          if (C == 1) {
+            tma_load_2d(smem_b(ps.stage), &tmap_p, full_bar(ps.stage), kb * BK, row0,
+                        kEvictFirst);
+          } else {
+            // this CTA's slice of the pool tile, multicast into every CTA of the cluster
+            const int rows = BN / C;
+            tma_load_2d_mc(smem_b(ps.stage) + crank * rows * (BK * 2), &tmap_p, full_bar(ps.stage),
+                           kb * BK, row0 + crank * rows, cmask, kEvictFirst);
+          }
+          ps.advance(nst);
+        }
+      }
+      if (dbg) dbg[0] += w_acc0;   // producer: cycles waiting for a free smem slot
     }
   } else if (warp == 1) {
     if (lane == 0) {
       PipeState ps;
       int it = 0;
+      if (a_res) {
+        mbar_wait(afull_bar, 0);
+        tc_fence_after();
+      }
       for (int tile = first_tile; tile < prm.num_tiles; tile += tile_step, ++it) {
         const int buf = it & 1;
-        mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);
+        timed_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1, w_acc1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(ps.stage), ps.phase);
+          timed_wait(full_bar(ps.stage), ps.phase, w_acc0);
           tc_fence_after();
-          const uint32_t a0 = smem_a(ps.stage);
+          const uint32_t a0 = smem_a(ps.stage, kb);
           const uint32_t b0 = smem_b(ps.stage);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -244,10 +369,16 @@ k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
             const uint64_t bdesc = make_sw128_desc(b0 + k * (UMMA_K * 2));
             umma_f16(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(ps.stage));  // frees the smem slot once the MMAs retire
-          ps.advance();
+          // frees the smem slot once the MMAs retire (in every CTA that multicasts into it)
+          if (C == 1) umma_commit(empty_bar(ps.stage));
+          else umma_commit_mc(empty_bar(ps.stage), cmask);
+          ps.advance(nst);
         }
         umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
+      }
+      if (dbg) {
+        dbg[1] += w_acc0;   // MMA issuer: cycles waiting for operands
+        dbg[2] += w_acc1;   // MMA issuer: cycles waiting for a free accumulator
       }
     }
   } else if (warp >= 4) {
@@ -256,14 +387,14 @@ k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
     const int ew = warp - 4;
     const int quarter = ew & 3;
     const int half = ew >> 2;
-    const int q = quarter * 32 + lane;
+    const int q = crank * BM + quarter * 32 + lane;   // query index within the group
     const bool q_valid = q < prm.nq;
     const int qs = q_valid ? q : 0;
     // invalid (padding) queries never hit: +inf threshold
     const float tau = !q_valid ? INFINITY : (prm.tau != nullptr ? prm.tau[q] : -INFINITY);
     const size_t slots = cand_slots(prm.nsub);
     uint2* my_seg = prm.cand + static_cast<size_t>(qs) * slots +
-                    static_cast<size_t>(blockIdx.x * 2 + half) * kSegCap;
+                    static_cast<size_t>(cid * 2 + half) * kSegCap;
     uint2* my_ovf = prm.cand + static_cast<size_t>(qs) * slots +
                     static_cast<size_t>(prm.nsub) * kSegCap;
     unsigned int* my_cnt = prm.cnt + static_cast<size_t>(qs) * (prm.nsub + 1);
@@ -275,8 +406,9 @@ k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
     for (int tile = first_tile; tile < prm.num_tiles; tile += tile_step, ++it) {
       const int buf = it & 1;
       const int row0 = static_cast<int>(static_cast<int64_t>(tile) * prm.tile_stride * BN);
-      mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+      timed_wait(tfull_bar(buf), (it >> 1) & 1, w_acc0);
       tc_fence_after();
+      const long long te0 = dbg ? clock64() : 0;
 #pragma unroll 1
       for (int c = half * HALF_N; c < (half + 1) * HALF_N; c += kChunk) {
         uint32_t r[32];
@@ -291,22 +423,29 @@ k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
                                fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
         if (prm.mode == 1) {
           if (q_valid) my_smax[tile * (BN / kChunk) + c / kChunk] = f32_to_key(mx);
-        } else if (__any_sync(0xffffffffu, mx >= tau)) {
+        } else if (mx >= tau) {
+          // Per-thread hit path (a thread owns its candidate segment, so no warp votes are
+          // needed): only the 4-element groups whose maximum clears the threshold are
+          // examined.  With the sampled threshold ~1000 rows per query clear tau, i.e. most
+          // 32x32 chunks contain a hit for SOME lane - this path is hot and must stay short.
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float s = __uint_as_float(r[j]);
-            const int row = row0 + c + j;
-            const bool hit = (s >= tau) && (row < prm.n_rows);
-            if (__any_sync(0xffffffffu, hit)) {
-              if (hit) {
-                const uint2 e = make_uint2(__float_as_uint(s), static_cast<uint32_t>(row));
-                if (my_count < static_cast<unsigned int>(kSegCap)) {
-                  my_seg[my_count] = e;
-                } else {
-                  const unsigned int pos = atomicAdd(my_cnt + prm.nsub, 1u);
-                  if (pos < static_cast<unsigned int>(kOvfCap)) my_ovf[pos] = e;
+          for (int g = 0; g < 8; ++g) {
+            if (m[g] >= tau) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = 4 * g + e;
+                const float s = __uint_as_float(r[j]);
+                const int row = row0 + c + j;
+                if (s >= tau && row < prm.n_rows) {
+                  const uint2 ent = make_uint2(__float_as_uint(s), static_cast<uint32_t>(row));
+                  if (my_count < static_cast<unsigned int>(kSegCap)) {
+                    my_seg[my_count] = ent;
+                  } else {
+                    const unsigned int pos = atomicAdd(my_cnt + prm.nsub, 1u);
+                    if (pos < static_cast<unsigned int>(kOvfCap)) my_ovf[pos] = ent;
+                  }
+                  ++my_count;
                 }
-                ++my_count;
               }
             }
           }
@@ -314,13 +453,20 @@ k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
+      if (dbg) w_acc1 += clock64() - te0;
+    }
+    if (dbg && threadIdx.x == 128) {
+      dbg[3] += w_acc0;   // epilogue: cycles waiting for an accumulator
+      dbg[4] += w_acc1;   // epilogue: cycles scanning accumulators
+      dbg[5] += it;       // tiles
     }
     if (q_valid && prm.mode == 0)
-      my_cnt[blockIdx.x * 2 + half] = min(my_count, static_cast<unsigned int>(kSegCap));
+      my_cnt[cid * 2 + half] = min(my_count, static_cast<unsigned int>(kSegCap));
   }
 
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();   // nobody leaves while a peer may still write into its smem
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -377,12 +523,47 @@ int make_fp16_rowmajor_tmap(void* out_map, const void* base, int64_t rows, int c
 int launch_coarse_tc(const void* tmap_q, const void* tmap_p, const CoarseParams& prm, int grid,
                      cudaStream_t stream) {
   CSLAM_CUDA(cudaFuncSetAttribute(k_nns_coarse_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  SMEM_BYTES));
+                                  SMEM_BYTES_RES));
   if (prm.num_tiles <= 0 || grid <= 0) return CSLAM_OK;
-  k_nns_coarse_tc<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(
-      *reinterpret_cast<const CUtensorMap*>(tmap_q), *reinterpret_cast<const CUtensorMap*>(tmap_p),
-      prm);
-  CSLAM_LAUNCH_CHECK();
+  if (prm.a_resident && (prm.num_kb > RES_MAX_KB || prm.cluster < 2)) {
+    set_error("coarse_tc: A-resident mode needs a cluster and dim_pad <= %d", RES_MAX_KB * BK);
+    return CSLAM_ERR_INVALID;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned int>(grid));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = prm.a_resident ? SMEM_BYTES_RES : SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned int>(prm.cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = prm.cluster > 1 ? 1 : 0;
+  CSLAM_CUDA(cudaLaunchKernelEx(&cfg, k_nns_coarse_tc, *reinterpret_cast<const CUtensorMap*>(tmap_q),
+                                *reinterpret_cast<const CUtensorMap*>(tmap_p), prm));
+  count_launch();
+  return CSLAM_OK;
+}
+
+int coarse_tc_max_clusters(int cluster, int* out) {
+  CSLAM_CUDA(cudaFuncSetAttribute(k_nns_coarse_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  SMEM_BYTES_RES));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned int>(cluster) * 64);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES_RES;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned int>(cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  CSLAM_CUDA(cudaOccupancyMaxActiveClusters(&n, k_nns_coarse_tc, &cfg));
+  *out = n;
   return CSLAM_OK;
 }
 

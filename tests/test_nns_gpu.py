@@ -159,3 +159,29 @@ def test_empty_and_growth():
             assert items == ref_items
             np.testing.assert_allclose(sims, ref_sims, atol=1e-9)
     assert nnsm.data.shape == (4000, 32)
+
+
+@pytest.mark.parametrize("nq", [129, 256, 300, 512, 700])
+def test_query_groups_run_as_clusters(nq):
+    """Batches wider than one 128-query tile take the thread-block-cluster path (2 or 4 CTAs
+    share every pool tile through TMA multicast; > 512 queries = several groups)."""
+    rng = np.random.default_rng(40 + nq)
+    pool = _unit(rng, 70000, 192, np.float32)     # sampled threshold + filtered full pass
+    gpu, orc = _build(pool)
+    queries = _unit(rng, nq, 192)
+    idx, sims = gpu.search_batch(queries, 30)
+    assert gpu.last_info[0] + gpu.last_info[2] == nq
+    for qi in list(range(0, nq, 37)) + [127, 128, nq - 1]:
+        full = orc.similarities_vec(queries[qi])
+        order = np.argsort(full)[::-1][:30]
+        assert lists_match_modulo_ties(list(idx[qi]), list(order), full), qi
+        np.testing.assert_allclose(sims[qi], full[idx[qi]], rtol=0, atol=1e-6)
+    # identical to the same queries searched one tile at a time
+    idx1 = np.concatenate([gpu.search_batch(queries[s:s + 128], 30)[0] for s in range(0, nq, 128)])
+    assert np.array_equal(idx, idx1)
+    # small pool: unfiltered (exhaustive) pass, one pool tile per cluster
+    small, orc2 = _build(_unit(rng, 3000, 192, np.float32))
+    idx2, sims2 = small.search_batch(queries, 5)
+    for qi in (0, 128, nq - 1):
+        full = orc2.similarities_vec(queries[qi])
+        assert lists_match_modulo_ties(list(idx2[qi]), list(np.argsort(full)[::-1][:5]), full)

@@ -17,6 +17,7 @@ SOURCES = [
     "nns.cu",
     "nns_coarse_tc.cu",
     "heads.cu",
+    "pca_tc.cu",
     "mac.cu",
 ]
 

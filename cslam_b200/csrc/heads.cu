@@ -20,6 +20,10 @@
 #include "common.cuh"
 
 namespace cslam {
+bool pca_tc_supported(const float* d_x, const float* d_w, int din, int dout);
+int launch_pca_gemm_tc(const float* d_x, int batch, int din, const float* d_w, int dout,
+                       int max_ksplit, int num_sms, float* d_part, int* ksplit_out,
+                       cudaStream_t stream);
 namespace {
 
 // ------------------------------------------------------------------ A1 preprocessing
@@ -326,6 +330,7 @@ k_vlad(const float* __restrict__ x, int S, const float* __restrict__ conv_w,
 }
 
 // ------------------------------------------------------------------ A4 PCA projection
+// (tensor-core GEMM in pca_tc.cu; the SIMT kernel below serves shapes TMA cannot address)
 // out_raw[b][d] = sum_j x[b][j] W[d][j]  (split-K partials), B <= 64 rows per launch.
 // CTA tile 64 (rows) x 64 (outputs), 256 threads, 4x4 register tile, K step 16.
 constexpr int PB = 64, PD = 64, PKS = 16;
@@ -591,13 +596,25 @@ int cslam_pca_project_l2(const float* d_x, int batch, int din, const float* d_w,
   CSLAM_REQUIRE(d_x && d_w && d_bias && d_out && d_work, "pca_project_l2: NULL argument");
   CSLAM_REQUIRE(batch >= 0 && din > 0 && dout > 0, "pca_project_l2: bad sizes");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int ksplit = 16;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    CSLAM_CUDA(cudaGetDevice(&dev));
+    CSLAM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  static const bool force_simt = getenv("CSLAM_PCA_SIMT") != nullptr;
   for (int b0 = 0; b0 < batch; b0 += PB) {
     const int nb = std::min(PB, batch - b0);
-    dim3 grid((dout + PD - 1) / PD, ksplit);
-    k_pca_gemm<<<grid, 256, 0, s>>>(d_x + static_cast<size_t>(b0) * din, nb, din, d_w, dout, ksplit,
-                                    d_work);
-    CSLAM_LAUNCH_CHECK();
+    const float* xb = d_x + static_cast<size_t>(b0) * din;
+    int ksplit = 16;
+    if (!force_simt && pca_tc_supported(xb, d_w, din, dout)) {
+      // tcgen05 kind::tf32 split-K GEMM (pca_tc.cu): W streams from HBM once
+      CSLAM_TRY(launch_pca_gemm_tc(xb, nb, din, d_w, dout, 16, num_sms, d_work, &ksplit, s));
+    } else {
+      dim3 grid((dout + PD - 1) / PD, ksplit);
+      k_pca_gemm<<<grid, 256, 0, s>>>(xb, nb, din, d_w, dout, ksplit, d_work);
+      CSLAM_LAUNCH_CHECK();
+    }
     k_pca_finish<<<nb, 256, 0, s>>>(d_work, nb, dout, ksplit, d_bias, d_scale,
                                     d_out + static_cast<size_t>(b0) * dout);
     CSLAM_LAUNCH_CHECK();

@@ -415,33 +415,59 @@ k_pca_finish(const float* __restrict__ part, int B, int Dout, int ksplit,
 
 // ------------------------------------------------------------------ A5 CosPlace head
 // One CTA per image: L2Norm over channels per location, GeM pooling, Linear, L2Norm.
+// When the image's feature map fits (ResNet trunks: 512 x 7 x 7 floats = 98 KB) it is staged
+// in shared memory with coalesced loads and both reductions run from there with all
+// threads; otherwise (VGG16 trunk) the map is read from global memory twice.
 __global__ void __launch_bounds__(512)
 k_gem_head(const float* __restrict__ x, int C, int S, float p, float eps,
            const float* __restrict__ fc_w, const float* __restrict__ fc_b, int D,
-           float* __restrict__ out) {
+           float* __restrict__ out, int stage_map) {
   extern __shared__ float gsm[];
   float* inv = gsm;            // [S]
   float* g = gsm + S;          // [C]
   float* y = g + C;            // [D]
+  float* part = y + D;         // [8][S] partial sums of squares
+  float* xs = part + 8 * S;    // [C*S] staged feature map (stage_map only)
   __shared__ float sh[16];
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const float* xb = x + static_cast<size_t>(b) * C * S;
-  for (int s = tid; s < S; s += blockDim.x) {
+  if (stage_map) {
+    for (int e = tid; e < C * S; e += blockDim.x) xs[e] = xb[e];
+    __syncthreads();
+    xb = xs;   // generic pointer into shared memory
+  }
+  // sum over channels of x^2 per location: thread (location, channel eighth); the partials are
+  // combined in a fixed order
+  for (int t = tid; t < 8 * S; t += blockDim.x) {
+    const int s = t % S, part_id = t / S;
+    const int c0 = part_id * ((C + 7) / 8), c1 = min(C, c0 + (C + 7) / 8);
     float acc = 0.f;
-    for (int c = 0; c < C; ++c) {
+    for (int c = c0; c < c1; ++c) {
       const float v = xb[static_cast<size_t>(c) * S + s];
       acc = fmaf(v, v, acc);
     }
+    part[part_id * S + s] = acc;
+  }
+  __syncthreads();
+  for (int s = tid; s < S; s += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += part[k * S + s];
     inv[s] = 1.0f / fmaxf(sqrtf(acc), 1e-12f);
   }
   __syncthreads();
   // GeM: mean_s clamp(xhat, eps)^p, then ^(1/p)   (layers.py:8-9)
+  const bool cube = p == 3.0f;   // the reference's initial (and usual) exponent
   for (int c = tid; c < C; c += blockDim.x) {
     float acc = 0.f;
-    for (int s = 0; s < S; ++s) acc += powf(fmaxf(xb[static_cast<size_t>(c) * S + s] * inv[s], eps), p);
-    g[c] = powf(acc / static_cast<float>(S), 1.0f / p);
+    for (int s = 0; s < S; ++s) {
+      const float v = fmaxf(xb[static_cast<size_t>(c) * S + s] * inv[s], eps);
+      acc += cube ? v * v * v : powf(v, p);
+    }
+    const float mean = acc / static_cast<float>(S);
+    g[c] = cube ? cbrtf(mean) : powf(mean, 1.0f / p);
   }
   __syncthreads();
   // Linear: y[d] = fc_w[d, :] . g + fc_b[d]; one warp per output row
@@ -628,12 +654,15 @@ int cslam_gem_head_forward(const float* d_x, int batch, int channels, int locati
   CSLAM_REQUIRE(d_x && d_fc_w && d_fc_b && d_out, "gem_head_forward: NULL argument");
   CSLAM_REQUIRE(batch >= 0 && channels > 0 && locations > 0 && dout > 0, "gem_head_forward: bad sizes");
   if (batch == 0) return CSLAM_OK;
-  const size_t smem = (static_cast<size_t>(locations) + channels + dout) * sizeof(float);
+  size_t smem = (static_cast<size_t>(locations) * 9 + channels + dout) * sizeof(float);
+  const size_t map_bytes = static_cast<size_t>(channels) * locations * sizeof(float);
+  const int stage_map = smem + map_bytes <= 200 * 1024 ? 1 : 0;
+  if (stage_map) smem += map_bytes;
   CSLAM_REQUIRE(smem <= 200 * 1024, "gem_head_forward: shapes need %zu B of shared memory", smem);
   CSLAM_CUDA(cudaFuncSetAttribute(k_gem_head, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
   k_gem_head<<<batch, 512, smem, static_cast<cudaStream_t>(stream)>>>(
-      d_x, channels, locations, p, eps, d_fc_w, d_fc_b, dout, d_out);
+      d_x, channels, locations, p, eps, d_fc_w, d_fc_b, dout, d_out, stage_map);
   CSLAM_LAUNCH_CHECK();
   return CSLAM_OK;
 }

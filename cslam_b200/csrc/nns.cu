@@ -796,7 +796,7 @@ int nns_run_tile(cslam_nns* h, int q0, int nqt, int k, bool exact, int32_t* out_
   cp.nq = nqt;
   cp.q_row0 = q0;
   cp.cluster = C;
-  cp.l2_prefetch = getenv("CSLAM_NNS_PF") ? atoi(getenv("CSLAM_NNS_PF")) : (C > 1 ? 3 : 0);
+  cp.l2_prefetch = getenv("CSLAM_NNS_PF") ? atoi(getenv("CSLAM_NNS_PF")) : 0;   // measured: no gain, the ring is not latency-bound
   cp.a_resident = (C > 1 && h->dim_pad <= 512 && !getenv("CSLAM_NNS_NO_ARES")) ? 1 : 0;
   cp.cnt = h->d_cnt;
   cp.cand = h->cand.p;

@@ -30,6 +30,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstring>
 #include <numeric>
 #include <random>
 #include <vector>
@@ -1250,6 +1251,8 @@ struct PersistArgs {
   double theta0[MAXM];
   double tol, lnorm;
   int max_iters, have_p;
+  int init;              // 1: X in global memory is a raw start block: centre it, form AX = L X and
+                         //    Rayleigh-Ritz it inside the kernel before the first iteration
   double* out;           // [0..MAXM) theta, [MAXM] iterations, [MAXM+1] status, [MAXM+2] res
   int rr_sweeps;         // Jacobi sweep cap of the Rayleigh-Ritz solve
   int cap0, cap1;        // shared-memory capacity (entries) for the CTA's slice of each adjacency
@@ -1455,11 +1458,52 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       t_prev = t;
     }
   };
+  // AX = L X with X published through global memory (start-up pass, periodic refresh)
+  auto ax_from_x = [&]() {
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (valid[j])
+#pragma unroll
+        for (int c = 0; c < MAXM; ++c)
+          if (c < m) a.X[static_cast<size_t>(c) * ld + row0 + j] = x[j][c];
+    grid_barrier(a.barrier, epoch, nb_grid);
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (valid[j]) {
+        double acc[MAXM];
+#pragma unroll
+        for (int c = 0; c < MAXM; ++c) acc[c] = 0.0;
+        for (int q = q0s[j]; q < q0e[j]; ++q)
+#pragma unroll
+          for (int c = 0; c < MAXM; ++c)
+            if (c < m) acc[c] = fma(V0[q], __ldcg(a.X + static_cast<size_t>(c) * ld + C0[q]), acc[c]);
+        for (int q = q1s[j]; q < q1e[j]; ++q)
+#pragma unroll
+          for (int c = 0; c < MAXM; ++c)
+            if (c < m) acc[c] = fma(V1[q], __ldcg(a.X + static_cast<size_t>(c) * ld + C1[q]), acc[c]);
+#pragma unroll
+        for (int c = 0; c < MAXM; ++c)
+          if (c < m) ax[j][c] = fma(dg[j], x[j][c], acc[c]);
+      }
+  };
+
+  bool init_pass = a.init != 0;
+  if (init_pass) it = -1;   // the start-up pass below is not an LOBPCG iteration
   for (; it < a.max_iters; ++it) {
-    // ---- phase 1: residual, forward aggregates -------------------------------------------
     double loc[MAXM];
 #pragma unroll
     for (int c = 0; c < MAXM; ++c) loc[c] = 0.0;
+    if (init_pass) {
+      // start-up pass: column sums of the raw start block (projection onto 1-perp)
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+#pragma unroll
+        for (int c = 0; c < MAXM; ++c)
+          if (valid[j] && c < m) loc[c] += x[j][c];
+      block_sum2(loc, a.pcs);
+      grid_barrier(a.barrier, epoch, nb_grid);
+    } else {
+    // ---- phase 1: residual, forward aggregates -------------------------------------------
     double A = 1.0, B[MAXM];
 #pragma unroll
     for (int c = 0; c < MAXM; ++c) B[c] = 0.0;
@@ -1559,6 +1603,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     tick(2);
     grid_barrier(a.barrier, epoch, nb_grid);
     tick(6);
+    }  // !init_pass
     // ---- phase 4: AW = L (W - mean), centre W, Gram partial sums ------------------------------
     grid_sum2(a.pcs, s_mu);
     tick(8);
@@ -1566,6 +1611,14 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 #pragma unroll
     for (int c = 0; c < MAXM; ++c) mu[c] = c < m ? s_mu[c] / n : 0.0;
     __syncthreads();
+    if (init_pass) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+#pragma unroll
+        for (int c = 0; c < MAXM; ++c)
+          if (valid[j] && c < m) x[j][c] -= mu[c];
+      ax_from_x();
+    }
     // W entries of this CTA's own row range (the odometry neighbours) come from shared memory,
     // the rest (loop closures, range boundaries) from L2.  Branch-free: both loads are
     // predicated so that a thread's remote gathers are all in flight together.
@@ -1577,7 +1630,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       if (on && !loc) vg = __ldcg(a.W + static_cast<size_t>(c) * ld + col);
       return loc ? vs : vg;
     };
-    {
+    if (!init_pass) {
       // gathers of all rows of the thread are issued before any is consumed: the first two
       // fixed entries (odometry neighbours) and the first active entry of each row are
       // predicated, longer rows continue in the loops below
@@ -1635,7 +1688,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       }
     }
     tick(9);
-    const int nbas = have_p ? 3 : 2;
+    const int nbas = init_pass ? 1 : (have_p ? 3 : 2);
     const int sdim = nbas * m;
     {
       // basis values of this thread's rows: S = [X | W | P], AS = [AX | AW | AP]
@@ -1758,37 +1811,15 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     __syncthreads();
 #pragma unroll
     for (int c = 0; c < MAXM; ++c) theta[c] = s_theta[c];
+    if (init_pass) {   // X, AX are now the Ritz pairs of the start block; P stays empty
+      init_pass = false;
+      continue;
+    }
     have_p = true;
     tick(4);
     if (it % 50 == 49) {
-      // refresh AX = L X against drift: X through global memory
-#pragma unroll
-      for (int j = 0; j < CH; ++j)
-        if (valid[j])
-#pragma unroll
-          for (int c = 0; c < MAXM; ++c)
-            if (c < m) a.X[static_cast<size_t>(c) * ld + row0 + j] = x[j][c];
-      grid_barrier(a.barrier, epoch, nb_grid);
-#pragma unroll
-      for (int j = 0; j < CH; ++j)
-        if (valid[j]) {
-          const int i = row0 + j;
-          double acc[MAXM];
-#pragma unroll
-          for (int c = 0; c < MAXM; ++c) acc[c] = 0.0;
-          for (int q = q0s[j]; q < q0e[j]; ++q)
-#pragma unroll
-            for (int c = 0; c < MAXM; ++c)
-              if (c < m) acc[c] = fma(V0[q], __ldcg(a.X + static_cast<size_t>(c) * ld + C0[q]), acc[c]);
-          for (int q = q1s[j]; q < q1e[j]; ++q)
-#pragma unroll
-            for (int c = 0; c < MAXM; ++c)
-              if (c < m) acc[c] = fma(V1[q], __ldcg(a.X + static_cast<size_t>(c) * ld + C1[q]), acc[c]);
-          (void)i;
-#pragma unroll
-          for (int c = 0; c < MAXM; ++c)
-            if (c < m) ax[j][c] = fma(dg[j], x[j][c], acc[c]);
-        }
+      // refresh AX = L X against drift
+      ax_from_x();
     }
   }
   // ---- epilogue: X, AX, P, AP back to global (warm start of the next solve) --------------------
@@ -1933,8 +1964,8 @@ struct FiedlerSolver {
   }
 
   // LOBPCG main loop in one cooperative kernel; theta in/out, *iters, *status out
-  int persist_loop(int ch, double tol, int max_iters, double* theta, bool have_p, int* iters,
-                   int* status) {
+  int persist_loop(int ch, double tol, int max_iters, double* theta, bool have_p, bool init,
+                   int* iters, int* status) {
     PersistArgs pa;
     pa.n = n;
     pa.m = m;
@@ -1952,6 +1983,7 @@ struct FiedlerSolver {
     pa.lnorm = lnorm;
     pa.max_iters = max_iters;
     pa.have_p = have_p ? 1 : 0;
+    pa.init = init ? 1 : 0;
     pa.out = pout;
     pa.barrier = pbar;
     CSLAM_CUDA(cudaMemsetAsync(pbar, 0, sizeof(unsigned int), stream));
@@ -2055,6 +2087,31 @@ struct FiedlerSolver {
     }
     // the host vectors may be destroyed by the caller right after this returns
     CSLAM_CUDA(cudaStreamSynchronize(stream));
+    return CSLAM_OK;
+  }
+
+  // same from caller-owned PINNED arrays, without synchronising (the caller keeps them intact
+  // until the stream has been synchronised)
+  int upload_async(Adj& a, const int* indptr, const int* cols, const int* src, size_t nnz) {
+    if (!a.indptr) CSLAM_TRY(dev_alloc(&a.indptr, static_cast<size_t>(n) + 1));
+    if (nnz > a.cap_nnz) {
+      CSLAM_CUDA(cudaStreamSynchronize(stream));
+      dev_free(a.cols);
+      dev_free(a.src);
+      dev_free(a.vals);
+      const size_t cap = std::max<size_t>(nnz * 2, 1024);
+      CSLAM_TRY(dev_alloc(&a.cols, cap));
+      CSLAM_TRY(dev_alloc(&a.src, cap));
+      CSLAM_TRY(dev_alloc(&a.vals, cap));
+      a.cap_nnz = cap;
+    }
+    a.nnz = static_cast<int64_t>(nnz);
+    CSLAM_CUDA(cudaMemcpyAsync(a.indptr, indptr, (static_cast<size_t>(n) + 1) * sizeof(int),
+                               cudaMemcpyHostToDevice, stream));
+    if (nnz) {
+      CSLAM_CUDA(cudaMemcpyAsync(a.cols, cols, nnz * sizeof(int), cudaMemcpyHostToDevice, stream));
+      CSLAM_CUDA(cudaMemcpyAsync(a.src, src, nnz * sizeof(int), cudaMemcpyHostToDevice, stream));
+    }
     return CSLAM_OK;
   }
 
@@ -2209,30 +2266,23 @@ struct FiedlerSolver {
       CSLAM_CUDA(cudaMemcpyAsync(X, x0.data(), x0.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
       CSLAM_CUDA(cudaStreamSynchronize(stream));
     }
-    // project X onto 1-perp and form AX
-    CSLAM_TRY(colsum_of(X));
-    // AX = L (X - mean), X <- X - mean
-    CSLAM_TRY(spmm(X, AX, red + 2 * NPAIR));
-    k_sub_mean<<<nblk, 256, 0, stream>>>(n, m, ld, X, red + 2 * NPAIR);
-    CSLAM_LAUNCH_CHECK();
     double theta[MAXM] = {};
     bool ok = true;
-    CSLAM_TRY(rr_update(1, theta, &ok));
-    if (!ok) {
-      set_error("fiedler: degenerate start basis");
-      return CSLAM_ERR_NOCONV;
-    }
     bool have_p = false;
     int it = 0;
     last_path = 0;
     const double tp2 = prof ? now() : 0;
-    t_prologue += tp2 - tp1;
     if (const int ch = persist_rows_per_thread()) {
+      // one cooperative kernel: start-up pass (centre X, AX = L X, Rayleigh-Ritz) + LOBPCG loop
       int status = 1;
-      CSLAM_TRY(persist_loop(ch, tol, max_iters, theta, false, &it, &status));
+      CSLAM_TRY(persist_loop(ch, tol, max_iters, theta, false, true, &it, &status));
       if (prof) t_loop += now() - tp2;
       last_path = 1;
-      last_iters = it;
+      last_iters = std::max(it, 0);
+      if (status == 2 && it < 0) {
+        set_error("fiedler: degenerate start basis");
+        return CSLAM_ERR_NOCONV;
+      }
       if (status == 1) {
         set_error("fiedler: LOBPCG did not reach tol %.1e in %d iterations", tol, max_iters);
         return CSLAM_ERR_NOCONV;
@@ -2240,6 +2290,17 @@ struct FiedlerSolver {
       *lambda2 = theta[0];
       warm = true;
       return CSLAM_OK;
+    }
+    // multi-kernel path: project X onto 1-perp and form AX
+    CSLAM_TRY(colsum_of(X));
+    // AX = L (X - mean), X <- X - mean
+    CSLAM_TRY(spmm(X, AX, red + 2 * NPAIR));
+    k_sub_mean<<<nblk, 256, 0, stream>>>(n, m, ld, X, red + 2 * NPAIR);
+    CSLAM_LAUNCH_CHECK();
+    CSLAM_TRY(rr_update(1, theta, &ok));
+    if (!ok) {
+      set_error("fiedler: degenerate start basis");
+      return CSLAM_ERR_NOCONV;
     }
     for (; it < max_iters; ++it) {
       Theta th;
@@ -2402,6 +2463,12 @@ struct cslam_mac {
   unsigned int *d_blk_eq = nullptr, *d_blk_sel = nullptr;
   int sel_blocks = 0, sel_per_block = 0;
   double* d_vec_tmp = nullptr;
+  // pinned staging of the active adjacency (rebuilt every Frank-Wolfe iteration)
+  int* hp_indptr = nullptr;
+  int* hp_cols = nullptr;
+  int* hp_src = nullptr;
+  size_t hp_cap = 0;
+  std::vector<int> deg;
   int fixed_components = 0;     // connected components of the fixed graph
   std::vector<int> fixed_root;  // component label per vertex (fixed graph)
   double tol = 1e-10;
@@ -2427,15 +2494,41 @@ int mac_set_active(cslam_mac* h, const std::vector<int>& support) {
               comps);
     return CSLAM_ERR_SINGULAR;
   }
-  std::vector<int> ei(support.size()), ej(support.size());
-  for (size_t t = 0; t < support.size(); ++t) {
-    ei[t] = h->ci[support[t]];
-    ej[t] = h->cj[support[t]];
+  // CSR of the active candidates (both directions), counting sort by row; entry order within a
+  // row = support order (deterministic).  Built in pinned staging buffers and copied
+  // asynchronously: they are next rewritten after solve(), which synchronises the stream.
+  const int n = h->n;
+  const size_t nnz = 2 * support.size();
+  if (!h->hp_indptr) CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->hp_indptr), (static_cast<size_t>(n) + 1) * sizeof(int)));
+  if (nnz > h->hp_cap) {
+    if (h->hp_cols) cudaFreeHost(h->hp_cols);
+    if (h->hp_src) cudaFreeHost(h->hp_src);
+    h->hp_cols = h->hp_src = nullptr;
+    h->hp_cap = std::max<size_t>(2 * nnz, 4096);
+    CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->hp_cols), h->hp_cap * sizeof(int)));
+    CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->hp_src), h->hp_cap * sizeof(int)));
   }
-  std::vector<int> indptr, cols, src;
-  build_adjacency(h->n, support.size(), ei.data(), ej.data(), indptr, cols, src);
-  for (auto& s : src) s = support[s];  // local -> candidate edge id
-  CSLAM_TRY(h->fs.upload(h->fs.act, indptr, cols, &src, nullptr));
+  int* indptr = h->hp_indptr;
+  std::memset(indptr, 0, (static_cast<size_t>(n) + 1) * sizeof(int));
+  for (int e : support) {
+    if (h->ci[e] == h->cj[e]) continue;   // self loops cancel in a Laplacian
+    indptr[h->ci[e] + 1]++;
+    indptr[h->cj[e] + 1]++;
+  }
+  for (int r = 0; r < n; ++r) indptr[r + 1] += indptr[r];
+  const size_t used = static_cast<size_t>(indptr[n]);
+  h->deg.assign(static_cast<size_t>(n), 0);
+  for (int e : support) {
+    const int i = h->ci[e], j = h->cj[e];
+    if (i == j) continue;
+    int p = indptr[i] + h->deg[i]++;
+    h->hp_cols[p] = j;
+    h->hp_src[p] = e;
+    p = indptr[j] + h->deg[j]++;
+    h->hp_cols[p] = i;
+    h->hp_src[p] = e;
+  }
+  CSLAM_TRY(h->fs.upload_async(h->fs.act, indptr, h->hp_cols, h->hp_src, used));
   h->fs.has_act = true;
   if (h->fs.act.nnz > 0) {
     const int blocks = static_cast<int>((h->fs.act.nnz + 255) / 256);
@@ -2552,7 +2645,7 @@ int cslam_mac_create(int num_poses, int64_t n_fixed, const int32_t* fi, const in
     }
   }
   const size_t mc = static_cast<size_t>(std::max<int64_t>(n_cand, 1));
-  h->sel_per_block = 4096;
+  h->sel_per_block = 1024;
   h->sel_blocks = static_cast<int>((mc + h->sel_per_block - 1) / h->sel_per_block);
   if ((st = dev_alloc(&h->d_ci, mc)) || (st = dev_alloc(&h->d_cj, mc)) ||
       (st = dev_alloc(&h->d_cw, mc)) || (st = dev_alloc(&h->d_w, mc)) ||
@@ -2580,6 +2673,9 @@ int cslam_mac_destroy(cslam_mac_t* h) {
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->fs.release();
+  if (h->hp_indptr) cudaFreeHost(h->hp_indptr);
+  if (h->hp_cols) cudaFreeHost(h->hp_cols);
+  if (h->hp_src) cudaFreeHost(h->hp_src);
   dev_free(h->d_ci);
   dev_free(h->d_cj);
   dev_free(h->d_cw);

@@ -49,6 +49,8 @@ constexpr int MAXS = 3 * MAXM;   // basis size limit
 constexpr int NPAIR = MAXS * (MAXS + 1) / 2;
 constexpr int CH = 4;            // elements per thread in the chunked scans
 constexpr int SCAN_B_THREADS = 1024;
+constexpr int FCH = 16;         // rows per thread in the LDL^T pivot scan (fewer, longer chunks:
+                                // the single-block combine k_fac_b is the serial part)
 
 // ------------------------------------------------------------------ Laplacian
 // Adjacency in CSR (off-diagonal entries only, duplicates allowed): L = D - A with
@@ -208,10 +210,10 @@ __device__ __forceinline__ M2 m2_mul(const M2& x, const M2& y) {  // x * y
 __global__ void k_fac_a(int n, const double* __restrict__ diag, const double* __restrict__ sup,
                         M2* __restrict__ agg) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i0 = t * CH;
+  const int i0 = t * FCH;
   if (i0 >= n) return;
   M2 acc = {1.0, 0.0, 0.0, 1.0};
-  for (int i = i0; i < min(n, i0 + CH); ++i) {
+  for (int i = i0; i < min(n, i0 + FCH); ++i) {
     const double b = i > 0 ? sup[i - 1] : 0.0;
     const M2 mi = {diag[i], -b * b, 1.0, 0.0};
     acc = m2_mul(mi, acc);
@@ -249,14 +251,14 @@ __global__ void k_fac_c(int n, const double* __restrict__ diag, const double* __
                         const M2* __restrict__ agg, double* __restrict__ dpiv,
                         double* __restrict__ lfac, int* __restrict__ bad) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i0 = t * CH;
+  const int i0 = t * FCH;
   if (i0 >= n) return;
   double dprev = 0.0;
   if (t > 0) {
     const M2 p = agg[t - 1];  // applied to (1, 0)^T: d = a / c
     dprev = p.a / p.c;
   }
-  for (int i = i0; i < min(n, i0 + CH); ++i) {
+  for (int i = i0; i < min(n, i0 + FCH); ++i) {
     double d, l;
     if (i == 0) {
       d = diag[0];
@@ -995,7 +997,7 @@ struct RRShared {
 
 __device__ __forceinline__ bool rr_warp(RRShared& S, int s, int m, const double* GA /*[MAXS*MAXS]*/,
                                         const double* GB, double (*C)[MAXM], double* theta,
-                                        int max_sweeps, long long* rrprof = nullptr) {
+                                        int max_sweeps, double tol2, long long* rrprof = nullptr) {
   const int lane = threadIdx.x & 31;
   long long tq = clock64();
   auto sect = [&](int k) {
@@ -1087,7 +1089,7 @@ __device__ __forceinline__ bool rr_warp(RRShared& S, int s, int m, const double*
       const int i = e / MAXS, j = e % MAXS;
       if (i < j && j < s) {
         const double v = S.T[i][j];
-        big = big || (v * v > 1e-32 * fabs(S.T[i][i] * S.T[j][j]) && fabs(v) > 1e-150);
+        big = big || (v * v > tol2 * fabs(S.T[i][i] * S.T[j][j]) && fabs(v) > 1e-150);
       }
     }
     if (!__any_sync(full, big)) break;
@@ -1255,6 +1257,7 @@ struct PersistArgs {
                          //    Rayleigh-Ritz it inside the kernel before the first iteration
   double* out;           // [0..MAXM) theta, [MAXM] iterations, [MAXM+1] status, [MAXM+2] res
   int rr_sweeps;         // Jacobi sweep cap of the Rayleigh-Ritz solve
+  double rr_tol2;        // squared relative off-diagonal level at which the Jacobi sweeps stop
   int cap0, cap1;        // shared-memory capacity (entries) for the CTA's slice of each adjacency
   unsigned int* barrier; // grid barrier counter, zero at launch
   long long* prof;       // optional [8] cycle counters of CTA 0 (phases 1-5, RR, barriers)
@@ -1762,7 +1765,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     __syncthreads();
     if (warp == 0) {
       int use = sdim;
-      bool ok = rr_warp(s_rr, sdim, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps, (a.prof && b == 0) ? rrprof_acc : nullptr);
+      bool ok = rr_warp(s_rr, sdim, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps, a.rr_tol2, (a.prof && b == 0) ? rrprof_acc : nullptr);
       if (!ok && have_p) {  // drop P (restart) and solve in span[X W]
         use = 2 * m;
         for (int e = lane; e < MAXS * MAXS; e += 32) {
@@ -1770,7 +1773,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
           if (i >= use || j >= use) { s_GA[e] = 0.0; s_GB[e] = 0.0; }
         }
         __syncwarp();
-        ok = rr_warp(s_rr, use, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps);
+        ok = rr_warp(s_rr, use, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps, a.rr_tol2);
       }
       if (lane == 0) s_ok = ok ? 1 : 0;
       if (lane < MAXM) s_theta[lane] = lane < m ? s_th2[lane] : 0.0;
@@ -2000,6 +2003,7 @@ struct FiedlerSolver {
     }
     pa.cap0 = pa.cap1 = 6144;
     pa.rr_sweeps = getenv("CSLAM_RR_SWEEPS") ? atoi(getenv("CSLAM_RR_SWEEPS")) : 3;
+    pa.rr_tol2 = getenv("CSLAM_RR_TOL2") ? atof(getenv("CSLAM_RR_TOL2")) : 1e-32;
     const size_t dyn = static_cast<size_t>(pa.cap0 + pa.cap1) * (sizeof(double) + sizeof(int)) +
                        static_cast<size_t>(MAXM) * pa.rpb * sizeof(double);
     CSLAM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
@@ -2136,11 +2140,13 @@ struct FiedlerSolver {
     k_max_reduce<<<std::min(64, (n + 2047) / 2048), 256, 0, stream>>>(rowabs, n, red);
     CSLAM_LAUNCH_CHECK();
     CSLAM_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), stream));
-    k_fac_a<<<nblk_t, 256, 0, stream>>>(n, diag, sup, fagg);
+    const int Tf = (n + FCH - 1) / FCH;
+    const int nblk_f = (Tf + 255) / 256;
+    k_fac_a<<<nblk_f, 256, 0, stream>>>(n, diag, sup, fagg);
     CSLAM_LAUNCH_CHECK();
-    k_fac_b<<<1, SCAN_B_THREADS, 0, stream>>>(T, fagg);
+    k_fac_b<<<1, SCAN_B_THREADS, 0, stream>>>(Tf, fagg);
     CSLAM_LAUNCH_CHECK();
-    k_fac_c<<<nblk_t, 256, 0, stream>>>(n, diag, sup, fagg, dpiv, lfac, d_bad);
+    k_fac_c<<<nblk_f, 256, 0, stream>>>(n, diag, sup, fagg, dpiv, lfac, d_bad);
     CSLAM_LAUNCH_CHECK();
     int bad = 0;
     CSLAM_CUDA(cudaMemcpyAsync(h_red, red, sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -2805,12 +2811,13 @@ int cslam_mac_fw_subset(cslam_mac_t* h, const double* w_init, int k, int max_ite
       for (int e : support) in_support[e] = 0;
       support.clear();
     }
-    for (int t = 0; t < k; ++t)
+    const size_t old_size = support.size();
+    for (int t = 0; t < k; ++t)   // slist is ascending, so the appended run is sorted
       if (!in_support[slist[t]]) {
         in_support[slist[t]] = 1;
         support.push_back(slist[t]);
       }
-    std::sort(support.begin(), support.end());
+    std::inplace_merge(support.begin(), support.begin() + old_size, support.end());
     if (prof) t_host += now() - t3;
   }
   if (prof)

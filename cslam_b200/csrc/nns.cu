@@ -513,20 +513,24 @@ k_nns_rerank(const int* __restrict__ sel_rows, const int* __restrict__ sel_cnt,
              double* __restrict__ sel_sims) {
   const int q = blockIdx.y;
   const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= sel_cnt[q]) return;
-  const int row = sel_rows[static_cast<size_t>(q) * kRerankMax + i];
-  const float* x = data + static_cast<size_t>(row) * dim;
+  const int cnt = sel_cnt[q];
   const double* qv = q64 + static_cast<size_t>(q) * dim;
-  double acc = 0.0;
-  for (int d = lane; d < dim; d += 32) acc = fma(qv[d], static_cast<double>(x[d]), acc);
-  const double uv = warp_sum(acc);
-  if (lane == 0) {
-    double dist = 1.0 - uv / sqrt(uu[q] * static_cast<double>(vv[row]));
-    dist = fmin(fmax(dist, 0.0), 2.0);
-    double sim = 1.0 - dist;
-    if (!(sim == sim)) sim = -INFINITY;  // NaN (zero-norm row) ranks last
-    sel_sims[static_cast<size_t>(q) * kRerankMax + i] = sim;
+  // grid-stride over the kept rows (typically ~2k of them): a small fixed grid.x instead of
+  // kRerankMax / 8 blocks per query, most of which would exit at once
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < cnt;
+       i += gridDim.x * (blockDim.x >> 5)) {
+    const int row = sel_rows[static_cast<size_t>(q) * kRerankMax + i];
+    const float* x = data + static_cast<size_t>(row) * dim;
+    double acc = 0.0;
+    for (int d = lane; d < dim; d += 32) acc = fma(qv[d], static_cast<double>(x[d]), acc);
+    const double uv = warp_sum(acc);
+    if (lane == 0) {
+      double dist = 1.0 - uv / sqrt(uu[q] * static_cast<double>(vv[row]));
+      dist = fmin(fmax(dist, 0.0), 2.0);
+      double sim = 1.0 - dist;
+      if (!(sim == sim)) sim = -INFINITY;  // NaN (zero-norm row) ranks last
+      sel_sims[static_cast<size_t>(q) * kRerankMax + i] = sim;
+    }
   }
 }
 
@@ -757,6 +761,9 @@ int nns_run_tile(cslam_nns* h, int q0, int nqt, int k, bool exact, int32_t* out_
   const int q_tiles = (nqt + kCoarseBM - 1) / kCoarseBM;
   int cl = exact ? 0 : (q_tiles <= 1 ? 0 : (q_tiles <= 2 ? 1 : 2));   // log2(cluster size)
   const int C = 1 << cl;
+  // two query tiles: SM-pair kernel (tcgen05 cta_group::2), one pool sweep per 256 queries
+  static const bool pair_enabled = !(getenv("CSLAM_NNS_PAIR") && atoi(getenv("CSLAM_NNS_PAIR")) == 0);
+  const bool use_pair = !exact && C == 2 && pair_enabled;
   CSLAM_REQUIRE(nqt <= (exact ? kCoarseBM : kGroupMax), "nns: query group of %d too wide", nqt);
   if (!exact && h->max_clusters[cl] == 0) {
     if (C == 1) h->max_clusters[0] = h->num_sms;
@@ -780,7 +787,15 @@ int nns_run_tile(cslam_nns* h, int q0, int nqt, int k, bool exact, int32_t* out_
     CSLAM_TRY(dev_alloc(&h->d_cnt, static_cast<size_t>(kGroupMax) * (nsub_needed + 1)));
     h->nsub = nsub_needed;
   }
-  const int smax_stride = sample_tiles * (kCoarseBN / kChunk);
+  // Wide groups sample more rows for the threshold (131072 instead of 32768): the candidate
+  // lists shrink ~4x (k / sample fraction rows clear tau), which is what the epilogue of the
+  // tensor-bound kernels pays for; single-tile searches are HBM-bound and keep the small sample.
+  int samp_tiles = sample_tiles;
+  if (C > 1 && !exhaustive) {
+    const int wide = kTauMax / (kCoarseBN / kChunk);          // 512 tiles = 131072 rows
+    if (n_rows / kCoarseBN >= 4 * wide) samp_tiles = wide;
+  }
+  const int smax_stride = samp_tiles * (kCoarseBN / kChunk);
   CSLAM_REQUIRE(smax_stride <= kTauMax, "nns: sample_rows too large");
   CSLAM_TRY(h->smax.reserve(static_cast<size_t>(kGroupMax) * smax_stride));
   // fp16 rounding of both unit-norm operands (2 * 2^-11), fp32 accumulation over
@@ -831,6 +846,8 @@ int nns_run_tile(cslam_nns* h, int q0, int nqt, int k, bool exact, int32_t* out_
     if (exact) {
       k_nns_coarse_exact<<<clusters, 256, 0, s>>>(h->d_data, h->d_vv, h->dim, h->d_q64, h->d_uu, cp);
       CSLAM_LAUNCH_CHECK();
+    } else if (use_pair) {
+      CSLAM_TRY(launch_coarse_pair(&h->tmap_q, &h->tmap_p[1], cp, clusters * 2, s));
     } else {
       CSLAM_TRY(launch_coarse_tc(&h->tmap_q, &h->tmap_p[cl], cp, clusters * C, s));
     }
@@ -845,8 +862,8 @@ int nns_run_tile(cslam_nns* h, int q0, int nqt, int k, bool exact, int32_t* out_
   } else {
     // sample pass over `sample_tiles` full tiles spread evenly over the pool
     const int full_tiles = n_rows / kCoarseBN;
-    const int stride = std::max(1, full_tiles / sample_tiles);
-    CSLAM_TRY(launch_coarse(1, sample_tiles, stride, nullptr, false));
+    const int stride = std::max(1, full_tiles / samp_tiles);
+    CSLAM_TRY(launch_coarse(1, samp_tiles, stride, nullptr, false));
     // tau = (k-th largest sampled chunk maximum) - 2 eps.  The sampled maxima are distinct
     // pool rows, so the pool's k-th largest coarse score c_k >= that value and therefore
     // tau <= c_k - 2 eps: every row k_nns_select needs is in the candidate list.
@@ -881,7 +898,7 @@ int nns_run_tile(cslam_nns* h, int q0, int nqt, int k, bool exact, int32_t* out_
   CSLAM_LAUNCH_CHECK();
   // one warp per kept row; blocks beyond a query's kept count exit immediately
   const int rr_rows = exhaustive ? std::min(kRerankMax, std::max(n_rows, 1)) : kRerankMax;
-  dim3 rgrid((rr_rows + 7) / 8, nqt);
+  dim3 rgrid(std::min((rr_rows + 7) / 8, 16), nqt);
   k_nns_rerank<<<rgrid, 256, 0, s>>>(h->d_sel_rows, h->d_sel_cnt, h->d_data, h->d_vv, h->dim,
                                      h->d_q64 + static_cast<size_t>(q0) * h->dim, h->d_uu + q0,
                                      h->d_sel_sims);
@@ -937,7 +954,10 @@ int nns_search_impl(cslam_nns* h, const void* d_queries, int dtype, int nq, int 
   }
   CSLAM_CUDA(cudaEventRecord(h->ev_t0, s));
   const bool exact = (h->mode == 1);
-  int group = exact ? kCoarseBM : kGroupMax;
+  // widest group one pool sweep serves: 256 with the SM-pair kernel (HBM-bound per sweep), 512 with
+  // the cluster-of-4 multicast kernel (CSLAM_NNS_PAIR=0)
+  const bool pair_on = !(getenv("CSLAM_NNS_PAIR") && atoi(getenv("CSLAM_NNS_PAIR")) == 0);
+  int group = exact ? kCoarseBM : (pair_on ? 2 * kCoarseBM : kGroupMax);
   if (!exact && getenv("CSLAM_NNS_GROUP")) group = std::max(kCoarseBM, std::min(kGroupMax, atoi(getenv("CSLAM_NNS_GROUP"))));
   for (int q0 = 0; q0 < nq; q0 += group) {
     const int nqt = std::min(group, nq - q0);

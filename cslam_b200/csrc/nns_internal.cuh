@@ -56,6 +56,8 @@ int make_fp16_rowmajor_tmap(void* out_map, const void* base, int64_t rows, int c
 // tmap_p must have box rows kCoarseBN / prm.cluster; grid = CTAs (a multiple of prm.cluster)
 int launch_coarse_tc(const void* tmap_q, const void* tmap_p, const CoarseParams& prm, int grid,
                      cudaStream_t stream);
+int launch_coarse_pair(const void* tmap_q, const void* tmap_p, const CoarseParams& prm, int grid,
+                       cudaStream_t stream);
 // co-resident clusters of the given size (cudaOccupancyMaxActiveClusters)
 int coarse_tc_max_clusters(int cluster, int* out);
 

@@ -113,10 +113,10 @@ for (n, d, q, k) in ((1000000, 512, 64, 30), (1000000, 512, 64, 1), (1000000, 51
         coarse.append(nn.last_timing()[0])
     cms = float(np.median(coarse))
     dpad = (d + 63) // 64 * 64
-    group = min(q, 512)          # queries served by the timed launch (one cluster group)
+    group = min(q, 256)          # queries served by the timed launch (one SM-pair sweep)
     tiles = (group + 127) // 128
     report(f"A6 k_nns_coarse_tc last group: pool {n}x{d}, {q} queries ({tiles} tile(s) per pool sweep), k={k}", cms,
            n * dpad * 2 + tiles * 128 * dpad * 2, flops=2.0 * tiles * 128 * n * dpad,
            extra={"search_total_ms": total, "queries_per_s": q / (total * 1e-3),
-                  "pool_sweeps": (q + 511) // 512, "info": nn.last_info.tolist()})
+                  "pool_sweeps": (q + 255) // 256, "info": nn.last_info.tolist()})
     del nn

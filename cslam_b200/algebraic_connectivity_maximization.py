@@ -1,21 +1,23 @@
 """AlgebraicConnectivityMaximization — inter-robot loop-closure candidate selection.
 
-Same class, method and attribute names as the reference
-(cslam/algebraic_connectivity_maximization.py:9-572); the graph bookkeeping stays on the
-host (dicts of `EdgeInterRobot`, as the reference tests read them), the numerical work
-(Laplacian, Fiedler pair, gradient, Frank-Wolfe) is delegated to `cslam_b200.mac.mac.MAC`,
-i.e. to the GPU.
+Class, method and attribute names are those of the reference
+(cslam/algebraic_connectivity_maximization.py:9-572) because its callers and tests address
+them (`candidate_edges` is a dict keyed by a 4-tuple, `fixed_edges` a list, `nb_poses`,
+`offsets`, ...).  The graph bookkeeping is host code; all numerical work (Laplacian,
+Fiedler pair, gradient, Frank-Wolfe) runs on the GPU behind `cslam_b200.mac.mac.MAC`.
 
-Quirks of the reference that are reproduced on purpose:
-  * `add_match` looks the un-normalised key up in a dict keyed by the normalised key, so a
-    match with robot0_id > robot1_id always overwrites the stored candidate (:559-572);
-  * `total_nb_poses` sums the poses of ALL robots, included or not (:501-503), and
-    `fill_odometry` chains every robot's poses on its (possibly zero) offset (:348-362);
-    with excluded robots the Laplacian is singular, the solver raises and, after
-    `nb_candidates_to_choose` re-initialisations, the greedy guess is returned (:448-466).
-Differences: `remove_candidate_edges` is O(candidates + edges) instead of the reference's
-O(candidates * edges) list scan (:178-190) — same result.
+Behaviour of the reference that is reproduced on purpose:
+  * `add_match` probes the candidate dict with the key exactly as the match spells it, while
+    the dict is keyed lower-robot-first: a match written with robot0_id > robot1_id never
+    finds the stored entry and always overwrites it (:559-572);
+  * `total_nb_poses` counts the poses of ALL robots, included or not (:501-503), and
+    `fill_odometry` chains every robot from its (possibly zero) offset (:348-362); with an
+    excluded robot the Laplacian is singular, the solver raises, and after
+    `nb_candidates_to_choose` re-initialisations the greedy guess is returned (:448-466).
+Difference: removing candidates is a dict pop per edge, not the reference's scan of the whole
+candidate list per edge (:178-190) — same result.
 """
+import bisect
 from typing import NamedTuple
 
 import numpy as np
@@ -26,346 +28,303 @@ from .mac.utils import Edge
 
 
 class EdgeInterRobot(NamedTuple):
-    """ Inter-robot loop closure edge (reference :9-31)."""
+    """Loop closure between keyframes of two robots (reference :9-31)."""
     robot0_id: int
     robot0_keyframe_id: int
     robot1_id: int
     robot1_keyframe_id: int
     weight: float
 
+    def _ends(self):
+        return frozenset(((self.robot0_id, self.robot0_keyframe_id),
+                          (self.robot1_id, self.robot1_keyframe_id)))
+
     def __eq__(self, other):
-        """Equality ignores the weight and the direction of the edge."""
-        a = (self.robot0_id, self.robot0_keyframe_id)
-        b = (self.robot1_id, self.robot1_keyframe_id)
-        c = (other.robot0_id, other.robot0_keyframe_id)
-        d = (other.robot1_id, other.robot1_keyframe_id)
-        return (a == c and b == d) or (a == d and b == c)
+        # same two vertices, in either direction; the weight does not take part
+        return self._ends() == EdgeInterRobot._ends(other)
 
     def __ne__(self, other):
-        return not self.__eq__(other)
+        return not self == other
 
     __hash__ = tuple.__hash__
 
 
+def _largest(values, count):
+    """0/1 vector marking the `count` largest entries (np.argpartition, like the reference)."""
+    mask = np.zeros(len(values))
+    mask[np.argpartition(values, -count)[-count:]] = 1.0
+    return mask
+
+
 class AlgebraicConnectivityMaximization(object):
 
-    def __init__(self,
-                 robot_id=0,
-                 max_nb_robots=1,
-                 max_iters=20,
-                 fixed_weight=1.0,
-                 extra_params={
-                     "frontend.enable_sparsification": True,
-                     "evaluation.enable_sparsification_comparison": False,
-                 }):
+    def __init__(self, robot_id=0, max_nb_robots=1, max_iters=20, fixed_weight=1.0,
+                 extra_params={"frontend.enable_sparsification": True,
+                               "evaluation.enable_sparsification_comparison": False}):
         """
         Args:
-            robot_id (int, optional): ID of the robot
-            max_nb_robots (int, optional): number of robots. Defaults to 1.
-            max_iters (int, optional): Frank-Wolfe iterations. Defaults to 20.
-            fixed_weight (float, optional): weight of fixed measurements. Defaults to 1.0.
+            robot_id (int): id of the local robot
+            max_nb_robots (int): number of robots in the swarm
+            max_iters (int): Frank-Wolfe iterations of the solver
+            fixed_weight (float): weight given to measured (fixed) edges
+            extra_params (dict): the node's parameter dict
         """
+        self.robot_id = robot_id
+        self.max_nb_robots = max_nb_robots
+        self.max_iters = max_iters
         self.fixed_weight = fixed_weight
         self.params = extra_params
-
+        robots = range(max_nb_robots)
+        self.nb_poses = dict.fromkeys(robots, 0)
+        self.initial_fixed_edge_exists = dict.fromkeys(robots, False)
         self.fixed_edges = []
         self.candidate_edges = {}
         self.already_considered_matches = set()
-
-        self.max_iters = max_iters
-        self.max_nb_robots = max_nb_robots
-        self.robot_id = robot_id
         self.total_nb_poses = 0
-
-        self.nb_poses = {i: 0 for i in range(max_nb_robots)}
-        self.initial_fixed_edge_exists = {i: False for i in range(max_nb_robots)}
-
         self.log_greedy_edges = []
         self.log_mac_edges = []
-        self.last_mac = None          # MAC instance of the last run (stats / traces)
-        self.last_mac_trials = 0      # re-initialisations needed by the last run
+        self.last_mac = None        # solver object of the last run (stats / traces)
+        self.last_mac_trials = 0    # re-initialisations the last run needed
 
-    # ---- keys / small helpers ------------------------------------------------
+    # ------------------------------------------------------------------ small helpers
     def edge_key(self, edge):
-        """Direction-independent key, lower robot id first (reference :76-90)."""
-        if edge.robot0_id < edge.robot1_id:
-            return (edge.robot0_id, edge.robot0_keyframe_id, edge.robot1_id,
-                    edge.robot1_keyframe_id)
-        return (edge.robot1_id, edge.robot1_keyframe_id, edge.robot0_id,
-                edge.robot0_keyframe_id)
+        """Direction-free dictionary key: the lower robot id comes first (reference :76-90)."""
+        a = (edge.robot0_id, edge.robot0_keyframe_id)
+        b = (edge.robot1_id, edge.robot1_keyframe_id)
+        return a + b if edge.robot0_id < edge.robot1_id else b + a
 
     def replace_weight(self, edge, weight):
-        """Copy of `edge` with another weight (reference :92-108)."""
-        if type(edge) is EdgeInterRobot:
-            return EdgeInterRobot(edge.robot0_id, edge.robot0_keyframe_id, edge.robot1_id,
-                                  edge.robot1_keyframe_id, weight)
-        elif type(edge) is Edge:
-            return Edge(edge.i, edge.j, weight)
+        """Same edge, other weight (reference :92-108); None for foreign types, as there."""
+        if type(edge) in (EdgeInterRobot, Edge):
+            return edge._replace(weight=weight)
+        return None
 
     def update_nb_poses(self, edge):
-        """nb_poses[r] = 1 + largest keyframe id seen for robot r (reference :110-119)."""
-        for r, kf in ((edge.robot0_id, edge.robot0_keyframe_id),
-                      (edge.robot1_id, edge.robot1_keyframe_id)):
-            if kf + 1 > self.nb_poses[r]:
-                self.nb_poses[r] = kf + 1
+        """A robot has at least (largest keyframe id seen) + 1 poses (reference :110-119)."""
+        for robot, keyframe in ((edge.robot0_id, edge.robot0_keyframe_id),
+                                (edge.robot1_id, edge.robot1_keyframe_id)):
+            self.nb_poses[robot] = max(self.nb_poses[robot], keyframe + 1)
 
     def update_initial_fixed_edge_exists(self, fixed_edge):
-        """Remember which robots already share a fixed inter-robot edge (reference :121-130)."""
-        if fixed_edge.robot0_id != fixed_edge.robot1_id:
-            self.initial_fixed_edge_exists[fixed_edge.robot0_id] = True
-            self.initial_fixed_edge_exists[fixed_edge.robot1_id] = True
+        """Robots joined by a measured inter-robot edge (reference :121-130)."""
+        if fixed_edge.robot0_id == fixed_edge.robot1_id:
+            return
+        self.initial_fixed_edge_exists[fixed_edge.robot0_id] = True
+        self.initial_fixed_edge_exists[fixed_edge.robot1_id] = True
 
-    # ---- graph editing ---------------------------------------------------------
+    # ------------------------------------------------------------------ graph editing
     def set_graph(self, fixed_edges, candidate_edges):
-        """Fill the graph (reference :132-152)."""
+        """Install a whole graph (reference :132-152)."""
         self.fixed_edges = fixed_edges
-        for e in self.fixed_edges:
-            self.update_nb_poses(e)
-            self.update_initial_fixed_edge_exists(e)
-        for e in candidate_edges:
-            self.update_nb_poses(e)
-        for e in candidate_edges:
-            self.candidate_edges[self.edge_key(e)] = e
+        for edge in fixed_edges:
+            self.update_nb_poses(edge)
+            self.update_initial_fixed_edge_exists(edge)
+        for edge in candidate_edges:
+            self.update_nb_poses(edge)
+            self.candidate_edges[self.edge_key(edge)] = edge
 
     def add_fixed_edge(self, edge):
-        """Add an already computed edge (reference :154-163)."""
+        """A measured edge (reference :154-163)."""
         self.fixed_edges.append(edge)
         self.update_nb_poses(edge)
         self.update_initial_fixed_edge_exists(edge)
 
     def add_candidate_edge(self, edge):
-        """Add a candidate unless it was already tried or fixed (reference :165-178)."""
+        """A candidate, unless that pair was already selected or measured (reference :165-178)."""
         key = self.edge_key(edge)
-        if key in self.already_considered_matches:
-            return
-        self.candidate_edges[key] = edge
-        self.update_nb_poses(edge)
+        if key not in self.already_considered_matches:
+            self.candidate_edges[key] = edge
+            self.update_nb_poses(edge)
 
     def remove_candidate_edges(self, edges, failed=False):
-        """Drop candidates and blacklist them (reference :178-190)."""
-        for edge in edges:
-            key = self.edge_key(edge)
+        """Forget candidates for good (reference :178-190)."""
+        for key in map(self.edge_key, edges):
             self.candidate_edges.pop(key, None)
             self.already_considered_matches.add(key)
 
     def candidate_edges_to_fixed(self, edges):
-        """Candidates that became measurements: fixed weight, fixed list (reference :192-203)."""
-        for i in range(len(edges)):
-            edges[i] = self.replace_weight(edges[i], weight=self.fixed_weight)
-            self.update_initial_fixed_edge_exists(edges[i])
+        """Verified candidates become measurements with the fixed weight (reference :192-203;
+        like there, the caller's list is rewritten in place)."""
+        edges[:] = [self.replace_weight(e, weight=self.fixed_weight) for e in edges]
+        for edge in edges:
+            self.update_initial_fixed_edge_exists(edge)
         self.fixed_edges.extend(edges)
         self.remove_candidate_edges(edges)
 
-    # ---- initial guesses -------------------------------------------------------
+    def add_match(self, match):
+        """Candidate from a descriptor match; a stored candidate is only replaced by a heavier
+        one — when the lookup finds it (see the module docstring; reference :559-572)."""
+        stored = self.candidate_edges.get((match.robot0_id, match.robot0_keyframe_id,
+                                           match.robot1_id, match.robot1_keyframe_id))
+        if stored is None or match.weight > stored.weight:
+            self.add_candidate_edge(match)
+
+    # ------------------------------------------------------------------ initial guesses
     def greedy_initialization(self, nb_candidates_to_choose, edges):
-        """1.0 on the `nb_candidates_to_choose` largest weights (reference :205-218)."""
-        weights = [e.weight for e in edges]
-        w_init = np.zeros(len(weights))
-        indices = np.argpartition(weights, -nb_candidates_to_choose)[-nb_candidates_to_choose:]
-        w_init[indices] = 1.0
-        return w_init
+        """The heaviest candidates (reference :205-218)."""
+        return _largest([e.weight for e in edges], nb_candidates_to_choose)
 
     def pseudo_greedy_initialization(self, nb_candidates_to_choose, nb_random, edges):
-        """Greedy for all but `nb_random` picks, those at random (reference :220-245)."""
+        """Greedy except for `nb_random` picks drawn with np.random.rand (at most 2*nb_random
+        draws, else plain greedy) (reference :220-245)."""
         w_init = self.greedy_initialization(nb_candidates_to_choose - nb_random, edges)
-        nb_edges = len(edges)
-        picked, trial, max_trials = 0, 0, 2 * nb_random
-        while picked < nb_random and trial < max_trials:
-            j = int(np.random.rand() * nb_edges)
+        draws_left, missing = 2 * nb_random, nb_random
+        while missing > 0 and draws_left > 0:
+            j = int(np.random.rand() * len(edges))
+            draws_left -= 1
             if w_init[j] < 0.5:
                 w_init[j] = 1.0
-                picked += 1
-            trial += 1
-        if trial >= max_trials:
-            w_init = self.greedy_initialization(nb_candidates_to_choose, edges)
+                missing -= 1
+        if draws_left <= 0:
+            return self.greedy_initialization(nb_candidates_to_choose, edges)
         return w_init
 
     def random_initialization(self, nb_candidates_to_choose, edges):
-        """Random weights, then greedy (reference :247-255; mutates `edges`)."""
-        for e in range(len(edges)):
-            edges[e] = self.replace_weight(edges[e], np.random.rand())
+        """Greedy over weights redrawn from U(0,1); rewrites `edges` like the reference (:247-255)."""
+        edges[:] = [self.replace_weight(e, np.random.rand()) for e in edges]
         return self.greedy_initialization(nb_candidates_to_choose, edges)
 
-    def connection_biased_greedy_selection(self, nb_candidates_to_choose, edges,
-                                           is_robot_included):
-        """Greedy selection that first links robots without a fixed edge (reference :257-289)."""
-        edges_copy = edges.copy()
+    def connection_biased_greedy_selection(self, nb_candidates_to_choose, edges, is_robot_included):
+        """Greedy selection that first gives every included robot without a measured
+        inter-robot edge its heaviest candidate (reference :257-289)."""
+        pool = list(edges)
         forced = []
-        for rid in [r for r in is_robot_included.keys() if is_robot_included[r]]:
-            if self.initial_fixed_edge_exists[rid]:
+        for robot in (r for r, inc in is_robot_included.items() if inc):
+            if self.initial_fixed_edge_exists[robot]:
                 continue
-            best, best_w = None, -1
-            for i, e in enumerate(edges_copy):
-                if (e.robot0_id == rid or e.robot1_id == rid) and e.weight > best_w:
-                    best, best_w = i, e.weight
-            if best is not None:
+            touching = [(e.weight, -i) for i, e in enumerate(pool)
+                        if robot in (e.robot0_id, e.robot1_id) and e.weight > -1]
+            if touching:
+                best = -max(touching)[1]          # heaviest, first one among equals
                 forced.append(best)
-                edges_copy[best] = self.replace_weight(edges_copy[best], weight=0.0)
+                pool[best] = self.replace_weight(pool[best], weight=0.0)
         w_init = np.zeros(len(edges))
-        if nb_candidates_to_choose - len(forced) > 0:
-            w_init = self.greedy_initialization(nb_candidates_to_choose - len(forced),
-                                                self.rekey_edges(edges_copy, is_robot_included))
-        for i in forced:
-            w_init[i] = 1.0
+        free = nb_candidates_to_choose - len(forced)
+        if free > 0:
+            w_init = self.greedy_initialization(free, self.rekey_edges(pool, is_robot_included))
+        w_init[forced] = 1.0
         return w_init
 
-    # ---- rekeying ----------------------------------------------------------------
+    # ------------------------------------------------------------------ (robot, keyframe) <-> node id
     def compute_offsets(self, is_robot_included):
-        """Node-id offset of every included robot: running sum of nb_poses (reference :291-310)."""
-        self.offsets = {i: 0 for i in range(self.max_nb_robots)}
-        running = 0
-        for rid in range(self.max_nb_robots):
-            if is_robot_included[rid]:
-                self.offsets[rid] = running
-                running += self.nb_poses[rid]
-
-    def rekey_edges(self, edges, is_robot_included):
-        """(robot, keyframe) pairs -> global node ids; edges touching an excluded robot are
-        dropped (reference :312-335)."""
-        out = []
-        for e in edges:
-            if is_robot_included[e.robot0_id] and is_robot_included[e.robot1_id]:
-                out.append(Edge(self.offsets[e.robot0_id] + e.robot0_keyframe_id,
-                                self.offsets[e.robot1_id] + e.robot1_keyframe_id, e.weight))
-        return out
+        """First node id of every included robot: running sum of nb_poses; excluded robots
+        keep offset 0 (reference :291-310)."""
+        self.offsets = dict.fromkeys(range(self.max_nb_robots), 0)
+        start = 0
+        for robot in range(self.max_nb_robots):
+            if is_robot_included[robot]:
+                self.offsets[robot] = start
+                start += self.nb_poses[robot]
 
     def get_included_edges(self, edges, is_robot_included):
-        """Edges whose two robots are included (reference :337-346)."""
+        """Edges between two included robots (reference :337-346)."""
         return [e for e in edges
                 if is_robot_included[e.robot0_id] and is_robot_included[e.robot1_id]]
 
+    def rekey_edges(self, edges, is_robot_included):
+        """Inter-robot edges -> `Edge(i, j, weight)` on global node ids (reference :312-335)."""
+        off = self.offsets
+        return [Edge(off[e.robot0_id] + e.robot0_keyframe_id,
+                     off[e.robot1_id] + e.robot1_keyframe_id, e.weight)
+                for e in self.get_included_edges(edges, is_robot_included)]
+
     def fill_odometry(self):
-        """Implicit odometry chains, weight `fixed_weight` (reference :348-362)."""
-        odom = []
-        for i in range(len(self.nb_poses)):
-            base = self.offsets[i]
-            for k in range(self.nb_poses[i] - 1):
-                odom.append(Edge(base + k, base + k + 1, self.fixed_weight))
-        return odom
+        """Consecutive poses of each robot, weight `fixed_weight` (reference :348-362)."""
+        chains = []
+        for robot in range(len(self.nb_poses)):
+            first = self.offsets[robot]
+            chains.extend(Edge(i, i + 1, self.fixed_weight)
+                          for i in range(first, first + self.nb_poses[robot] - 1))
+        return chains
 
     def recover_inter_robot_edges(self, edges, is_robot_included):
-        """Inverse of `rekey_edges` (reference :364-389)."""
+        """Node ids back to (robot, keyframe): the owner of a node is the last included robot
+        (other than robot 0, the default) whose offset does not exceed it (reference :364-389)."""
+        owners = [r for r in self.offsets if r != 0 and is_robot_included[r]]
+        starts = [self.offsets[r] for r in owners]
+
+        def owner(node):
+            pos = bisect.bisect_right(starts, node)
+            return owners[pos - 1] if pos > 0 else 0
+
         out = []
         for e in edges:
-            r0 = r1 = 0
-            for o in self.offsets:
-                if o != 0 and is_robot_included[o]:
-                    if e.i >= self.offsets[o]:
-                        r0 = o
-                    if e.j >= self.offsets[o]:
-                        r1 = o
-            out.append(EdgeInterRobot(r0, e.i - self.offsets[r0], r1, e.j - self.offsets[r1],
-                                      e.weight))
+            r0, r1 = owner(e.i), owner(e.j)
+            out.append(EdgeInterRobot(r0, e.i - self.offsets[r0], r1, e.j - self.offsets[r1], e.weight))
         return out
 
-    # ---- inclusion logic --------------------------------------------------------------
+    # ------------------------------------------------------------------ which robots take part
     def check_graph_disconnections(self, is_other_robot_considered):
-        """A robot is included if it is the local one or appears in any fixed/candidate edge
-        while being in range (reference :391-417)."""
-        connected = {i: (i == self.robot_id) for i in range(self.max_nb_robots)}
+        """The local robot, plus every robot in range that appears in some edge (reference :391-417)."""
+        seen = {self.robot_id}
         for edge in list(self.fixed_edges) + list(self.candidate_edges.values()):
-            if is_other_robot_considered[edge.robot0_id]:
-                connected[edge.robot0_id] = True
-            if is_other_robot_considered[edge.robot1_id]:
-                connected[edge.robot1_id] = True
-        return connected
+            seen.update(r for r in (edge.robot0_id, edge.robot1_id) if is_other_robot_considered[r])
+        return {r: r in seen for r in range(self.max_nb_robots)}
 
     def check_initial_fixed_measurements_exists(self, is_robot_included):
-        """True when every included robot already has a fixed inter-robot edge (reference :419-434)."""
-        return all(self.initial_fixed_edge_exists[rid]
-                   for rid in is_robot_included if is_robot_included[rid])
+        """Does every included robot already share a measured edge with another one? (reference :419-434)"""
+        return all(self.initial_fixed_edge_exists[r] for r, inc in is_robot_included.items() if inc)
 
-    # ---- solver ---------------------------------------------------------------------------
+    # ------------------------------------------------------------------ solver
     def run_mac_solver(self, fixed_edges, candidate_edges, w_init, nb_candidates_to_choose):
-        """Frank-Wolfe on the GPU with the reference's retry policy (reference :436-466): if the
-        Laplacian is singular (graph disconnected) the initial guess is re-drawn with
-        increasing randomness, at most `nb_candidates_to_choose` times, else the initial
-        guess is returned."""
-        mac = MAC(fixed_edges, candidate_edges, self.total_nb_poses)
-        self.last_mac = mac
-        result = w_init.copy()
-        trial = 0
-        while trial < nb_candidates_to_choose:
+        """GPU Frank-Wolfe with the reference's retry policy (:436-466): a singular Laplacian
+        (disconnected graph) re-draws the start with one more random pick each time, at most
+        `nb_candidates_to_choose` times, then the start vector itself is the answer."""
+        mac = self.last_mac = MAC(fixed_edges, candidate_edges, self.total_nb_poses)
+        answer = w_init.copy()
+        for trial in range(nb_candidates_to_choose):
             try:
-                result, _, _ = mac.fw_subset(w_init, nb_candidates_to_choose,
-                                             max_iters=self.max_iters)
-                break
-            except CslamError:
-                # reference: bare `except` around a SuperLU "Factor is exactly singular"
-                trial += 1
-                w_init = self.pseudo_greedy_initialization(nb_candidates_to_choose, trial,
+                answer = mac.fw_subset(w_init, nb_candidates_to_choose, max_iters=self.max_iters)[0]
+                self.last_mac_trials = trial
+                return answer
+            except CslamError:    # the reference swallows SuperLU's "Factor is exactly singular"
+                w_init = self.pseudo_greedy_initialization(nb_candidates_to_choose, trial + 1,
                                                            candidate_edges)
-        self.last_mac_trials = trial
-        return result
+        self.last_mac_trials = nb_candidates_to_choose
+        return answer
 
     def select_candidates(self, nb_candidates_to_choose, is_other_robot_considered,
                           greedy_initialization=True):
-        """Solve algebraic connectivity maximisation (reference :468-543).
+        """Choose the candidates that maximise the algebraic connectivity (reference :468-543).
 
         Args:
             nb_candidates_to_choose (int): budget
-            is_other_robot_considered: dict(int, bool): robots in communication range
-            greedy_initialization: initialise from the similarity weights
-
+            is_other_robot_considered (dict(int, bool)): robots in communication range
+            greedy_initialization (bool): start from the heaviest candidates (else random)
         Returns:
-            list(EdgeInterRobot): selected edges
+            list(EdgeInterRobot): the selection; it is removed from the candidates
         """
-        is_robot_included = self.check_graph_disconnections(is_other_robot_considered)
-
-        self.compute_offsets(is_robot_included)
-        rekeyed_fixed_edges = self.rekey_edges(self.fixed_edges, is_robot_included)
-        rekeyed_fixed_edges.extend(self.fill_odometry())
-        rekeyed_candidate_edges = self.rekey_edges(self.candidate_edges.values(),
-                                                   is_robot_included)
-
-        if nb_candidates_to_choose > len(rekeyed_candidate_edges):
-            nb_candidates_to_choose = len(rekeyed_candidate_edges)
-        if len(rekeyed_candidate_edges) == 0:
+        included = self.check_graph_disconnections(is_other_robot_considered)
+        self.compute_offsets(included)
+        fixed = self.rekey_edges(self.fixed_edges, included) + self.fill_odometry()
+        candidates = self.rekey_edges(self.candidate_edges.values(), included)
+        if not candidates:
             return []
+        budget = min(nb_candidates_to_choose, len(candidates))
+        self.total_nb_poses = sum(self.nb_poses.values())
 
-        self.total_nb_poses = sum(self.nb_poses[n] for n in range(len(self.nb_poses)))
-
-        if greedy_initialization:
-            w_init = self.greedy_initialization(nb_candidates_to_choose, rekeyed_candidate_edges)
-        else:
-            w_init = self.random_initialization(nb_candidates_to_choose, rekeyed_candidate_edges)
-
+        start = (self.greedy_initialization if greedy_initialization
+                 else self.random_initialization)(budget, candidates)
         if self.params["frontend.enable_sparsification"] and \
-                self.check_initial_fixed_measurements_exists(is_robot_included):
-            result = self.run_mac_solver(rekeyed_fixed_edges, rekeyed_candidate_edges, w_init,
-                                         nb_candidates_to_choose)
+                self.check_initial_fixed_measurements_exists(included):
+            chosen = self.run_mac_solver(fixed, candidates, start, budget)
         else:
-            result = self.connection_biased_greedy_selection(
-                nb_candidates_to_choose,
-                self.get_included_edges(self.candidate_edges.values(), is_robot_included),
-                is_robot_included)
+            chosen = self.connection_biased_greedy_selection(
+                budget, self.get_included_edges(self.candidate_edges.values(), included), included)
 
         if self.params["evaluation.enable_sparsification_comparison"]:
-            self.sparsification_comparison_logs(rekeyed_candidate_edges, is_robot_included,
-                                                w_init, result)
-
-        selected_edges = [rekeyed_candidate_edges[i] for i in np.nonzero(result.astype(int))[0]]
-        inter_robot_edges = self.recover_inter_robot_edges(selected_edges, is_robot_included)
-        self.remove_candidate_edges(inter_robot_edges)
-        return inter_robot_edges
+            self.sparsification_comparison_logs(candidates, included, start, chosen)
+        picked = [candidates[i] for i in np.flatnonzero(np.asarray(chosen).astype(int))]
+        selection = self.recover_inter_robot_edges(picked, included)
+        self.remove_candidate_edges(selection)
+        return selection
 
     def sparsification_comparison_logs(self, rekeyed_candidate_edges, is_robot_included,
                                        greedy_result, mac_result):
-        """Keep the greedy and the MAC selections for evaluation logs (reference :545-557)."""
-        self.log_greedy_edges = self.recover_inter_robot_edges(
-            [rekeyed_candidate_edges[i] for i in np.nonzero(greedy_result.astype(int))[0]],
-            is_robot_included)
-        self.log_mac_edges = self.recover_inter_robot_edges(
-            [rekeyed_candidate_edges[i] for i in np.nonzero(mac_result.astype(int))[0]],
-            is_robot_included)
-
-    def add_match(self, match):
-        """Add a potential match, keeping the better weight (reference :559-572, including its
-        un-normalised key lookup)."""
-        key = (match.robot0_id, match.robot0_keyframe_id, match.robot1_id,
-               match.robot1_keyframe_id)
-        if key in self.candidate_edges:
-            if match.weight > self.candidate_edges[key].weight:
-                self.add_candidate_edge(match)
-        else:
-            self.add_candidate_edge(match)
+        """Keep both selections for the evaluation topics (reference :545-557)."""
+        def as_edges(mask):
+            return self.recover_inter_robot_edges(
+                [rekeyed_candidate_edges[i] for i in np.flatnonzero(np.asarray(mask).astype(int))],
+                is_robot_included)
+        self.log_greedy_edges = as_edges(greedy_result)
+        self.log_mac_edges = as_edges(mac_result)

@@ -202,8 +202,16 @@ class GlobalDescriptorLoopClosureDetection(object):
                 buf = torch.empty(shape, dtype=torch.uint8).pin_memory()
                 self._pinned_images = buf
             view = buf[:shape[0]].numpy()
-            for b, img in enumerate(images):
-                view[b] = img
+            if len(images) >= 8:
+                # numpy releases the GIL while copying: a few threads fill the staging buffer
+                pool = getattr(self, "_copy_pool", None)
+                if pool is None:
+                    from concurrent.futures import ThreadPoolExecutor
+                    pool = self._copy_pool = ThreadPoolExecutor(max_workers=4)
+                list(pool.map(lambda bi: np.copyto(view[bi[0]], bi[1]), enumerate(images)))
+            else:
+                for b, img in enumerate(images):
+                    view[b] = img
             batch = buf[:shape[0]]
         emb = self.global_descriptor.compute_embeddings_device(batch)
         return self.add_global_descriptors_to_map(emb, [m.id for m in keyframe_msgs])

@@ -1951,7 +1951,7 @@ struct FiedlerSolver {
   }
 
   static int persist_threads(int ch) {
-    return ch == 1 ? 1024 : ch == 2 ? 512 : (ch == 4 || ch == 8) ? 256 : 0;
+    return (ch == 4 || ch == 8) ? 256 : 0;   // 256-thread CTAs, 4 or 8 rows per thread
   }
   // rows per thread of the persistent kernel for this problem size (0 = not applicable)
   int persist_rows_per_thread() const {
@@ -1995,8 +1995,6 @@ struct FiedlerSolver {
     const void* fn = nullptr;
     int threads = 0;
     switch (ch) {
-      case 1: fn = reinterpret_cast<const void*>(&k_lobpcg_persist<1, 1024>); threads = 1024; break;
-      case 2: fn = reinterpret_cast<const void*>(&k_lobpcg_persist<2, 512>); threads = 512; break;
       case 4: fn = reinterpret_cast<const void*>(&k_lobpcg_persist<4, 256>); threads = 256; break;
       case 8: fn = reinterpret_cast<const void*>(&k_lobpcg_persist<8, 256>); threads = 256; break;
       default: set_error("fiedler: bad persistent variant %d", ch); return CSLAM_ERR_INVALID;

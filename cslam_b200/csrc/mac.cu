@@ -863,11 +863,6 @@ __global__ void k_fw_update(int64_t n, double alpha, const double* __restrict__ 
   w[e] = __dadd_rn(w[e], __dmul_rn(alpha, __dsub_rn(s[e], w[e])));
 }
 
-__global__ void k_gather(int cnt, const int* __restrict__ idx, const double* __restrict__ src,
-                         double* __restrict__ dst) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < cnt) dst[i] = src[idx[i]];
-}
 
 // ------------------------------------------------------------------ small dense math
 // Symmetric generalized eigenproblem GA y = theta GB y for s <= MAXS, smallest m pairs.
@@ -1854,6 +1849,8 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 }
 
 // ------------------------------------------------------------------ solver object
+constexpr int kPersistUnavailable = 1;   // internal status: fall back to the multi-kernel path
+
 struct FiedlerSolver {
   int device = 0;
   int n = 0;
@@ -2010,7 +2007,16 @@ struct FiedlerSolver {
       CSLAM_CUDA(cudaEventCreate(&pev1));
     }
     CSLAM_CUDA(cudaEventRecord(pev0, stream));
-    CSLAM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms), dim3(threads), args, dyn, stream));
+    {
+      const cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(num_sms), dim3(threads), args, dyn, stream);
+      if (le != cudaSuccess) {
+        // the grid cannot be made co-resident (GPU shared with another context, MPS limits, ...):
+        // the grid barrier would deadlock, so this handle uses the multi-kernel solver from now on
+        cudaGetLastError();
+        persist_variant = 0;
+        return kPersistUnavailable;
+      }
+    }
     CSLAM_CUDA(cudaEventRecord(pev1, stream));
     count_launch();
     CSLAM_CUDA(cudaMemcpyAsync(h_red, pout, (MAXM + 3) * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -2279,7 +2285,9 @@ struct FiedlerSolver {
     if (const int ch = persist_rows_per_thread()) {
       // one cooperative kernel: start-up pass (centre X, AX = L X, Rayleigh-Ritz) + LOBPCG loop
       int status = 1;
-      CSLAM_TRY(persist_loop(ch, tol, max_iters, theta, false, true, &it, &status));
+      const int pst = persist_loop(ch, tol, max_iters, theta, false, true, &it, &status);
+      if (pst != CSLAM_OK && pst != kPersistUnavailable) return pst;
+      if (pst == CSLAM_OK) {
       if (prof) t_loop += now() - tp2;
       last_path = 1;
       last_iters = std::max(it, 0);
@@ -2294,6 +2302,8 @@ struct FiedlerSolver {
       *lambda2 = theta[0];
       warm = true;
       return CSLAM_OK;
+      }
+      it = 0;   // cooperative launch unavailable: continue on the multi-kernel path
     }
     // multi-kernel path: project X onto 1-perp and form AX
     CSLAM_TRY(colsum_of(X));

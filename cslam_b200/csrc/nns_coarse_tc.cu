@@ -191,7 +191,7 @@ k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
 
   const int num_kb = prm.num_kb;
   long long* dbg = (prm.dbg != nullptr && blockIdx.x == 0) ? prm.dbg : nullptr;
-  long long w_acc0 = 0, w_acc1 = 0, w_acc2 = 0;
+  long long w_acc0 = 0, w_acc1 = 0;
   auto timed_wait = [&](uint32_t bar, uint32_t parity, long long& acc) {
     if (dbg) {
       const long long t0 = clock64();
@@ -313,7 +313,6 @@ k_nns_coarse_tc(const __grid_constant__ CUtensorMap tmap_q,
     uint32_t* my_smax = prm.smax + static_cast<size_t>(qs) * prm.smax_stride;
     unsigned int my_count = 0;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    constexpr int HALF_N = BN / 2;
     int it = 0;
     for (int tile = first_tile; tile < prm.num_tiles; tile += tile_step, ++it) {
       const int buf = it & 1;

@@ -1233,6 +1233,13 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 //      (<= 6x6) Rayleigh-Ritz problem, all threads update X, AX, P, AP in registers
 // The multi-kernel path above needs ~13 launches and one host round trip per iteration
 // (~140 us at n = 100k); this kernel needs neither.
+// W gathers after the grid barrier: the barrier's acquire makes plain (L1-allocating) loads see
+// the other CTAs' stores; CSLAM_W_LDCG selects ld.global.cg instead (compile-time experiment)
+#ifdef CSLAM_W_LDCG
+#define W_LOAD(p) __ldcg(p)
+#else
+#define W_LOAD(p) (*(p))
+#endif
 constexpr bool kUseWCache = false;   // shared copy of the CTA's own W rows (measured slower: see DESIGN.md)
 struct PersistArgs {
   int n, m, rpb;         // rows, block size of the eigen-solver, rows per CTA
@@ -1625,7 +1632,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       const int li = loc ? col - r_lo_cta : 0;
       const double vs = s_w[c * a.rpb + li];
       double vg = 0.0;
-      if (on && !loc) vg = __ldcg(a.W + static_cast<size_t>(c) * ld + col);
+      if (on && !loc) vg = W_LOAD(a.W + static_cast<size_t>(c) * ld + col);
       return loc ? vs : vg;
     };
     if (!init_pass) {
@@ -1651,6 +1658,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
             gw[j][e][c] = (on && c < m) ? w_at(c, col, on && c < m) : mu[c];
         }
       }
+      tick(10);
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
         if (valid[j]) {
@@ -1662,20 +1670,28 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 #pragma unroll
             for (int c = 0; c < MAXM; ++c)
               if (c < m) acc[c] = fma(gv[j][e], gw[j][e][c] - mu[c], acc[c]);
-          for (int q = q0s[j] + PF; q < q0e[j]; ++q) {
-            const double v = V0[q];
-            const int col = C0[q];
+          // longer rows: four gathers in flight at a time (a serial loop would pay one L2 round
+          // trip per entry, and the slowest row of the CTA sets the pace of the phase)
+          auto tail = [&](const int* Cx, const double* Vx, int q0, int q1) {
+            for (int q = q0; q < q1; q += 4) {
+              double tv[4], tw[4][MAXM];
 #pragma unroll
-            for (int c = 0; c < MAXM; ++c)
-              if (c < m) acc[c] = fma(v, w_at(c, col, true) - mu[c], acc[c]);
-          }
-          for (int q = q1s[j] + PA; q < q1e[j]; ++q) {
-            const double v = V1[q];
-            const int col = C1[q];
+              for (int u = 0; u < 4; ++u) {
+                const bool on = q + u < q1;
+                tv[u] = on ? Vx[q + u] : 0.0;
+                const int col = on ? Cx[q + u] : 0;
 #pragma unroll
-            for (int c = 0; c < MAXM; ++c)
-              if (c < m) acc[c] = fma(v, w_at(c, col, true) - mu[c], acc[c]);
-          }
+                for (int c = 0; c < MAXM; ++c) tw[u][c] = (on && c < m) ? w_at(c, col, true) : mu[c];
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int c = 0; c < MAXM; ++c)
+                  if (c < m) acc[c] = fma(tv[u], tw[u][c] - mu[c], acc[c]);
+            }
+          };
+          tail(C0, V0, q0s[j] + PF, q0e[j]);
+          tail(C1, V1, q1s[j] + PA, q1e[j]);
 #pragma unroll
           for (int c = 0; c < MAXM; ++c)
             if (c < m) {
@@ -1834,11 +1850,12 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
           a.AP[o] = ap[j][c];
         }
   if (do_prof) {
-    for (int k = 0; k < 8; ++k) a.prof[k] += prof_acc[k];
+    for (int k = 0; k < 7; ++k) a.prof[k] += prof_acc[k];
     for (int k = 0; k < 5; ++k) a.prof[8 + k] += rrprof_acc[k];
     a.prof[13] += it;
     a.prof[14] += prof_acc[8];
-    a.prof[15] += prof_acc[9];
+    a.prof[15] += prof_acc[9] + prof_acc[10];
+    a.prof[7] += prof_acc[10];
   }
   if (b == 0 && tid == 0) {
     for (int c = 0; c < MAXM; ++c) a.out[c] = theta[c];
@@ -2048,9 +2065,9 @@ struct FiedlerSolver {
       long long hp[16] = {};
       cudaMemcpy(hp, pprof, sizeof(hp), cudaMemcpyDeviceToHost);
       const double it_ = static_cast<double>(std::max<long long>(hp[13], 1));
-      fprintf(stderr, "[cslam lobpcg prof] cycles/iter over %lld iters: p1 %.0f p2 %.0f p3 %.0f p4 %.0f p5 %.0f rr %.0f barriers %.0f | rr: setup %.0f chol %.0f tri %.0f jacobi %.0f back %.0f | p4: gridsum %.0f spmm %.0f (gram = p4)\n",
+      fprintf(stderr, "[cslam lobpcg prof] cycles/iter over %lld iters: p1 %.0f p2 %.0f p3 %.0f p4 %.0f p5 %.0f rr %.0f barriers %.0f | rr: setup %.0f chol %.0f tri %.0f jacobi %.0f back %.0f | p4: gridsum %.0f spmm %.0f (of which gather issue %.0f) (gram = p4)\n",
               hp[13], hp[0] / it_, hp[1] / it_, hp[2] / it_, hp[3] / it_, hp[4] / it_, hp[5] / it_, hp[6] / it_,
-              hp[8] / it_, hp[9] / it_, hp[10] / it_, hp[11] / it_, hp[12] / it_, hp[14] / it_, hp[15] / it_);
+              hp[8] / it_, hp[9] / it_, hp[10] / it_, hp[11] / it_, hp[12] / it_, hp[14] / it_, hp[15] / it_, hp[7] / it_);
       dev_free(pprof);
     }
     dev_free(pbar);

@@ -1,3 +1,3 @@
-timeout 600 python -m pytest tests/test_mac_gpu.py tests/test_acm_gpu.py -x -q 2>&1 | tail -2
-CSLAM_LOBPCG_PROF=1 timeout 300 python tools/probe_mac.py --reps 3 --bs 2 2>&1 | grep -E "prof|fw_subset" | tail -3
-timeout 300 python tools/probe_mac.py --R 4 --P 5000 --m 20000 --k 200 --reps 1 --bs 2 --oracle 1 2>&1 | tail -1
+set -x
+CSLAM_LOBPCG_PROF=1 timeout 300 python tools/probe_mac.py --reps 3 --bs 2 > gpurun_out/probe_mac_prof_final.log 2>&1; tail -3 gpurun_out/probe_mac_prof_final.log | cut -c1-300
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r1_n1.json 2> gpurun_out/bench_r1_n1.err; tail -2 gpurun_out/bench_r1_n1.err; cut -c1-250 gpurun_out/bench_r1_n1.json

@@ -16,6 +16,13 @@ Behaviour of the reference that is reproduced on purpose:
     `nb_candidates_to_choose` re-initialisations the greedy guess is returned (:448-466).
 Difference: removing candidates is a dict pop per edge, not the reference's scan of the whole
 candidate list per edge (:178-190) — same result.
+
+Scale: `candidate_edges` is a `CandidateTable` — the reference's dict
+plus numpy columns kept in step with it — and `select_candidates` sets the problem up from
+those columns (inclusion, offsets, rekeying, greedy start, recovery of the picked edges) without
+walking the candidates in Python; `add_matches` is the bulk form of `add_match`.  The
+edge-by-edge methods of the reference API remain and are used whenever `candidate_edges` was
+replaced by a plain dict.
 """
 import bisect
 from typing import NamedTuple
@@ -23,6 +30,7 @@ from typing import NamedTuple
 import numpy as np
 
 from ._lib import CslamError
+from .candidate_table import CandidateTable
 from .mac.mac import MAC
 from .mac.utils import Edge
 
@@ -56,6 +64,31 @@ def _largest(values, count):
     return mask
 
 
+def _is_columns(edges):
+    """True for the (i, j, weight) array triple that stands in for a list of `Edge`."""
+    return isinstance(edges, tuple) and len(edges) == 3 and isinstance(edges[0], np.ndarray)
+
+
+def _weights_of(edges):
+    return edges[2] if _is_columns(edges) else [e.weight for e in edges]
+
+
+def _count(edges):
+    return len(edges[2]) if _is_columns(edges) else len(edges)
+
+
+def _picked(edges, mask):
+    """The edges whose entry of the 0/1 vector `mask` is set, as a list of `Edge`."""
+    idx = np.flatnonzero(np.asarray(mask).astype(int))
+    if _is_columns(edges):
+        i, j, w = edges
+        return [Edge(int(i[t]), int(j[t]), float(w[t])) for t in idx]
+    return [edges[t] for t in idx]
+
+
+_KF_BITS = 40   # keyframe ids below 2^40, robot ids below 2^23: one int64 per (robot, keyframe)
+
+
 class AlgebraicConnectivityMaximization(object):
 
     def __init__(self, robot_id=0, max_nb_robots=1, max_iters=20, fixed_weight=1.0,
@@ -78,7 +111,7 @@ class AlgebraicConnectivityMaximization(object):
         self.nb_poses = dict.fromkeys(robots, 0)
         self.initial_fixed_edge_exists = dict.fromkeys(robots, False)
         self.fixed_edges = []
-        self.candidate_edges = {}
+        self.candidate_edges = CandidateTable(EdgeInterRobot)
         self.already_considered_matches = set()
         self.total_nb_poses = 0
         self.log_greedy_edges = []
@@ -138,9 +171,13 @@ class AlgebraicConnectivityMaximization(object):
 
     def remove_candidate_edges(self, edges, failed=False):
         """Forget candidates for good (reference :178-190)."""
-        for key in map(self.edge_key, edges):
-            self.candidate_edges.pop(key, None)
-            self.already_considered_matches.add(key)
+        keys = [self.edge_key(e) for e in edges]
+        if isinstance(self.candidate_edges, CandidateTable):
+            self.candidate_edges.remove_keys(keys)
+        else:
+            for key in keys:
+                self.candidate_edges.pop(key, None)
+        self.already_considered_matches.update(keys)
 
     def candidate_edges_to_fixed(self, edges):
         """Verified candidates become measurements with the fixed weight (reference :192-203;
@@ -159,10 +196,80 @@ class AlgebraicConnectivityMaximization(object):
         if stored is None or match.weight > stored.weight:
             self.add_candidate_edge(match)
 
+    def add_matches(self, robot0_id, robot0_keyframe_id, robot1_id, robot1_keyframe_id, weight):
+        """`add_match` for a whole batch given as five equally long arrays: the candidate
+        table ends up exactly as if the matches had been passed to `add_match` one after the
+        other (including the reversed-key overwrite of :565-569 and the blacklist of
+        :170-171), but the work per match is a few numpy passes; Python touches each DISTINCT
+        vertex pair once."""
+        r0 = np.asarray(robot0_id, dtype=np.int64).ravel()
+        k0 = np.asarray(robot0_keyframe_id, dtype=np.int64).ravel()
+        r1 = np.asarray(robot1_id, dtype=np.int64).ravel()
+        k1 = np.asarray(robot1_keyframe_id, dtype=np.int64).ravel()
+        w = np.asarray(weight, dtype=np.float64).ravel()
+        n = len(w)
+        if n == 0:
+            return
+        table = self.candidate_edges
+        if (not isinstance(table, CandidateTable) or np.any(r0 == r1) or np.any(np.isnan(w))
+                or max(k0.max(), k1.max()) >= (1 << _KF_BITS) or min(k0.min(), k1.min()) < 0):
+            for t in range(n):
+                self.add_match(EdgeInterRobot(int(r0[t]), int(k0[t]), int(r1[t]), int(k1[t]), float(w[t])))
+            return
+        direct = r0 < r1            # spelled the way the table is keyed: the lookup of :568 can hit
+        lo = np.where(direct, (r0 << _KF_BITS) | k0, (r1 << _KF_BITS) | k1)
+        hi = np.where(direct, (r1 << _KF_BITS) | k1, (r0 << _KF_BITS) | k0)
+        order = np.lexsort((hi, lo))                      # stable: batch order inside a pair
+        slo, shi = lo[order], hi[order]
+        first = np.flatnonzero(np.r_[True, (slo[1:] != slo[:-1]) | (shi[1:] != shi[:-1])])
+        group = np.cumsum(np.r_[True, (slo[1:] != slo[:-1]) | (shi[1:] != shi[:-1])]) - 1
+        pos = np.arange(n)
+        sw, srev = w[order], ~direct[order]
+        # the last reversed spelling of a pair overwrites whatever was stored; after it only a
+        # strictly heavier direct spelling replaces the entry: the survivor is the first maximum
+        # among the positions from that overwrite on (from the start when there is none)
+        last_rev = np.maximum.reduceat(np.where(srev, pos, -1), first)
+        eligible = pos >= last_rev[group]
+        best_w = np.maximum.reduceat(np.where(eligible, sw, -np.inf), first)
+        winner = np.minimum.reduceat(np.where(eligible & (sw == best_w[group]), pos, n), first)
+        mask = (1 << _KF_BITS) - 1
+        glo, ghi = slo[first], shi[first]
+        keys = list(zip((glo >> _KF_BITS).tolist(), (glo & mask).tolist(),
+                        (ghi >> _KF_BITS).tolist(), (ghi & mask).tolist()))
+        considered = self.already_considered_matches
+        blocked = np.zeros(len(keys), dtype=bool)
+        if considered:
+            blocked = np.fromiter((key in considered for key in keys), dtype=bool, count=len(keys))
+        keep = ~blocked
+        if len(table):
+            # a stored entry survives a batch of direct spellings that are not heavier
+            stored = table.weight_of
+            for g in np.flatnonzero(keep & (last_rev < 0)).tolist():
+                sw0 = stored(keys[g])
+                if sw0 is not None and not best_w[g] > sw0:
+                    keep[g] = False
+        # every accepted match raised nb_poses (:110-119); a refused (lighter) one names the
+        # same two vertices as the stored edge, so only blacklisted pairs must be left out
+        live = ~blocked[group]
+        if np.any(live):
+            src = order[live]
+            for robots, frames in ((r0[src], k0[src]), (r1[src], k1[src])):
+                top = np.zeros(self.max_nb_robots, dtype=np.int64)
+                np.maximum.at(top, robots, frames + 1)
+                for robot in np.flatnonzero(top).tolist():
+                    self.nb_poses[robot] = max(self.nb_poses[robot], int(top[robot]))
+        chosen = np.flatnonzero(keep)
+        if len(chosen) == 0:
+            return
+        chosen = chosen[np.argsort(order[first[chosen]], kind="stable")]   # new pairs in batch order
+        src = order[winner[chosen]]
+        table.put_rows([keys[g] for g in chosen.tolist()],
+                       np.stack([r0[src], k0[src], r1[src], k1[src]], axis=1), w[src])
+
     # ------------------------------------------------------------------ initial guesses
     def greedy_initialization(self, nb_candidates_to_choose, edges):
         """The heaviest candidates (reference :205-218)."""
-        return _largest([e.weight for e in edges], nb_candidates_to_choose)
+        return _largest(_weights_of(edges), nb_candidates_to_choose)
 
     def pseudo_greedy_initialization(self, nb_candidates_to_choose, nb_random, edges):
         """Greedy except for `nb_random` picks drawn with np.random.rand (at most 2*nb_random
@@ -170,7 +277,7 @@ class AlgebraicConnectivityMaximization(object):
         w_init = self.greedy_initialization(nb_candidates_to_choose - nb_random, edges)
         draws_left, missing = 2 * nb_random, nb_random
         while missing > 0 and draws_left > 0:
-            j = int(np.random.rand() * len(edges))
+            j = int(np.random.rand() * _count(edges))
             draws_left -= 1
             if w_init[j] < 0.5:
                 w_init[j] = 1.0
@@ -228,6 +335,35 @@ class AlgebraicConnectivityMaximization(object):
                      off[e.robot1_id] + e.robot1_keyframe_id, e.weight)
                 for e in self.get_included_edges(edges, is_robot_included)]
 
+    def _candidate_columns(self, is_robot_included):
+        """`rekey_edges(self.candidate_edges.values(), ...)` as an (i, j, weight) array triple
+        straight from the candidate table's columns."""
+        ends, w = self.candidate_edges.columns()
+        robots = range(self.max_nb_robots)
+        inc = np.array([bool(is_robot_included[r]) for r in robots])
+        off = np.array([self.offsets[r] for r in robots], dtype=np.int64)
+        r0, r1 = ends[:, 0], ends[:, 2]
+        i = off[r0] + ends[:, 1]
+        j = off[r1] + ends[:, 3]
+        both = inc[r0] & inc[r1]
+        if not both.all():
+            i, j, w = i[both], j[both], w[both]
+        return i.astype(np.int32), j.astype(np.int32), np.array(w, dtype=np.float64)
+
+    def _fixed_columns(self, is_robot_included):
+        """`rekey_edges(self.fixed_edges, ...) + fill_odometry()` as an array triple."""
+        fixed = self.rekey_edges(self.fixed_edges, is_robot_included)
+        first = np.array([self.offsets[r] for r in range(len(self.nb_poses))], dtype=np.int64)
+        links = np.array([max(self.nb_poses[r] - 1, 0) for r in range(len(self.nb_poses))], dtype=np.int64)
+        # chain r = first[r], first[r]+1, ... : position inside the chain by a segmented arange
+        base = np.repeat(first - np.r_[0, np.cumsum(links)[:-1]], links)
+        tail = base + np.arange(int(links.sum()), dtype=np.int64)
+        i = np.r_[np.array([e.i for e in fixed], dtype=np.int64), tail]
+        j = np.r_[np.array([e.j for e in fixed], dtype=np.int64), tail + 1]
+        w = np.r_[np.array([e.weight for e in fixed], dtype=np.float64),
+                  np.full(len(tail), float(self.fixed_weight))]
+        return i.astype(np.int32), j.astype(np.int32), w
+
     def fill_odometry(self):
         """Consecutive poses of each robot, weight `fixed_weight` (reference :348-362)."""
         chains = []
@@ -257,7 +393,17 @@ class AlgebraicConnectivityMaximization(object):
     def check_graph_disconnections(self, is_other_robot_considered):
         """The local robot, plus every robot in range that appears in some edge (reference :391-417)."""
         seen = {self.robot_id}
-        for edge in list(self.fixed_edges) + list(self.candidate_edges.values()):
+        edges = list(self.fixed_edges)
+        if isinstance(self.candidate_edges, CandidateTable):
+            ends, _ = self.candidate_edges.columns()
+            if len(ends):
+                present = np.bincount(ends[:, 0]) > 0
+                other = np.bincount(ends[:, 2]) > 0
+                seen.update(r for r in np.flatnonzero(present).tolist() + np.flatnonzero(other).tolist()
+                            if is_other_robot_considered[r])
+        else:
+            edges += list(self.candidate_edges.values())
+        for edge in edges:
             seen.update(r for r in (edge.robot0_id, edge.robot1_id) if is_other_robot_considered[r])
         return {r: r in seen for r in range(self.max_nb_robots)}
 
@@ -296,15 +442,26 @@ class AlgebraicConnectivityMaximization(object):
         """
         included = self.check_graph_disconnections(is_other_robot_considered)
         self.compute_offsets(included)
-        fixed = self.rekey_edges(self.fixed_edges, included) + self.fill_odometry()
-        candidates = self.rekey_edges(self.candidate_edges.values(), included)
-        if not candidates:
+        if isinstance(self.candidate_edges, CandidateTable):
+            fixed = self._fixed_columns(included)
+            candidates = self._candidate_columns(included)
+        else:
+            fixed = self.rekey_edges(self.fixed_edges, included) + self.fill_odometry()
+            candidates = self.rekey_edges(self.candidate_edges.values(), included)
+        if _count(candidates) == 0:
             return []
-        budget = min(nb_candidates_to_choose, len(candidates))
+        budget = min(nb_candidates_to_choose, _count(candidates))
         self.total_nb_poses = sum(self.nb_poses.values())
 
-        start = (self.greedy_initialization if greedy_initialization
-                 else self.random_initialization)(budget, candidates)
+        if greedy_initialization:
+            start = self.greedy_initialization(budget, candidates)
+        elif _is_columns(candidates):
+            # random_initialization redraws the weights of the rekeyed edges themselves (:247-255),
+            # one np.random.rand() per edge in order = one vectorised draw from the same stream
+            candidates = candidates[:2] + (np.random.rand(_count(candidates)),)
+            start = self.greedy_initialization(budget, candidates)
+        else:
+            start = self.random_initialization(budget, candidates)
         if self.params["frontend.enable_sparsification"] and \
                 self.check_initial_fixed_measurements_exists(included):
             chosen = self.run_mac_solver(fixed, candidates, start, budget)
@@ -314,8 +471,7 @@ class AlgebraicConnectivityMaximization(object):
 
         if self.params["evaluation.enable_sparsification_comparison"]:
             self.sparsification_comparison_logs(candidates, included, start, chosen)
-        picked = [candidates[i] for i in np.flatnonzero(np.asarray(chosen).astype(int))]
-        selection = self.recover_inter_robot_edges(picked, included)
+        selection = self.recover_inter_robot_edges(_picked(candidates, chosen), included)
         self.remove_candidate_edges(selection)
         return selection
 
@@ -323,8 +479,7 @@ class AlgebraicConnectivityMaximization(object):
                                        greedy_result, mac_result):
         """Keep both selections for the evaluation topics (reference :545-557)."""
         def as_edges(mask):
-            return self.recover_inter_robot_edges(
-                [rekeyed_candidate_edges[i] for i in np.flatnonzero(np.asarray(mask).astype(int))],
-                is_robot_included)
+            return self.recover_inter_robot_edges(_picked(rekeyed_candidate_edges, mask),
+                                                  is_robot_included)
         self.log_greedy_edges = as_edges(greedy_result)
         self.log_mac_edges = as_edges(mac_result)

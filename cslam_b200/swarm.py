@@ -142,17 +142,18 @@ class SwarmLoopClosureMatching(object):
         g_sims = g_sims.cpu().numpy().reshape(R, R, B, kx)
         all_ids = all_ids.cpu().numpy()
         thr = self.params['frontend.similarity_threshold']
-        edges = []
-        for q in range(R):
-            for b in range(B):
-                for g in range(R):
-                    if g == q or g_kf[g, q, b, 0] < 0:
-                        continue
-                    s = g_sims[g, q, b, 0]
-                    if s >= thr:
-                        e = EdgeInterRobot(q, int(all_ids[q, b]), g, int(g_kf[g, q, b, 0]), float(s))
-                        self.candidate_selector.add_match(e)
-                        edges.append(e)
+        # best match of every descriptor in every OTHER robot's pool, in the order the reference
+        # meets them (query robot, keyframe, pool robot); one bulk insert into the candidate table
+        top_kf = g_kf[:, :, :, 0].transpose(1, 2, 0)                    # [query robot, b, pool]
+        top_s = g_sims[:, :, :, 0].transpose(1, 2, 0)
+        robots = np.arange(R)
+        with np.errstate(invalid="ignore"):
+            hit = (top_kf >= 0) & (top_s >= thr) & (robots[:, None, None] != robots[None, None, :])
+        qq, bb, gg = np.nonzero(hit)
+        m_kf0, m_kf1, m_s = all_ids[qq, bb], top_kf[qq, bb, gg], top_s[qq, bb, gg]
+        self.candidate_selector.add_matches(qq, m_kf0, gg, m_kf1, m_s)
+        edges = [EdgeInterRobot(*e) for e in zip(qq.tolist(), m_kf0.tolist(), gg.tolist(),
+                                                 m_kf1.tolist(), m_s.tolist())]
         intra = []
         if intra_on:
             own_idx = idx[me * B:(me + 1) * B].cpu().numpy()

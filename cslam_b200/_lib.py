@@ -67,6 +67,15 @@ SIGNATURES = {
     "cslam_pca_workspace_floats": (_i64, [_i, _i]),
     "cslam_pca_project_l2": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "cslam_gem_head_forward": (_i, [_vp, _i, _i, _i, _f, _f, _vp, _vp, _i, _vp, _vp]),
+    # (f4) Scan Context matching
+    "cslam_sc_create": (_i, [_i, _i, _i, _i, _P(_vp)]),
+    "cslam_sc_destroy": (_i, [_vp]),
+    "cslam_sc_size": (_i64, [_vp]),
+    "cslam_sc_capacity": (_i64, [_vp]),
+    "cslam_sc_add_host": (_i, [_vp, _vp, _i, _i64]),
+    "cslam_sc_read": (_i, [_vp, _i64, _i64, _vp, _vp]),
+    "cslam_sc_search_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cslam_sc_last_timing": (_i, [_vp, _P(_f), _P(_f)]),
 }
 
 _lib = None

@@ -19,6 +19,7 @@ SOURCES = [
     "heads.cu",
     "pca_tc.cu",
     "mac.cu",
+    "scancontext.cu",
 ]
 
 NVCC_FLAGS = [

@@ -19,16 +19,16 @@ class LoopClosureSparseMatching(object):
             params (dict): the reference's flat ROS 2 parameter dict
         """
         self.params = params
+        # reference :21-31: Scan Context matchers for lidar, cosine matchers otherwise
         if self.params["frontend.sensor_type"] == "lidar":
-            # reference :21-22,28-29 uses ScanContextMatching here; the lidar modality is
-            # outside the scope of this GPU front end (SURVEY.md section 2, row 12)
-            raise NotImplementedError("cslam_b200 covers the visual (global descriptor) path; "
-                                      "sensor_type 'lidar' is not supported")
-        self.local_nnsm = NearestNeighborsMatching()
+            from .lidar_pr.scancontext_matching import ScanContextMatching as matcher
+        else:
+            matcher = NearestNeighborsMatching
+        self.local_nnsm = matcher()
         self.other_robots_nnsm = {}
         for i in range(self.params['max_nb_robots']):
             if i != self.params['robot_id']:
-                self.other_robots_nnsm[i] = NearestNeighborsMatching()
+                self.other_robots_nnsm[i] = matcher()
         self.candidate_selector = AlgebraicConnectivityMaximization(
             self.params['robot_id'], self.params['max_nb_robots'], extra_params=self.params)
 

@@ -204,6 +204,44 @@ int cslam_gem_head_forward(const float* d_x, int batch, int channels, int locati
                            float eps, const float* d_fc_w, const float* d_fc_b, int dout,
                            float* d_out, void* stream);
 
+/* ---- (f4) lidar place recognition: Scan Context matching ------------------- *
+ * Replaces cslam/lidar_pr/scancontext_matching.py:6-104 (ScanContextMatching) with the
+ * helpers cslam/lidar_pr/scancontext_utils.py:78-79 (sc2rk) and :81-113 (distance_sc).
+ * Descriptors are [rings, sectors] row-major (the reference's `descriptor.reshape(shape)`),
+ * float64 arithmetic throughout.  Host pointers; the library owns the pool in HBM. */
+typedef struct cslam_sc cslam_sc_t;
+
+/* ScanContextMatching(shape=[rings, sectors], num_candidates)  (:10-22).
+ * 1 <= num_candidates <= 16. */
+int cslam_sc_create(int rings, int sectors, int num_candidates, int device, cslam_sc_t** out);
+int cslam_sc_destroy(cslam_sc_t* h);
+int64_t cslam_sc_size(cslam_sc_t* h);
+/* rows allocated: 1000, doubling (:18-19,33-37) */
+int64_t cslam_sc_capacity(cslam_sc_t* h);
+/* add_item for `count` descriptors ([count, rings*sectors], F32 or F64): stores the scan
+ * context and its ring key (row means, numpy's summation order)  (:24-46). */
+int cslam_sc_add_host(cslam_sc_t* h, const void* descriptors, int dtype, int64_t count);
+/* `.scancontexts[start:start+count]` ([count, rings, sectors]) and `.ringkeys[...]`
+ * ([count, rings]); either pointer may be NULL. */
+int cslam_sc_read(cslam_sc_t* h, int64_t start, int64_t count, double* out_scancontexts,
+                  double* out_ringkeys);
+/* search for `nq` queries  (:48-89).  Per query: the num_candidates entries with the nearest
+ * ring keys (Euclidean; equal distances in ascending row order -- scipy's KDTree leaves that
+ * order unspecified), the column-shift distance to each, and the first candidate with the
+ * smallest distance below 1.
+ *   out_row        [nq] pool row of the match, -1 when no candidate is closer than 1 (the
+ *                  reference then answers item 0 with similarity 0, :81-84)
+ *   out_similarity [nq] 1 - distance (0.0 when out_row is -1)
+ *   out_yaw_shift  [nq] nullable: the best column shift, 1..sectors (`yaw_diff`, :110)
+ *   out_candidates [nq, num_candidates] nullable: candidate rows, nearest ring key first, -1 padded
+ *   out_candidate_dist [nq, num_candidates] nullable: their column-shift distances
+ * The pool must not be empty. */
+int cslam_sc_search_host(cslam_sc_t* h, const void* queries, int dtype, int nq, int32_t* out_row,
+                         double* out_similarity, int32_t* out_yaw_shift, int32_t* out_candidates,
+                         double* out_candidate_dist);
+/* CUDA-event times (ms) of the last search: ring-key kNN kernels, distance + pick kernels. */
+int cslam_sc_last_timing(cslam_sc_t* h, float* knn_ms, float* distance_ms);
+
 #ifdef __cplusplus
 }
 #endif

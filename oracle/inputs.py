@@ -139,3 +139,40 @@ def frontend_scenario(seed=11, dim=32, n_local=48, n_remote=40, block=8):
                 events.append(('remote', r, ids, draw(len(ids))))
                 next_remote[r] += len(ids)
     return events
+
+
+# ---------------------------------------------------------------- lidar / Scan Context (f4)
+SC_CASES = {"p300": (300, 40, 11), "p4": (4, 6, 12), "p1": (1, 3, 13), "p1100": (1100, 12, 14)}
+
+
+def sc_case(tag, shape=(20, 60)):
+    """Synthetic scan contexts: non-negative heights with empty cells and empty sectors
+    (columns), as a lidar sweep with occlusions produces.  Queries: rotated (column-rolled)
+    noisy copies of pool entries, exact copies, unrelated scans, an all-zero scan.
+    Returns (pool [n, rings*sectors] float64, items, queries [q, rings*sectors] float64)."""
+    n, nq, seed = SC_CASES[tag]
+    rng = np.random.default_rng(seed)
+    R, S = shape
+
+    def scan():
+        sc = rng.random((R, S)) * 6.0
+        sc[rng.random((R, S)) < 0.3] = 0.0
+        sc[:, rng.random(S) < 0.12] = 0.0
+        return sc
+
+    pool = np.stack([scan() for _ in range(n)])
+    queries = []
+    for t in range(nq):
+        kind = t % 4
+        if kind == 0 or kind == 1:                       # a revisit under another heading
+            sc = np.roll(pool[int(rng.integers(0, n))], int(rng.integers(0, S)), axis=1).copy()
+            sc[sc > 0] += rng.normal(0, 0.3 if kind == 0 else 1.5, size=int((sc > 0).sum()))
+            sc = np.maximum(sc, 0.0)
+        elif kind == 2:
+            sc = pool[int(rng.integers(0, n))].copy()    # exact copy
+        else:
+            sc = scan()                                  # a place never seen
+        queries.append(sc)
+    queries[-1] = np.zeros((R, S))                       # nothing engaged: similarity 0, item 0
+    items = [3 * i + 5 for i in range(n)]
+    return pool.reshape(n, -1), items, np.stack(queries).reshape(nq, -1)

@@ -990,7 +990,7 @@ struct RRShared {
   int fail;
 };
 
-__device__ __forceinline__ bool rr_warp(RRShared& S, int s, int m, const double* GA /*[MAXS*MAXS]*/,
+__device__ __noinline__ bool rr_warp(RRShared& S, int s, int m, const double* GA /*[MAXS*MAXS]*/,
                                         const double* GB, double (*C)[MAXM], double* theta,
                                         int max_sweeps, double tol2, long long* rrprof = nullptr) {
   const int lane = threadIdx.x & 31;
@@ -1201,6 +1201,319 @@ __device__ __forceinline__ bool rr_warp(RRShared& S, int s, int m, const double*
   return true;
 }
 
+// ------------------------------------------------------------------ register-resident Rayleigh-Ritz
+// Building blocks of rr_warp_elem() below: the 6 x 6 matrices of the small eigen-solve never touch
+// shared memory.  For the scaling, the Cholesky factorisation and T = L^-1 A L^-T lane i (i < 6)
+// holds ROW i of every matrix in registers, rows travel between lanes by warp shuffles, all
+// register indices are compile-time constants.  A basis of fewer than 6 vectors is padded with
+// unit rows (B) and a huge diagonal (A): the pads never rotate (their off-diagonals are exactly
+// zero) and sort last.  Lanes >= 6 shadow lane 0 (same loads, same arithmetic), so every shuffle
+// is full-warp.
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// forward substitution on row-distributed M: M <- L^-1 M (l = this lane's row of L, invd its 1/L[i][i])
+__device__ __forceinline__ void rr_forward(double (&mrow)[MAXS], const double (&l)[MAXS], double invd, int li) {
+#pragma unroll
+  for (int k = 0; k < MAXS; ++k) {
+    if (li == k) {
+#pragma unroll
+      for (int c = 0; c < MAXS; ++c) mrow[c] *= invd;
+    }
+#pragma unroll
+    for (int c = 0; c < MAXS; ++c) {
+      const double yk = shfl_d(mrow[c], k);
+      if (li > k) mrow[c] = fma(-l[k], yk, mrow[c]);
+    }
+  }
+}
+
+// out[c] = M[c][li]
+__device__ __forceinline__ void rr_transpose(const double (&mrow)[MAXS], double (&out)[MAXS], int li) {
+#pragma unroll
+  for (int c = 0; c < MAXS; ++c) {
+#pragma unroll
+    for (int e = 0; e < MAXS; ++e) {
+      const double x = shfl_d(mrow[e], c);
+      if (li == e) out[c] = x;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ element-distributed Jacobi
+// The default small eigen-solve (rr_impl = 1; 0 selects rr_warp()): same method as rr_warp(), but the
+// Jacobi sweeps keep the SYMMETRIC matrix T one entry per lane (21 lanes: lane idx(i,j), i <= j) so
+// that a warp instruction updates the whole matrix at once:
+//     T'[i][j] = ai aj T[i][j] + bi aj T[i'][j] + ai bj T[i][j'] + bi bj T[i'][j']
+// (i', j' the round's opponents of i and j; a = c, b = -s / +s of the pair for its lower / upper
+// member), i.e. three shuffles and eight fp64 instructions per round, the three angles computed
+// in parallel by lanes 0-2 and broadcast.  A single warp issues an instruction every few cycles at
+// best, so what this solve costs is its instruction count per warp, not flops (a row-per-lane
+// Jacobi, three redundant angle computations and six-entry rows per lane, measured 37 k cycles for
+// three sweeps; this one 11 k, rr_warp() 26 k: profiles/r1_rr_variants.txt).  The shuffle sources
+// of every (round, lane) come from two small tables (circle-method tournament: player 5 fixed,
+// pairs (r,5), ((r+1)%5,(r+4)%5), ((r+2)%5,(r+3)%5) in round r; word A: sources of the three partner
+// entries, pair ids and signs of i and j, lanes of T[i][i] and T[j][j]; word B, lanes 0-2: lanes of
+// T[p][p], T[q][q], T[p][q] of the pair whose angle the lane computes).  V stays row-per-lane
+// (lanes 0-5), its column rotations are register-local.
+__device__ const uint32_t g_rr_tab_a[5][32] = {
+    {0x001850a5u, 0x181a4c8au, 0x2c1c446eu, 0x3c0c3851u, 0x480a2833u, 0x50081414u, 0x18dac929u, 0x2cdcc10du, 0x3cccb4f0u, 0x48caa4d2u, 0x50c89033u, 0x2d7d3d8cu, 0x3d6d316fu, 0x496b20f0u, 0x51690c51u, 0x3de52d8cu, 0x49e31d0du, 0x51e1086eu, 0x4a429929u, 0x5240848au, 0x528000a5u, 0x001850a5u, 0x001850a5u, 0x001850a5u, 0x001850a5u, 0x001850a5u, 0x001850a5u, 0x001850a5u, 0x001850a5u, 0x001850a5u, 0x001850a5u, 0x001850a5u},
+    {0x001aac42u, 0x1818b8a7u, 0x2c0a880bu, 0x3c1cb48cu, 0x480cb06du, 0x50089c2eu, 0x18d8514au, 0x2cca142eu, 0x3cdc4d31u, 0x48cc4513u, 0x50c828d4u, 0x2d628042u, 0x3d7491a3u, 0x49648d84u, 0x516084e5u, 0x3dfd4a10u, 0x49ed41f2u, 0x51e92513u, 0x4a453e10u, 0x52412131u, 0x5280194au, 0x001aac42u, 0x001aac42u, 0x001aac42u, 0x001aac42u, 0x001aac42u, 0x001aac42u, 0x001aac42u, 0x001aac42u, 0x001aac42u, 0x001aac42u, 0x001aac42u},
+    {0x001d4884u, 0x181b4069u, 0x2c194cadu, 0x3c0b2430u, 0x480d1012u, 0x50093453u, 0x18dabd08u, 0x2cd8c54cu, 0x3ccaa0cfu, 0x48cc8c30u, 0x50c8b0f1u, 0x2d7851ceu, 0x3d6a28f1u, 0x496c1453u, 0x51683974u, 0x3de29908u, 0x49e48469u, 0x51e09d8au, 0x4a450084u, 0x524109a5u, 0x52802dceu, 0x001d4884u, 0x001d4884u, 0x001d4884u, 0x001d4884u, 0x001d4884u, 0x001d4884u, 0x001d4884u, 0x001d4884u, 0x001d4884u, 0x001d4884u, 0x001d4884u},
+    {0x001d1821u, 0x180d0406u, 0x2c1b2487u, 0x3c1928a8u, 0x480b1c49u, 0x5009206au, 0x18c50021u, 0x2cd31122u, 0x3cd11543u, 0x48c308e4u, 0x50c10d05u, 0x2d7ac9adu, 0x3d78cdd0u, 0x496ab572u, 0x5168c193u, 0x3df85231u, 0x49ea3993u, 0x51e845f4u, 0x4a42adadu, 0x5240b20eu, 0x52803e31u, 0x001d1821u, 0x001d1821u, 0x001d1821u, 0x001d1821u, 0x001d1821u, 0x001d1821u, 0x001d1821u, 0x001d1821u, 0x001d1821u, 0x001d1821u, 0x001d1821u},
+    {0x001abc63u, 0x181cb048u, 0x2c0ca02cu, 0x3c0a8c0fu, 0x4818c4b0u, 0x5008c091u, 0x18dd2ce7u, 0x2ccd1ccbu, 0x3ccb082cu, 0x48d9394du, 0x50c9352eu, 0x2d6518e7u, 0x3d630448u, 0x497129c9u, 0x516125aau, 0x3de28063u, 0x49f09624u, 0x51e09205u, 0x4a585273u, 0x52484e54u, 0x52804a73u, 0x001abc63u, 0x001abc63u, 0x001abc63u, 0x001abc63u, 0x001abc63u, 0x001abc63u, 0x001abc63u, 0x001abc63u, 0x001abc63u, 0x001abc63u, 0x001abc63u}};
+__device__ const uint32_t g_rr_tab_b[5][32] = {
+    {0x00001680u, 0x00002646u, 0x000031ebu, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u},
+    {0x00002a86u, 0x00000960u, 0x0000424fu, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u},
+    {0x00003a8bu, 0x000021e6u, 0x00001240u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u},
+    {0x0000468fu, 0x0000364bu, 0x000004c0u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u},
+    {0x00004e92u, 0x00000de0u, 0x00001d66u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u}};
+
+__device__ __forceinline__ void jacobi_angle_fast(double app, double aqq, double apq, double& c, double& sn) {
+  c = 1.0;
+  sn = 0.0;
+  if (apq * apq > 1e-40 * fabs(app * aqq) && fabs(apq) > 1e-150) {
+    const double h = aqq - app, bb = 2.0 * apq;
+    // power-of-two scaling into float range without frexp/ldexp (~100 cycles): 2^(1023 - exponent)
+    const int ebits = (__double2hiint(fmax(fabs(h), fabs(bb))) >> 20) & 0x7ff;
+    const double scale = __hiloint2double((2046 - min(ebits, 2045)) << 20, 0);
+    const float hf = static_cast<float>(h * scale), bf = static_cast<float>(bb * scale);
+    const float r2 = fmaf(hf, hf, bf * bf);
+    const float inv_r = rsqrtf(r2);
+    const float rr = r2 * inv_r;
+    const float u = fabsf(hf) + rr;
+    const float cf = sqrtf(0.5f * u * inv_r);
+    const float sf = ((hf >= 0.f) == (bf >= 0.f) ? 1.f : -1.f) * fabsf(bf) * rsqrtf(2.f * rr * u);
+    double cd = cf, sd = sf;
+    double nrm = fma(cd, cd, sd * sd);
+    double fix = fma(-0.5, nrm, 1.5);
+    cd *= fix;
+    sd *= fix;
+    nrm = fma(cd, cd, sd * sd);
+    fix = fma(-0.5, nrm, 1.5);
+    c = cd * fix;
+    sn = sd * fix;
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void jacobi_round_elem(double& tel, double (&v)[MAXS], uint32_t wa, uint32_t wb) {
+  // pairs of round R: (R, 5), then the two rotating pairs
+  constexpr int A1 = (R + 1) % 5, B1 = (R + 4) % 5, A2 = (R + 2) % 5, B2 = (R + 3) % 5;
+  constexpr int P0 = R, Q0 = 5;
+  constexpr int P1 = A1 < B1 ? A1 : B1, Q1 = A1 < B1 ? B1 : A1;
+  constexpr int P2 = A2 < B2 ? A2 : B2, Q2 = A2 < B2 ? B2 : A2;
+  double c, sn;
+  {
+    const double app = shfl_d(tel, wb & 31), aqq = shfl_d(tel, (wb >> 5) & 31), apq = shfl_d(tel, (wb >> 10) & 31);
+    jacobi_angle_fast(app, aqq, apq, c, sn);     // lanes 0-2: pairs 0-2 (other lanes: unused)
+  }
+  const double c0 = shfl_d(c, 0), s0 = shfl_d(sn, 0);
+  const double c1 = shfl_d(c, 1), s1 = shfl_d(sn, 1);
+  const double c2 = shfl_d(c, 2), s2 = shfl_d(sn, 2);
+  // T: one entry per lane
+  const double t1 = shfl_d(tel, wa & 31), t2 = shfl_d(tel, (wa >> 5) & 31), t3 = shfl_d(tel, (wa >> 10) & 31);
+  const int ti = (wa >> 15) & 3, tj = (wa >> 17) & 3;
+  const double ai = ti == 0 ? c0 : ti == 1 ? c1 : c2;
+  const double si = ti == 0 ? s0 : ti == 1 ? s1 : s2;
+  const double aj = tj == 0 ? c0 : tj == 1 ? c1 : c2;
+  const double sj = tj == 0 ? s0 : tj == 1 ? s1 : s2;
+  const double bi = ((wa >> 19) & 1) ? -si : si;
+  const double bj = ((wa >> 20) & 1) ? -sj : sj;
+  tel = fma(ai * aj, tel, fma(bi * aj, t1, fma(ai * bj, t2, (bi * bj) * t3)));
+  // V: rows in lanes 0-5, columns rotate in registers
+#define CSLAM_ROT_COLS(M, P, Q, C, S)                  \
+  {                                                    \
+    const double kp = M[P], kq = M[Q];                 \
+    M[P] = C * kp - S * kq;                            \
+    M[Q] = S * kp + C * kq;                            \
+  }
+  CSLAM_ROT_COLS(v, P0, Q0, c0, s0)
+  CSLAM_ROT_COLS(v, P1, Q1, c1, s1)
+  CSLAM_ROT_COLS(v, P2, Q2, c2, s2)
+#undef CSLAM_ROT_COLS
+}
+
+// tab: [2][5][32] words A then B (shared or global memory)
+__device__ __noinline__ bool rr_warp_elem(int s, int m, const double* GA, const double* GB,
+                                             double (*C)[MAXM], double* theta, int max_sweeps, double tol2,
+                                             const uint32_t* tab, long long* rrprof = nullptr) {
+  static_assert(MAXS == 6 && MAXM == 2, "rr_warp_elem is written for a basis of at most 6 vectors");
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int li = lane < MAXS ? lane : 0;
+  long long tq = clock64();
+  auto sect = [&](int k) {
+    if (rrprof && lane == 0) {
+      const long long t = clock64();
+      rrprof[k] += t - tq;
+      tq = t;
+    }
+  };
+  constexpr double kPad = 1e150;
+  const double dmine = li < s ? GB[li * MAXS + li] : 1.0;
+  if (__any_sync(full, !(dmine > 0.0) || !isfinite(dmine))) return false;
+  const double dsi = rsqrt(dmine);
+  double a[MAXS], b[MAXS];
+#pragma unroll
+  for (int e = 0; e < MAXS; ++e) {
+    const double dse = shfl_d(dsi, e);
+    const bool in = li < s && e < s;
+    const double sc = dsi * dse;
+    a[e] = in ? 0.5 * (GA[li * MAXS + e] + GA[e * MAXS + li]) * sc : (e == li ? kPad : 0.0);
+    b[e] = in ? 0.5 * (GB[li * MAXS + e] + GB[e * MAXS + li]) * sc : (e == li ? 1.0 : 0.0);
+  }
+  sect(0);
+  double l[MAXS], lt[MAXS], invd = 1.0;
+#pragma unroll
+  for (int e = 0; e < MAXS; ++e) { l[e] = 0.0; lt[e] = 0.0; }
+#pragma unroll
+  for (int j = 0; j < MAXS; ++j) {
+    const double d = shfl_d(b[j], j);
+    if (!(d > 1e-14)) return false;
+    const double inv = rsqrt(d);
+    if (li == j) {
+      l[j] = d * inv;
+      invd = inv;
+    } else if (li > j) {
+      l[j] = b[j] * inv;
+    }
+#pragma unroll
+    for (int k = j + 1; k < MAXS; ++k) {
+      const double lk = shfl_d(l[j], k);
+      if (li == j) lt[k] = lk;
+      if (li >= k) b[k] = fma(-l[j], lk, b[k]);
+    }
+  }
+  sect(1);
+  double t[MAXS];
+  rr_forward(a, l, invd, li);
+  rr_transpose(a, t, li);
+  rr_forward(t, l, invd, li);
+  // entry (i, j), i <= j, of the symmetrised T for lane idx(i, j): 0.5 (T[i][j] + T[j][i])
+  int ei = 0, ej = 0;
+  {
+    int run = 0;
+#pragma unroll
+    for (int i = 0; i < MAXS; ++i) {
+      if (lane >= run && lane < run + (MAXS - i)) { ei = i; ej = i + (lane - run); }
+      run += MAXS - i;
+    }
+  }
+  double tel = 0.0;
+#pragma unroll
+  for (int e = 0; e < MAXS; ++e) {
+    const double x = shfl_d(t[e], ei);   // T[ei][e]
+    const double y = shfl_d(t[e], ej);   // T[ej][e]
+    if (e == ej) tel += 0.5 * x;
+    if (e == ei) tel += 0.5 * y;
+  }
+  double v[MAXS];
+#pragma unroll
+  for (int e = 0; e < MAXS; ++e) v[e] = e == li ? 1.0 : 0.0;
+  uint32_t wa[5], wb[5];
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    wa[r] = tab[r * 32 + lane];
+    wb[r] = tab[(5 + r) * 32 + lane];
+  }
+  sect(2);
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    const double dii = shfl_d(tel, (wa[0] >> 21) & 31), djj = shfl_d(tel, (wa[0] >> 26) & 31);
+    const bool big = lane < NPAIR && ei != ej && tel * tel > tol2 * fabs(dii * djj) && fabs(tel) > 1e-150;
+    if (!__any_sync(full, big)) break;
+    jacobi_round_elem<0>(tel, v, wa[0], wb[0]);
+    jacobi_round_elem<1>(tel, v, wa[1], wb[1]);
+    jacobi_round_elem<2>(tel, v, wa[2], wb[2]);
+    jacobi_round_elem<3>(tel, v, wa[3], wb[3]);
+    jacobi_round_elem<4>(tel, v, wa[4], wb[4]);
+  }
+  sect(3);
+  double diag[MAXS];
+  diag[0] = shfl_d(tel, 0);
+  diag[1] = shfl_d(tel, 6);
+  diag[2] = shfl_d(tel, 11);
+  diag[3] = shfl_d(tel, 15);
+  diag[4] = shfl_d(tel, 18);
+  diag[5] = shfl_d(tel, 20);
+  double z[MAXM], th[MAXM];
+#pragma unroll
+  for (int c = 0; c < MAXM; ++c) { z[c] = 0.0; th[c] = 0.0; }
+#pragma unroll
+  for (int e = 0; e < MAXS; ++e) {
+    int rank = 0;
+#pragma unroll
+    for (int f = 0; f < MAXS; ++f)
+      if (f != e) rank += (diag[f] < diag[e] || (diag[f] == diag[e] && f < e)) ? 1 : 0;
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c)
+      if (rank == c) { z[c] = v[e]; th[c] = diag[e]; }
+  }
+#pragma unroll
+  for (int k = MAXS - 1; k >= 0; --k) {
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) {
+      if (li == k) z[c] *= invd;
+      const double zk = shfl_d(z[c], k);
+      if (li < k) z[c] = fma(-lt[k], zk, z[c]);
+    }
+  }
+  if (lane < MAXS) {
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c)
+      if (c < m) C[lane][c] = lane < s ? z[c] * dsi : 0.0;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c)
+      if (c < m) theta[c] = th[c];
+  }
+  __syncwarp();
+  sect(4);
+  return true;
+}
+
+// Test hook: one warp solves one small problem with one of the implementations, `reps` times,
+// and reports the cycles per solve (total and per section).
+__global__ void k_rr_debug(const double* GA, const double* GB, int s, int m, int impl, int sweeps,
+                           double tol2, int reps, double* C_out /*[MAXS][MAXM]*/, double* theta_out,
+                           int* ok_out, long long* cycles_out /*[6]*/) {
+  __shared__ RRShared S;
+  __shared__ double sGA[MAXS * MAXS], sGB[MAXS * MAXS];
+  __shared__ double sC[MAXS][MAXM];
+  __shared__ double sth[MAXM];
+  __shared__ uint32_t stab[2 * 5 * 32];
+  __shared__ long long sprof[8];
+  for (int e = threadIdx.x; e < MAXS * MAXS; e += 32) {
+    sGA[e] = GA[e];
+    sGB[e] = GB[e];
+  }
+  for (int e = threadIdx.x; e < 5 * 32; e += 32) {
+    stab[e] = g_rr_tab_a[e / 32][e % 32];
+    stab[5 * 32 + e] = g_rr_tab_b[e / 32][e % 32];
+  }
+  for (int e = threadIdx.x; e < MAXS * MAXM; e += 32) sC[e / MAXM][e % MAXM] = 0.0;
+  if (threadIdx.x < MAXM) sth[threadIdx.x] = 0.0;
+  if (threadIdx.x < 8) sprof[threadIdx.x] = 0;
+  __syncwarp();
+  bool ok = true;
+  const long long t0 = clock64();
+  for (int rep = 0; rep < reps; ++rep) {
+    ok = impl ? rr_warp_elem(s, m, sGA, sGB, sC, sth, sweeps, tol2, stab, sprof)
+              : rr_warp(S, s, m, sGA, sGB, sC, sth, sweeps, tol2, sprof);
+    __syncwarp();
+  }
+  const long long t1 = clock64();
+  for (int e = threadIdx.x; e < MAXS * MAXM; e += 32) C_out[e] = sC[e / MAXM][e % MAXM];
+  if (threadIdx.x < MAXM) theta_out[threadIdx.x] = sth[threadIdx.x];
+  if (threadIdx.x == 0) {
+    *ok_out = ok ? 1 : 0;
+    if (cycles_out) {
+      cycles_out[0] = (t1 - t0) / (reps > 0 ? reps : 1);
+      for (int k = 0; k < 5; ++k) cycles_out[1 + k] = sprof[k] / (reps > 0 ? reps : 1);
+    }
+  }
+}
+
 // Grid-wide barrier for a co-resident (cooperatively launched) grid: one arrival per CTA on a
 // monotonically increasing counter, release/acquire at GPU scope.  `epoch` is the CTA-uniform
 // number of barriers passed so far.  (cooperative_groups' grid.sync() measured ~11 us per call
@@ -1258,6 +1571,7 @@ struct PersistArgs {
   int init;              // 1: X in global memory is a raw start block: centre it, form AX = L X and
                          //    Rayleigh-Ritz it inside the kernel before the first iteration
   double* out;           // [0..MAXM) theta, [MAXM] iterations, [MAXM+1] status, [MAXM+2] res
+  int rr_impl;           // small eigen-solve: 1 register-resident rr_warp_elem (default), 0 shared-memory rr_warp
   int rr_sweeps;         // Jacobi sweep cap of the Rayleigh-Ritz solve
   double rr_tol2;        // squared relative off-diagonal level at which the Jacobi sweeps stop
   int cap0, cap1;        // shared-memory capacity (entries) for the CTA's slice of each adjacency
@@ -1283,6 +1597,11 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   __shared__ RRShared s_rr;
   __shared__ double s_GA[MAXS * MAXS], s_GB[MAXS * MAXS];
   __shared__ double s_th2[MAXM];
+  __shared__ uint32_t s_rrtab[2 * 5 * 32];
+  for (int e = threadIdx.x; e < 5 * 32; e += T) {
+    s_rrtab[e] = g_rr_tab_a[e / 32][e % 32];
+    s_rrtab[5 * 32 + e] = g_rr_tab_b[e / 32][e % 32];
+  }
   unsigned int epoch = 0;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1776,7 +2095,12 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     __syncthreads();
     if (warp == 0) {
       int use = sdim;
-      bool ok = rr_warp(s_rr, sdim, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps, a.rr_tol2, (a.prof && b == 0) ? rrprof_acc : nullptr);
+      long long* rrp = (a.prof && b == 0) ? rrprof_acc : nullptr;
+      auto solve = [&](int dim, long long* prof_to) {
+        return a.rr_impl ? rr_warp_elem(dim, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps, a.rr_tol2, s_rrtab, prof_to)
+                         : rr_warp(s_rr, dim, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps, a.rr_tol2, prof_to);
+      };
+      bool ok = solve(sdim, rrp);
       if (!ok && have_p) {  // drop P (restart) and solve in span[X W]
         use = 2 * m;
         for (int e = lane; e < MAXS * MAXS; e += 32) {
@@ -1784,7 +2108,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
           if (i >= use || j >= use) { s_GA[e] = 0.0; s_GB[e] = 0.0; }
         }
         __syncwarp();
-        ok = rr_warp(s_rr, use, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps, a.rr_tol2);
+        ok = solve(use, nullptr);
       }
       if (lane == 0) s_ok = ok ? 1 : 0;
       if (lane < MAXM) s_theta[lane] = lane < m ? s_th2[lane] : 0.0;
@@ -2014,6 +2338,7 @@ struct FiedlerSolver {
       default: set_error("fiedler: bad persistent variant %d", ch); return CSLAM_ERR_INVALID;
     }
     pa.cap0 = pa.cap1 = 6144;
+    pa.rr_impl = getenv("CSLAM_RR_IMPL") ? atoi(getenv("CSLAM_RR_IMPL")) : 1;
     pa.rr_sweeps = getenv("CSLAM_RR_SWEEPS") ? atoi(getenv("CSLAM_RR_SWEEPS")) : 3;
     pa.rr_tol2 = getenv("CSLAM_RR_TOL2") ? atof(getenv("CSLAM_RR_TOL2")) : 1e-32;
     const size_t dyn = static_cast<size_t>(pa.cap0 + pa.cap1) * (sizeof(double) + sizeof(int)) +
@@ -2897,6 +3222,43 @@ int cslam_mac_stats(cslam_mac_t* h, int64_t* lobpcg_iters, int64_t* spmv_columns
   if (lobpcg_iters) *lobpcg_iters = h->total_lobpcg_iters;
   if (spmv_columns) *spmv_columns = h->fs.spmv_count;
   if (jacobi_fallback) *jacobi_fallback = h->fs.jacobi ? 1 : 0;
+  return CSLAM_OK;
+}
+
+int cslam_debug_rayleigh_ritz(const double* ga, const double* gb, int s, int m, int impl, int sweeps,
+                              int reps, int device, double* c_out, double* theta_out, int* ok_out,
+                              int64_t* cycles_out) {
+  CSLAM_REQUIRE(ga && gb && c_out && theta_out && ok_out, "debug_rayleigh_ritz: NULL argument");
+  CSLAM_REQUIRE(s >= 1 && s <= MAXS && m >= 1 && m <= MAXM && m <= s && reps >= 1 && impl >= 0 && impl <= 1,
+                "debug_rayleigh_ritz: bad sizes");
+  if (cslam_device_count() <= 0) {
+    set_error("debug_rayleigh_ritz: no CUDA device");
+    return CSLAM_ERR_CUDA;
+  }
+  DeviceGuard g(device);
+  double* d = nullptr;
+  int* dok = nullptr;
+  long long* dcyc = nullptr;
+  const size_t nm = MAXS * MAXS;
+  CSLAM_TRY(dev_alloc(&d, 2 * nm + MAXS * MAXM + MAXM));
+  CSLAM_TRY(dev_alloc(&dok, 1));
+  CSLAM_TRY(dev_alloc(&dcyc, 6));
+  CSLAM_CUDA(cudaMemcpy(d, ga, nm * sizeof(double), cudaMemcpyHostToDevice));
+  CSLAM_CUDA(cudaMemcpy(d + nm, gb, nm * sizeof(double), cudaMemcpyHostToDevice));
+  k_rr_debug<<<1, 32>>>(d, d + nm, s, m, impl, sweeps, 1e-32, reps, d + 2 * nm, d + 2 * nm + MAXS * MAXM, dok, dcyc);
+  CSLAM_LAUNCH_CHECK();
+  CSLAM_CUDA(cudaDeviceSynchronize());
+  CSLAM_CUDA(cudaMemcpy(c_out, d + 2 * nm, MAXS * MAXM * sizeof(double), cudaMemcpyDeviceToHost));
+  CSLAM_CUDA(cudaMemcpy(theta_out, d + 2 * nm + MAXS * MAXM, MAXM * sizeof(double), cudaMemcpyDeviceToHost));
+  CSLAM_CUDA(cudaMemcpy(ok_out, dok, sizeof(int), cudaMemcpyDeviceToHost));
+  if (cycles_out) {
+    long long h[6];
+    CSLAM_CUDA(cudaMemcpy(h, dcyc, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 6; ++k) cycles_out[k] = h[k];
+  }
+  dev_free(d);
+  dev_free(dok);
+  dev_free(dcyc);
   return CSLAM_OK;
 }
 

@@ -20,9 +20,10 @@
 //                               HBM-bound scan: rings*8 B per entry and query batch)
 // Kernels:
 //   k_sc_prepare   transpose + column norms + ring key (numpy's pairwise summation order)
-//   k_sc_knn       per (query, chunk of the pool): every thread keeps a sorted list of its
-//                  `num_candidates` nearest entries in registers, lists merged per CTA
-//   k_sc_knn_merge per query: merge of the per-chunk lists
+//   k_sc_knn       per (range of the pool, tile of up to 8 queries): ring keys staged through
+//                  shared memory once per tile, one warp per query keeps its nearest entries in
+//                  a lane-distributed sorted list (vote + shift insertion)
+//   k_sc_knn_merge per query: merge of the per-range lists
 //   k_sc_distance  per (query, candidate): the sectors x sectors cosine table in shared memory,
 //                  one ordered sum per shift, first maximum
 //   k_sc_pick      per query: first candidate with the smallest distance below 1 (:70-79)
@@ -36,7 +37,7 @@ namespace cslam {
 namespace {
 
 constexpr int kMaxCand = 16;       // candidates per query kept in registers
-constexpr int kKnnThreads = 128;
+constexpr int kKnnThreads = 256;
 constexpr int kDistThreads = 256;
 
 // numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, pairwise_sum_DOUBLE),
@@ -96,122 +97,132 @@ __device__ __forceinline__ bool closer(double d, int i, double d2, int i2) {
   return d < d2 || (d == d2 && i < i2);
 }
 
-// Insert (d, i) into the ascending list (td, ti).
-__device__ __forceinline__ void list_insert(double (&td)[kMaxCand], int (&ti)[kMaxCand], double d, int i) {
-#pragma unroll
-  for (int p = 0; p < kMaxCand; ++p) {
-    if (closer(d, i, td[p], ti[p])) {
-      const double xd = td[p];
-      const int xi = ti[p];
-      td[p] = d;
-      ti[p] = i;
-      d = xd;
-      i = xi;
+// Sorted list of the warp's nearest entries, one per lane: lane p < kMaxCand holds the p-th
+// nearest (ld, li); the other lanes hold +inf.  A candidate that beats the current
+// `ncand`-th entry is inserted by a vote (its position = number of entries that stay ahead
+// of it) and a one-lane shift: ~10 warp instructions, and it happens ~ncand*ln(rows/ncand)
+// times per scan, so the scan itself is what the kernel spends its time on.
+struct WarpList {
+  double ld;
+  int li;
+  double thr;     // current ncand-th entry
+  int thr_i;
+  __device__ __forceinline__ void init() {
+    ld = INFINITY;
+    li = 0x7fffffff;
+    thr = INFINITY;
+    thr_i = 0x7fffffff;
+  }
+  // every lane offers one (d, i); i == 0x7fffffff marks "nothing"
+  __device__ __forceinline__ void offer(double d, int i, int ncand, int lane) {
+    unsigned mask = __ballot_sync(0xffffffffu, closer(d, i, thr, thr_i));
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const double bd = __shfl_sync(0xffffffffu, d, src);
+      const int bi = __shfl_sync(0xffffffffu, i, src);
+      if (!closer(bd, bi, thr, thr_i)) continue;     // the threshold moved meanwhile
+      const int pos = __popc(__ballot_sync(0xffffffffu, closer(ld, li, bd, bi)));
+      const double ud = __shfl_up_sync(0xffffffffu, ld, 1);
+      const int ui = __shfl_up_sync(0xffffffffu, li, 1);
+      if (lane < kMaxCand) {
+        if (lane > pos) { ld = ud; li = ui; }
+        if (lane == pos) { ld = bd; li = bi; }
+      }
+      thr = __shfl_sync(0xffffffffu, ld, ncand - 1);
+      thr_i = __shfl_sync(0xffffffffu, li, ncand - 1);
     }
   }
-}
+};
 
-// The `ncand` smallest entries over the sorted per-thread lists of a CTA, in order, written by
-// thread 0 to out_d/out_i.  Every round takes the smallest list head (a CTA-wide arg-min).
-__device__ void block_take_smallest(double (&td)[kMaxCand], int (&ti)[kMaxCand], int ncand,
-                                    double* out_d, int* out_i) {
-  __shared__ double s_d[kKnnThreads / 32];
-  __shared__ int s_i[kKnnThreads / 32];
-  __shared__ int s_t[kKnnThreads / 32];
-  __shared__ int s_win;
+constexpr int kKnnWarps = kKnnThreads / 32;   // 8
+constexpr int kKnnRows = 256;                 // pool entries staged per step
+
+// Step 1.  grid (row ranges, query tiles of up to 8).  The CTA streams its range of the ring-key
+// table through shared memory 256 entries at a time ([rings][256] doubles, loaded once and used
+// by every query of the tile); warp w scans the staged entries for query (w % qslots), row part
+// (w / qslots) -- 8 queries x 1 part, 4 x 2, 2 x 4 or 1 x 8 -- and keeps its nearest entries in a
+// WarpList.  part_*: [queries][parts][ncand], parts = ranges * row parts.
+// Algorithmic traffic: rings*8 B per pool entry per query TILE (not per query).
+__global__ void __launch_bounds__(kKnnThreads)
+k_sc_knn(const double* __restrict__ rk, int64_t rk_stride, int64_t n, int rings,
+         const double* __restrict__ qrk, int nq, int ncand, int64_t rows_per_range, int qslots,
+         double* part_d, int* part_i) {
+  extern __shared__ double s_rk[];            // [rings][kKnnRows]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int head = 0;
-  for (int round = 0; round < ncand; ++round) {
-    double d = INFINITY;
-    int i = 0x7fffffff;
-#pragma unroll
-    for (int p = 0; p < kMaxCand; ++p)
-      if (p == head) { d = td[p]; i = ti[p]; }
-    if (i < 0) { d = INFINITY; i = 0x7fffffff; }      // empty slot
-    int t = threadIdx.x;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double d2 = __shfl_xor_sync(0xffffffffu, d, o);
-      const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
-      const int t2 = __shfl_xor_sync(0xffffffffu, t, o);
-      if (closer(d2, i2, d, i) || (d2 == d && i2 == i && t2 < t)) { d = d2; i = i2; t = t2; }
-    }
-    if (lane == 0) { s_d[warp] = d; s_i[warp] = i; s_t[warp] = t; }
+  const int rparts = kKnnWarps / qslots;
+  const int slot = warp % qslots, rpart = warp / qslots;
+  const int q = blockIdx.y * qslots + slot;
+  const bool active = q < nq;
+  // this warp's query ring key: lane r holds ring r (rings <= 32), else read from global
+  double qk_lane = 0.0;
+  if (active && lane < rings && rings <= 32) qk_lane = qrk[static_cast<int64_t>(lane) * nq + q];
+  WarpList wl;
+  wl.init();
+  const int64_t lo = blockIdx.x * rows_per_range;
+  const int64_t hi = min(n, lo + rows_per_range);
+  for (int64_t base = lo; base < hi; base += kKnnRows) {
+    const int cnt = static_cast<int>(min(static_cast<int64_t>(kKnnRows), hi - base));
     __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < kKnnThreads / 32; ++w)
-        if (closer(s_d[w], s_i[w], d, i) || (s_d[w] == d && s_i[w] == i && s_t[w] < t)) {
-          d = s_d[w]; i = s_i[w]; t = s_t[w];
+    for (int e = threadIdx.x; e < rings * kKnnRows; e += kKnnThreads) {
+      const int r = e / kKnnRows, c = e % kKnnRows;
+      s_rk[e] = c < cnt ? rk[r * rk_stride + base + c] : 0.0;
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int c = rpart * 32 + lane; c - lane < cnt; c += 32 * rparts) {   // warp-uniform trip count
+      double d = 0.0;
+      if (rings <= 32) {
+        for (int r = 0; r < rings; ++r) {
+          const double t = s_rk[r * kKnnRows + c] - __shfl_sync(0xffffffffu, qk_lane, r);
+          d = __dadd_rn(d, __dmul_rn(t, t));     // the reference's order of additions, no fma
         }
-      const bool none = i == 0x7fffffff;
-      out_d[round] = none ? INFINITY : d;
-      out_i[round] = none ? -1 : i;
-      s_win = none ? -1 : t;
+      } else {
+        for (int r = 0; r < rings; ++r) {
+          const double t = s_rk[r * kKnnRows + c] - qrk[static_cast<int64_t>(r) * nq + q];
+          d = __dadd_rn(d, __dmul_rn(t, t));
+        }
+      }
+      const bool valid = c < cnt;
+      wl.offer(valid ? d : INFINITY, valid ? static_cast<int>(base + c) : 0x7fffffff, ncand, lane);
     }
-    __syncthreads();
-    if (s_win == static_cast<int>(threadIdx.x)) ++head;
+  }
+  if (active && lane < ncand) {
+    const int64_t parts = static_cast<int64_t>(gridDim.x) * rparts;
+    const int64_t slot_out = (static_cast<int64_t>(q) * parts + blockIdx.x * rparts + rpart) * ncand + lane;
+    part_d[slot_out] = wl.li == 0x7fffffff ? INFINITY : wl.ld;
+    part_i[slot_out] = wl.li == 0x7fffffff ? -1 : wl.li;
   }
 }
 
-// grid (chunks, queries).  part_*: [queries][chunks][ncand]
-template <int RINGS>
+// grid (queries).  Merge `parts` sorted lists of `ncand` into cand_*: [queries][ncand].
 __global__ void __launch_bounds__(kKnnThreads)
-k_sc_knn(const double* __restrict__ rk, int64_t rk_stride, int64_t n, int rings_rt,
-         const double* __restrict__ qrk, int ncand, int64_t rows_per_chunk, double* part_d,
-         int* part_i) {
-  const int rings = RINGS > 0 ? RINGS : rings_rt;
-  const int q = blockIdx.y;
-  double qk[RINGS > 0 ? RINGS : 1];
-  if (RINGS > 0) {
-#pragma unroll
-    for (int r = 0; r < RINGS; ++r) qk[r] = qrk[r * gridDim.y + q];   // ring-major [rings][queries]
-  }
-  double td[kMaxCand];
-  int ti[kMaxCand];
-#pragma unroll
-  for (int p = 0; p < kMaxCand; ++p) { td[p] = INFINITY; ti[p] = -1; }
-  const int64_t lo = blockIdx.x * rows_per_chunk;
-  const int64_t hi = min(n, lo + rows_per_chunk);
-  for (int64_t row = lo + threadIdx.x; row < hi; row += kKnnThreads) {
-    double d = 0.0;
-    if (RINGS > 0) {
-#pragma unroll
-      for (int r = 0; r < RINGS; ++r) {
-        const double t = rk[r * rk_stride + row] - qk[r];
-        d = __dadd_rn(d, __dmul_rn(t, t));
-      }
-    } else {
-      for (int r = 0; r < rings; ++r) {
-        const double t = rk[r * rk_stride + row] - qrk[r * gridDim.y + q];
-        d = __dadd_rn(d, __dmul_rn(t, t));
-      }
-    }
-    // only entries that beat the current worst kept one reach the insertion
-    bool take = false;
-#pragma unroll
-    for (int p = 0; p < kMaxCand; ++p)
-      if (p == ncand - 1) take = closer(d, static_cast<int>(row), td[p], ti[p] < 0 ? 0x7fffffff : ti[p]);
-    if (take) list_insert(td, ti, d, static_cast<int>(row));
-  }
-  const int64_t slot = (static_cast<int64_t>(q) * gridDim.x + blockIdx.x) * ncand;
-  block_take_smallest(td, ti, ncand, part_d + slot, part_i + slot);
-}
-
-// grid (queries).  Merge `chunks` sorted lists of `ncand` into cand_*: [queries][ncand].
-__global__ void __launch_bounds__(kKnnThreads)
-k_sc_knn_merge(const double* __restrict__ part_d, const int* __restrict__ part_i, int chunks,
+k_sc_knn_merge(const double* __restrict__ part_d, const int* __restrict__ part_i, int parts,
                int ncand, double* cand_d, int* cand_i) {
+  __shared__ double s_d[kKnnWarps][kMaxCand];
+  __shared__ int s_i[kKnnWarps][kMaxCand];
   const int q = blockIdx.x;
-  double td[kMaxCand];
-  int ti[kMaxCand];
-#pragma unroll
-  for (int p = 0; p < kMaxCand; ++p) { td[p] = INFINITY; ti[p] = -1; }
-  const int64_t base = static_cast<int64_t>(q) * chunks * ncand;
-  for (int e = threadIdx.x; e < chunks * ncand; e += kKnnThreads) {
-    const int i = part_i[base + e];
-    if (i >= 0) list_insert(td, ti, part_d[base + e], i);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpList wl;
+  wl.init();
+  const int64_t base = static_cast<int64_t>(q) * parts * ncand;
+  const int total = parts * ncand;
+  for (int e = warp * 32 + lane; e - lane < total; e += kKnnThreads) {
+    const bool valid = e < total && part_i[base + e] >= 0;
+    wl.offer(valid ? part_d[base + e] : INFINITY, valid ? part_i[base + e] : 0x7fffffff, ncand, lane);
   }
-  block_take_smallest(td, ti, ncand, cand_d + q * ncand, cand_i + q * ncand);
+  if (lane < kMaxCand) { s_d[warp][lane] = wl.ld; s_i[warp][lane] = wl.li; }
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < kKnnWarps; ++w) {
+      const bool has = lane < kMaxCand;
+      wl.offer(has ? s_d[w][lane] : INFINITY, has ? s_i[w][lane] : 0x7fffffff, ncand, lane);
+    }
+    if (lane < ncand) {
+      cand_d[q * ncand + lane] = wl.li == 0x7fffffff ? INFINITY : wl.ld;
+      cand_i[q * ncand + lane] = wl.li == 0x7fffffff ? -1 : wl.li;
+    }
+  }
 }
 
 // grid (ncand, queries).  distance_sc(candidate, query) of scancontext_utils.py:81-113.
@@ -377,7 +388,7 @@ extern "C" {
 int cslam_sc_create(int rings, int sectors, int num_candidates, int device, cslam_sc_t** out) {
   CSLAM_REQUIRE(out != nullptr, "cslam_sc_create: out is NULL");
   *out = nullptr;
-  CSLAM_REQUIRE(rings > 0 && sectors > 0 && rings <= 256 && sectors <= 1024,
+  CSLAM_REQUIRE(rings > 0 && sectors > 0 && rings <= 96 && sectors <= 1024,
                 "cslam_sc_create: shape [%d, %d] out of range", rings, sectors);
   CSLAM_REQUIRE(num_candidates >= 1 && num_candidates <= kMaxCand,
                 "cslam_sc_create: num_candidates must be 1..%d", kMaxCand);
@@ -406,6 +417,7 @@ int cslam_sc_create(int rings, int sectors, int num_candidates, int device, csla
                        static_cast<int>(dist_smem(rings, sectors)));
   cudaFuncSetAttribute(k_sc_prepare<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, rings * sectors * 8);
   cudaFuncSetAttribute(k_sc_prepare<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, rings * sectors * 8);
+  cudaFuncSetAttribute(k_sc_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, rings * kKnnRows * 8);
   int s = sc_grow(h, 1000);
   if (s != CSLAM_OK) { cslam_sc_destroy(h); return s; }
   *out = h;
@@ -491,16 +503,23 @@ int cslam_sc_search_host(cslam_sc_t* h, const void* queries, int dtype, int nq, 
   CSLAM_TRY(h->qrk.reserve(static_cast<size_t>(nq) * R));
   // query ring keys are ring-major like the pool's: [rings][nq]
   CSLAM_TRY(sc_prepare(h, queries, dtype, nq, h->qcols.p, h->qnorm.p, h->qrk.p, nq, 0));
-  // chunks: enough CTAs for ~4 waves of the 148 SMs, at least 1024 entries per chunk
+  // query tiles of up to 8 (one warp each); with fewer queries the warps split the rows instead
+  const int qslots = nq >= 8 ? 8 : nq >= 4 ? 4 : nq >= 2 ? 2 : 1;
+  const int rparts = kKnnWarps / qslots;
+  const int qtiles = (nq + qslots - 1) / qslots;
   int dev_sms = 148;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device);
-  int chunks = (4 * dev_sms * 4 + nq - 1) / nq;
-  const int64_t max_chunks = (h->n + 1023) / 1024;
-  if (chunks > max_chunks) chunks = static_cast<int>(max_chunks);
-  if (chunks < 1) chunks = 1;
-  const int64_t rows_per_chunk = (h->n + chunks - 1) / chunks;
-  CSLAM_TRY(h->part_d.reserve(static_cast<size_t>(nq) * chunks * C));
-  CSLAM_TRY(h->part_i.reserve(static_cast<size_t>(nq) * chunks * C));
+  // ranges: ~2 waves of CTAs (4 resident per SM), at least one 256-entry step each
+  int ranges = (2 * dev_sms * 4 + qtiles - 1) / qtiles;
+  const int64_t max_ranges = (h->n + kKnnRows - 1) / kKnnRows;
+  if (ranges > max_ranges) ranges = static_cast<int>(max_ranges);
+  if (ranges < 1) ranges = 1;
+  int64_t rows_per_range = (h->n + ranges - 1) / ranges;
+  rows_per_range = (rows_per_range + kKnnRows - 1) / kKnnRows * kKnnRows;
+  ranges = static_cast<int>((h->n + rows_per_range - 1) / rows_per_range);
+  const int parts = ranges * rparts;
+  CSLAM_TRY(h->part_d.reserve(static_cast<size_t>(nq) * parts * C));
+  CSLAM_TRY(h->part_i.reserve(static_cast<size_t>(nq) * parts * C));
   CSLAM_TRY(h->cand_d.reserve(static_cast<size_t>(nq) * C));
   CSLAM_TRY(h->cand_i.reserve(static_cast<size_t>(nq) * C));
   CSLAM_TRY(h->dist.reserve(static_cast<size_t>(nq) * C));
@@ -510,15 +529,12 @@ int cslam_sc_search_host(cslam_sc_t* h, const void* queries, int dtype, int nq, 
   CSLAM_TRY(h->best_yaw.reserve(nq));
   cudaEventRecord(h->ev[0], h->stream);
   {
-    dim3 grid(chunks, nq);
-    if (R == 20)
-      k_sc_knn<20><<<grid, kKnnThreads, 0, h->stream>>>(h->rk, h->cap, h->n, R, h->qrk.p, C, rows_per_chunk,
-                                                      h->part_d.p, h->part_i.p);
-    else
-      k_sc_knn<0><<<grid, kKnnThreads, 0, h->stream>>>(h->rk, h->cap, h->n, R, h->qrk.p, C, rows_per_chunk,
-                                                     h->part_d.p, h->part_i.p);
+    dim3 grid(ranges, qtiles);
+    const size_t smem = static_cast<size_t>(R) * kKnnRows * sizeof(double);
+    k_sc_knn<<<grid, kKnnThreads, smem, h->stream>>>(h->rk, h->cap, h->n, R, h->qrk.p, nq, C, rows_per_range,
+                                                    qslots, h->part_d.p, h->part_i.p);
     CSLAM_LAUNCH_CHECK();
-    k_sc_knn_merge<<<nq, kKnnThreads, 0, h->stream>>>(h->part_d.p, h->part_i.p, chunks, C, h->cand_d.p, h->cand_i.p);
+    k_sc_knn_merge<<<nq, kKnnThreads, 0, h->stream>>>(h->part_d.p, h->part_i.p, parts, C, h->cand_d.p, h->cand_i.p);
     CSLAM_LAUNCH_CHECK();
   }
   cudaEventRecord(h->ev[1], h->stream);

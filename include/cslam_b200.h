@@ -165,6 +165,16 @@ int cslam_fiedler_csr(int n, const int32_t* indptr, const int32_t* indices, cons
                       double tol, int block_size, int device, double* lambda2, double* vec_out,
                       int* iters_out);
 
+/* Test hook: the small generalised eigenproblem GA y = theta GB y (s x s, row-major with a
+ * leading dimension of 6; 1 <= m <= 2 smallest pairs) that the eigen-solver solves once per
+ * iteration, by one warp, `reps` times.  impl 1 = register-resident solver (entry-per-lane
+ * Jacobi, the default of the eigen-solver), 0 = shared-memory solver.  c_out [6][2] (GB-orthonormal vectors), theta_out [2],
+ * *ok_out 0 when GB is not positive definite, cycles_out (nullable) [6]: SM cycles per solve:
+ * total, then set-up, Cholesky, triangular transforms, Jacobi sweeps, back substitution. */
+int cslam_debug_rayleigh_ritz(const double* ga, const double* gb, int s, int m, int impl, int sweeps,
+                              int reps, int device, double* c_out, double* theta_out, int* ok_out,
+                              int64_t* cycles_out);
+
 /* ---- A1-A5: descriptor extraction around the PyTorch backbone ------------- *
  * All pointers are DEVICE pointers (float32 unless noted); `stream` as above. */
 

@@ -137,3 +137,50 @@ def test_block_size_two_and_medium_graph_vs_oracle():
         assert abs(lam - lam_ref) < 1e-7 * max(1.0, lam_ref)
         assert np.abs(_align(vec, vec_ref) - vec_ref).max() < 1e-3
     assert not mac.stats()["jacobi_fallback"]
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_small_rayleigh_ritz_solvers_against_scipy(impl):
+    """The 6 x 6 generalised eigenproblem solved once per LOBPCG iteration (register-resident
+    and shared-memory warp solvers) against scipy.linalg.eigh: Ritz values to 1e-10 relative,
+    vectors GB-orthonormal with a small residual, for full and padded bases and for the badly
+    scaled bases of a nearly converged iteration."""
+    import ctypes
+    from scipy.linalg import eigh
+    from cslam_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    for s in (2, 4, 6):
+        for trial in range(12):
+            S = rng.normal(size=(40, s))
+            if trial % 3 == 1:
+                S[:, 2:] *= 1e-5          # W, P tiny next to X
+            if trial % 3 == 2:
+                S[:, s // 2:] = S[:, :s - s // 2] + 1e-3 * S[:, s // 2:]   # nearly dependent
+            M = rng.normal(size=(40, 40))
+            M = M @ M.T
+            GA = np.zeros((6, 6))
+            GB = np.zeros((6, 6))
+            GA[:s, :s] = S.T @ M @ S
+            GB[:s, :s] = S.T @ S
+            m = 2
+            C = np.zeros((6, 2))
+            th = np.zeros(2)
+            ok = ctypes.c_int()
+            _lib.check(lib.cslam_debug_rayleigh_ritz(_lib.ptr(GA), _lib.ptr(GB), s, m, impl, 8, 1, 0,
+                                                     _lib.ptr(C), _lib.ptr(th), ctypes.byref(ok), None))
+            assert ok.value == 1
+            w = eigh(GA[:s, :s], GB[:s, :s], eigvals_only=True)
+            cond = np.linalg.cond(GB[:s, :s] / np.sqrt(np.outer(np.diag(GB)[:s], np.diag(GB)[:s])))
+            np.testing.assert_allclose(th, w[:2], rtol=1e-13 * max(cond, 1e3), atol=0)
+            assert not C[s:].any()
+            G = C[:s].T @ GB[:s, :s] @ C[:s]
+            np.testing.assert_allclose(G, np.eye(2), atol=1e-13 * max(cond, 1e3))
+            res = GA[:s, :s] @ C[:s] - GB[:s, :s] @ C[:s] * th
+            scale = np.abs(GA[:s, :s] @ C[:s]).max()
+            assert np.abs(res).max() <= 1e-6 * scale     # single-precision angles, 8 sweeps
+    bad = np.eye(6)
+    bad[1, 1] = -1.0
+    _lib.check(lib.cslam_debug_rayleigh_ritz(_lib.ptr(np.eye(6)), _lib.ptr(bad), 4, 2, impl, 3, 1, 0,
+                                             _lib.ptr(C), _lib.ptr(th), ctypes.byref(ok), None))
+    assert ok.value == 0

@@ -18,6 +18,7 @@ SOURCES = [
     "nns_coarse_tc.cu",
     "heads.cu",
     "pca_tc.cu",
+    "vlad_tc.cu",
     "mac.cu",
     "scancontext.cu",
 ]

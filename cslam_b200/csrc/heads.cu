@@ -20,6 +20,9 @@
 #include "common.cuh"
 
 namespace cslam {
+bool vlad_tc_supported(const float* d_x, int channels, int locations, int clusters);
+int launch_vlad_tc(const float* d_x, int batch, int locations, const float* d_conv_w,
+                   const float* d_centroids, float* d_out, cudaStream_t stream);
 bool pca_tc_supported(const float* d_x, const float* d_w, int din, int dout);
 int launch_pca_gemm_tc(const float* d_x, int batch, int din, const float* d_w, int dout,
                        int max_ksplit, int num_sms, float* d_part, int* ksplit_out,
@@ -603,6 +606,12 @@ int cslam_vlad_forward(const float* d_x, int batch, int channels, int locations,
   CSLAM_REQUIRE(locations >= 1 && locations <= V_SMAX, "vlad_forward: 1 <= locations <= %d (got %d)",
                 V_SMAX, locations);
   if (batch == 0) return CSLAM_OK;
+  // default: aggregation on the tensor cores (vlad_tc.cu); CSLAM_VLAD_TC=0 or a shape TMA cannot
+  // address selects the fused fp32 kernel below
+  static const bool tc_off = getenv("CSLAM_VLAD_TC") && atoi(getenv("CSLAM_VLAD_TC")) == 0;
+  if (!tc_off && vlad_tc_supported(d_x, channels, locations, clusters))
+    return launch_vlad_tc(d_x, batch, locations, d_conv_w, d_centroids, d_out,
+                          static_cast<cudaStream_t>(stream));
   CSLAM_CUDA(cudaFuncSetAttribute(k_vlad, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(sizeof(VladSmem))));
   k_vlad<<<batch, V_THREADS, sizeof(VladSmem), static_cast<cudaStream_t>(stream)>>>(

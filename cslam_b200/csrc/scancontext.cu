@@ -144,19 +144,24 @@ constexpr int kKnnRows = 256;                 // pool entries staged per step
 // (w / qslots) -- 8 queries x 1 part, 4 x 2, 2 x 4 or 1 x 8 -- and keeps its nearest entries in a
 // WarpList.  part_*: [queries][parts][ncand], parts = ranges * row parts.
 // Algorithmic traffic: rings*8 B per pool entry per query TILE (not per query).
+template <int RINGS>   // > 0: compile-time ring count (query key in registers); 0: any count
 __global__ void __launch_bounds__(kKnnThreads)
-k_sc_knn(const double* __restrict__ rk, int64_t rk_stride, int64_t n, int rings,
+k_sc_knn(const double* __restrict__ rk, int64_t rk_stride, int64_t n, int rings_rt,
          const double* __restrict__ qrk, int nq, int ncand, int64_t rows_per_range, int qslots,
          double* part_d, int* part_i) {
+  const int rings = RINGS > 0 ? RINGS : rings_rt;
   extern __shared__ double s_rk[];            // [rings][kKnnRows]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rparts = kKnnWarps / qslots;
   const int slot = warp % qslots, rpart = warp / qslots;
   const int q = blockIdx.y * qslots + slot;
   const bool active = q < nq;
-  // this warp's query ring key: lane r holds ring r (rings <= 32), else read from global
-  double qk_lane = 0.0;
-  if (active && lane < rings && rings <= 32) qk_lane = qrk[static_cast<int64_t>(lane) * nq + q];
+  // this warp's query ring key in registers
+  double qk[RINGS > 0 ? RINGS : 1];
+  if (RINGS > 0) {
+#pragma unroll
+    for (int r = 0; r < RINGS; ++r) qk[r] = active ? qrk[static_cast<int64_t>(r) * nq + q] : 0.0;
+  }
   WarpList wl;
   wl.init();
   const int64_t lo = blockIdx.x * rows_per_range;
@@ -172,9 +177,10 @@ k_sc_knn(const double* __restrict__ rk, int64_t rk_stride, int64_t n, int rings,
     if (!active) continue;
     for (int c = rpart * 32 + lane; c - lane < cnt; c += 32 * rparts) {   // warp-uniform trip count
       double d = 0.0;
-      if (rings <= 32) {
-        for (int r = 0; r < rings; ++r) {
-          const double t = s_rk[r * kKnnRows + c] - __shfl_sync(0xffffffffu, qk_lane, r);
+      if (RINGS > 0) {
+#pragma unroll
+        for (int r = 0; r < RINGS; ++r) {
+          const double t = s_rk[r * kKnnRows + c] - qk[r];
           d = __dadd_rn(d, __dmul_rn(t, t));     // the reference's order of additions, no fma
         }
       } else {
@@ -417,7 +423,8 @@ int cslam_sc_create(int rings, int sectors, int num_candidates, int device, csla
                        static_cast<int>(dist_smem(rings, sectors)));
   cudaFuncSetAttribute(k_sc_prepare<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, rings * sectors * 8);
   cudaFuncSetAttribute(k_sc_prepare<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, rings * sectors * 8);
-  cudaFuncSetAttribute(k_sc_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, rings * kKnnRows * 8);
+  cudaFuncSetAttribute(k_sc_knn<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, rings * kKnnRows * 8);
+  cudaFuncSetAttribute(k_sc_knn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, rings * kKnnRows * 8);
   int s = sc_grow(h, 1000);
   if (s != CSLAM_OK) { cslam_sc_destroy(h); return s; }
   *out = h;
@@ -509,9 +516,10 @@ int cslam_sc_search_host(cslam_sc_t* h, const void* queries, int dtype, int nq, 
   const int qtiles = (nq + qslots - 1) / qslots;
   int dev_sms = 148;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device);
-  // ranges: ~2 waves of CTAs (4 resident per SM), at least one 256-entry step each
+  // ranges: ~2 waves of CTAs (4 resident per SM), at least four 256-entry steps each (every
+  // range adds `rparts` candidate lists per query to the merge)
   int ranges = (2 * dev_sms * 4 + qtiles - 1) / qtiles;
-  const int64_t max_ranges = (h->n + kKnnRows - 1) / kKnnRows;
+  const int64_t max_ranges = (h->n + 4 * kKnnRows - 1) / (4 * kKnnRows);
   if (ranges > max_ranges) ranges = static_cast<int>(max_ranges);
   if (ranges < 1) ranges = 1;
   int64_t rows_per_range = (h->n + ranges - 1) / ranges;
@@ -531,8 +539,12 @@ int cslam_sc_search_host(cslam_sc_t* h, const void* queries, int dtype, int nq, 
   {
     dim3 grid(ranges, qtiles);
     const size_t smem = static_cast<size_t>(R) * kKnnRows * sizeof(double);
-    k_sc_knn<<<grid, kKnnThreads, smem, h->stream>>>(h->rk, h->cap, h->n, R, h->qrk.p, nq, C, rows_per_range,
-                                                    qslots, h->part_d.p, h->part_i.p);
+    if (R == 20)
+      k_sc_knn<20><<<grid, kKnnThreads, smem, h->stream>>>(h->rk, h->cap, h->n, R, h->qrk.p, nq, C, rows_per_range,
+                                                          qslots, h->part_d.p, h->part_i.p);
+    else
+      k_sc_knn<0><<<grid, kKnnThreads, smem, h->stream>>>(h->rk, h->cap, h->n, R, h->qrk.p, nq, C, rows_per_range,
+                                                         qslots, h->part_d.p, h->part_i.p);
     CSLAM_LAUNCH_CHECK();
     k_sc_knn_merge<<<nq, kKnnThreads, 0, h->stream>>>(h->part_d.p, h->part_i.p, parts, C, h->cand_d.p, h->cand_i.p);
     CSLAM_LAUNCH_CHECK();

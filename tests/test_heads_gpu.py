@@ -51,6 +51,19 @@ def test_vlad_head_matches_reference_layer():
     assert np.abs(v2 - heads.netvlad_layer(x2, conv_w, cent)).max() < 2e-6
     # deterministic
     assert np.array_equal(v2, layer(_cuda(x2)).cpu().numpy())
+    # tensor-core aggregation path (locations % 4 == 0): one location tile with a K tail (7x8 = 56),
+    # two tiles without a tail (14x16 = 224), sharp soft-assignment (large conv weights, as in
+    # trained checkpoints), batch 64; S = 63 above took the fused fp32 kernel
+    rng = np.random.default_rng(6)
+    for shape, scale in (((3, 512, 7, 8), 1.0), ((3, 512, 14, 16), 1.0), ((64, 512, 14, 14), 1.0),
+                         ((2, 512, 14, 14), 40.0)):
+        x3 = rng.standard_normal(shape).astype(np.float32)
+        layer.load_state(conv_w * scale, cent)
+        v3 = layer(_cuda(x3)).cpu().numpy()
+        idx = np.arange(0, shape[0], max(1, shape[0] // 4))
+        assert np.abs(v3[idx] - heads.netvlad_layer(x3[idx], conv_w * scale, cent)).max() < 2e-6
+        np.testing.assert_allclose(np.linalg.norm(v3, axis=1), 1.0, atol=1e-5)
+        assert np.array_equal(v3, layer(_cuda(x3)).cpu().numpy())
 
 
 def test_pca_projection_matches_sklearn():

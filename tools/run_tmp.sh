@@ -1,12 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 python tools/probe_rr.py > gpurun_out/probe_rr.txt 2>&1; cat gpurun_out/probe_rr.txt
-timeout 300 python -m pytest tests/test_mac_gpu.py tests/test_acm_gpu.py -x -q -m gpu > gpurun_out/t_mac.txt 2>&1; tail -3 gpurun_out/t_mac.txt
-run() { tag=$1; shift; env "$@" timeout 200 python tools/probe_mac.py --reps 4 --bs 2 > gpurun_out/probe_mac_$tag.log 2>&1; echo "== $tag"; grep "rep 2\|rep 3\|prof" gpurun_out/probe_mac_$tag.log | cut -c1-420; }
-run rr0 CSLAM_RR_IMPL=0
-run rr1 CSLAM_RR_IMPL=1
-run rr1_s2 CSLAM_RR_IMPL=1 CSLAM_RR_SWEEPS=2
-run rr1_t24 CSLAM_RR_IMPL=1 CSLAM_RR_TOL2=1e-24
-run rr1_prof CSLAM_RR_IMPL=1 CSLAM_LOBPCG_PROF=1
-CSLAM_RR_SWEEPS=2 timeout 300 python tools/probe_mac.py --reps 1 --bs 2 --R 4 --P 5000 --m 20000 --k 100 --oracle 1 > gpurun_out/probe_mac_s2_oracle.log 2>&1; grep -c "= 0 " gpurun_out/probe_mac_s2_oracle.log; tail -1 gpurun_out/probe_mac_s2_oracle.log
-CSLAM_RR_TOL2=1e-24 timeout 300 python tools/probe_mac.py --reps 1 --bs 2 --R 4 --P 5000 --m 20000 --k 100 --oracle 1 > gpurun_out/probe_mac_t24_oracle.log 2>&1; grep -c "= 0 " gpurun_out/probe_mac_t24_oracle.log; tail -1 gpurun_out/probe_mac_t24_oracle.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r1b.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu_r1b.log; tail -6 gpurun_out/pytest_gpu_r1b.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -6 | tee gpurun_out/smoke_r1b.log
+CSLAM_VLAD_TC=1 timeout 100 python tools/probe_vlad.py | tee gpurun_out/probe_vlad_tc1.json
+CSLAM_VLAD_TC=0 timeout 100 python tools/probe_vlad.py | tee gpurun_out/probe_vlad_tc0.json
+timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_vlad' --csv --log-file gpurun_out/vlad_launches.csv python tools/probe_vlad.py > /dev/null 2>&1; tail -4 gpurun_out/vlad_launches.csv | cut -c1-250
+timeout 200 python tools/probe_sc.py --n 200000 --q 64 2>/dev/null | tee gpurun_out/probe_sc.json
+timeout 200 python tools/probe_sc.py --n 200000 --q 1 2>/dev/null | tee gpurun_out/probe_sc_q1.json
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r1b_n1.json 2> gpurun_out/bench_r1b_n1.err; tail -2 gpurun_out/bench_r1b_n1.err; cut -c1-400 gpurun_out/bench_r1b_n1.json

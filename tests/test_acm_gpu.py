@@ -199,3 +199,33 @@ def test_sparse_matching_facade():
     # intra-robot matching: too-recent keyframes are skipped
     kf, kfs = lcsm.match_local_loop_closures(lcsm.local_nnsm.data[50].astype(np.float64), 50)
     assert kf is None or abs(kf - 50) >= 5
+
+
+@pytest.mark.parametrize("tag", ["g1", "g2"])
+def test_columnar_and_edge_by_edge_paths_select_the_same_edges(tag):
+    """The candidate table's vectorised set-up and the reference-style walk over a plain dict feed
+    the solver the same problem: identical selections over three successive rounds (selected
+    edges leave the table, two of them come back as measurements each round)."""
+    R, P, m, k, seed = MAC_CASES[tag]
+    fixed, cand = _graph(R, P, m, seed)
+    fast, slow = _acm(R), _acm(R)
+    slow.candidate_edges = {}
+    for ac in (fast, slow):
+        ac.set_graph(list(fixed), list(cand))
+    in_range = {r: True for r in range(R)}
+    for rnd in range(3):
+        a = fast.select_candidates(k, in_range)
+        b = slow.select_candidates(k, in_range)
+        assert [tuple(e) for e in a] == [tuple(e) for e in b] and len(a) == k
+        assert list(fast.candidate_edges) == list(slow.candidate_edges)
+        assert fast.last_mac.stats()["lobpcg_iters"] == slow.last_mac.stats()["lobpcg_iters"]
+        fast.candidate_edges_to_fixed(list(a[:2]))
+        slow.candidate_edges_to_fixed(list(b[:2]))
+    r0 = np.array([e.robot0_id for e in cand[:50]])
+    more = (r0, np.array([e.robot0_keyframe_id for e in cand[:50]]), np.array([e.robot1_id for e in cand[:50]]),
+            np.array([e.robot1_keyframe_id for e in cand[:50]]), np.linspace(0.1, 0.9, 50))
+    fast.add_matches(*more)                       # blacklisted pairs stay out, the others come back
+    for t in range(50):
+        slow.add_match(_edges([tuple(int(c[t]) for c in more[:4]) + (float(more[4][t]),)])[0])
+    assert [(k_, tuple(v)) for k_, v in fast.candidate_edges.items()] == \
+        [(k_, tuple(v)) for k_, v in slow.candidate_edges.items()]

@@ -1,3 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:'k_sc_knn|k_sc_distance|k_sc_pick' -c 4 -o gpurun_out/r1_sc_search_ncu_full python tools/probe_sc.py --n 200000 --q 64 --reps 1 > gpurun_out/ncu_sc.log 2>&1; tail -2 gpurun_out/ncu_sc.log
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r1_final.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu_r1_final.log; tail -5 gpurun_out/pytest_gpu_r1_final.log
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke_r1_final.log
+timeout 100 python tools/probe_mac.py --reps 4 --bs 2 2>&1 | grep "rep " | cut -c1-100

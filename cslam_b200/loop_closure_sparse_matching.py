@@ -20,7 +20,8 @@ class LoopClosureSparseMatching(object):
         """
         self.params = params
         # reference :21-31: Scan Context matchers for lidar, cosine matchers otherwise
-        if self.params["frontend.sensor_type"] == "lidar":
+        self._lidar = self.params["frontend.sensor_type"] == "lidar"
+        if self._lidar:
             from .lidar_pr.scancontext_matching import ScanContextMatching as matcher
         else:
             matcher = NearestNeighborsMatching
@@ -60,6 +61,10 @@ class LoopClosureSparseMatching(object):
         Returns:
             list(EdgeInterRobot): new candidate edges, keyframe-major like the reference
         """
+        if self._lidar:   # Scan Context pools: the reference's one-by-one routing (same result by definition)
+            rows = embeddings.detach().cpu().numpy() if hasattr(embeddings, "detach") else np.asarray(embeddings)
+            return [m for row, k in zip(rows, keyframe_ids)
+                    for m in self.add_local_global_descriptor(row, int(k))]
         import torch
         keyframe_ids = [int(k) for k in keyframe_ids]
         if not torch.is_tensor(embeddings):
@@ -103,6 +108,8 @@ class LoopClosureSparseMatching(object):
         """
         if len(msgs) == 0:
             return []
+        if self._lidar:
+            return [self.add_other_robot_global_descriptor(m) for m in msgs]
         robot_id = msgs[0].robot_id
         assert all(m.robot_id == robot_id for m in msgs)
         desc = np.stack([np.asarray(m.descriptor) for m in msgs])
@@ -132,6 +139,9 @@ class LoopClosureSparseMatching(object):
         Returns:
             list((kf_match or None, kfs or None)): per keyframe, as match_local_loop_closures
         """
+        if self._lidar:
+            raise NotImplementedError("batched intra-robot matching is written for the cosine pools; "
+                                      "use match_local_loop_closures per keyframe with Scan Context")
         import torch
         k = self.params['frontend.nb_best_matches']
         B = len(keyframe_ids)

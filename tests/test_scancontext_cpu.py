@@ -54,3 +54,42 @@ def test_distance_is_rotation_invariant_and_zero_safe():
         assert abs(d) < 1e-12 and yaw == shift
     assert distance_sc(np.zeros((20, 60)), sc) == (1.0, 1)
     assert np.allclose(sc2rk(sc), sc.mean(axis=1))
+
+
+def test_sparse_matching_facade_routes_lidar_descriptors(monkeypatch):
+    """`frontend.sensor_type: lidar` makes LoopClosureSparseMatching build Scan Context matchers
+    (reference cslam/loop_closure_sparse_matching.py:21-31); the routing (:36-72) and the batched
+    forms give the same candidate edges.  The GPU matcher is replaced by the oracle here (host
+    logic only)."""
+    import types
+    from collections import namedtuple
+    import cslam_b200.lidar_pr.scancontext_matching as mod
+    from cslam_b200.loop_closure_sparse_matching import LoopClosureSparseMatching
+    monkeypatch.setattr(mod, "ScanContextMatching", ScanContextMatchingOracle)
+    Msg = namedtuple("Msg", ["robot_id", "keyframe_id", "descriptor"])
+    params = {"frontend.sensor_type": "lidar", "robot_id": 0, "max_nb_robots": 3,
+              "frontend.similarity_threshold": 0.6, "frontend.nb_best_matches": 5,
+              "frontend.intra_loop_min_inbetween_keyframes": 2,
+              "frontend.enable_sparsification": True, "evaluation.enable_sparsification_comparison": False}
+    pool, _, queries = sc_case("p4")
+    one, many = LoopClosureSparseMatching(dict(params)), LoopClosureSparseMatching(dict(params))
+    assert isinstance(one.local_nnsm, ScanContextMatchingOracle)
+    assert all(isinstance(m, ScanContextMatchingOracle) for m in one.other_robots_nnsm.values())
+    remote = [Msg(1 + t % 2, 10 + t, pool[t]) for t in range(4)]
+    local = [np.roll(pool[t].reshape(20, 60), 7 + t, axis=1).ravel() for t in range(4)]
+    a = [one.add_other_robot_global_descriptor(m) for m in remote]
+    b = many.add_other_robot_global_descriptors(remote)
+    assert a == b == [None] * 4                       # nothing local yet
+    a = [m for t, d in enumerate(local) for m in one.add_local_global_descriptor(d, t)]
+    b = many.add_local_global_descriptors(np.stack(local), range(4))
+    assert [tuple(e) for e in a] == [tuple(e) for e in b] and len(a) == 4
+    assert [(e.robot1_id, e.robot1_keyframe_id) for e in a] == [(1 + t % 2, 10 + t) for t in range(4)]
+    assert all(e.weight > 0.999 for e in a)           # rotated revisits
+    more = [Msg(2, 20 + t, np.roll(local[t].reshape(20, 60), 3, axis=1).ravel()) for t in range(4)]
+    a2 = [one.add_other_robot_global_descriptor(m) for m in more]
+    b2 = many.add_other_robot_global_descriptors(more)
+    assert [tuple(e) for e in a2] == [tuple(e) for e in b2] and [e.robot0_keyframe_id for e in a2] == [0, 1, 2, 3]
+    assert dict(one.candidate_selector.candidate_edges.items()) == dict(many.candidate_selector.candidate_edges.items())
+    assert one.match_local_loop_closures(local[0], 9)[0] == 0
+    with pytest.raises(NotImplementedError):
+        many.match_local_loop_closures_batch(np.stack(local), [4, 5, 6, 7], 4)

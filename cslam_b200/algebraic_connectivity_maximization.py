@@ -338,17 +338,21 @@ class AlgebraicConnectivityMaximization(object):
     def _candidate_columns(self, is_robot_included):
         """`rekey_edges(self.candidate_edges.values(), ...)` as an (i, j, weight) array triple
         straight from the candidate table's columns."""
-        ends, w = self.candidate_edges.columns()
+        ends, w, alive = self.candidate_edges.raw()
         robots = range(self.max_nb_robots)
         inc = np.array([bool(is_robot_included[r]) for r in robots])
         off = np.array([self.offsets[r] for r in robots], dtype=np.int64)
         r0, r1 = ends[:, 0], ends[:, 2]
-        i = off[r0] + ends[:, 1]
-        j = off[r1] + ends[:, 3]
-        both = inc[r0] & inc[r1]
-        if not both.all():
-            i, j, w = i[both], j[both], w[both]
-        return i.astype(np.int32), j.astype(np.int32), np.array(w, dtype=np.float64)
+        # computed over every slot, live or not, and filtered once (a removed slot keeps its old,
+        # valid, contents): one 16 MB gather instead of copying the 40 MB of live columns first
+        i = (off[r0] + ends[:, 1]).astype(np.int32)
+        j = (off[r1] + ends[:, 3]).astype(np.int32)
+        keep = inc[r0] & inc[r1]
+        if alive is not None:
+            keep &= alive
+        if not keep.all():
+            return i[keep], j[keep], w[keep]
+        return i, j, np.array(w, dtype=np.float64)
 
     def _fixed_columns(self, is_robot_included):
         """`rekey_edges(self.fixed_edges, ...) + fill_odometry()` as an array triple."""
@@ -395,12 +399,7 @@ class AlgebraicConnectivityMaximization(object):
         seen = {self.robot_id}
         edges = list(self.fixed_edges)
         if isinstance(self.candidate_edges, CandidateTable):
-            ends, _ = self.candidate_edges.columns()
-            if len(ends):
-                present = np.bincount(ends[:, 0]) > 0
-                other = np.bincount(ends[:, 2]) > 0
-                seen.update(r for r in np.flatnonzero(present).tolist() + np.flatnonzero(other).tolist()
-                            if is_other_robot_considered[r])
+            seen.update(r for r in self.candidate_edges.robots_present() if is_other_robot_considered[r])
         else:
             edges += list(self.candidate_edges.values())
         for edge in edges:

@@ -123,6 +123,26 @@ class CandidateTable(MutableMapping):
         live = self._alive[:self._top]
         return self._ends[:self._top][live], self._w[:self._top][live]
 
+    def raw(self):
+        """(ends [top, 4], weight [top], alive [top] or None): every slot handed out so far, dead
+        ones included (`alive` is None when there are none) — for callers that filter once at
+        the end instead of copying the live rows first."""
+        if self._dead and self._dead * 2 > self._top:
+            self._compact()
+        top = self._top
+        return self._ends[:top], self._w[:top], (self._alive[:top] if self._dead else None)
+
+    def robots_present(self):
+        """Sorted robot ids that appear in a live edge (either end)."""
+        ends, _, alive = self.raw()
+        if len(ends) == 0:
+            return []
+        if alive is None:
+            seen = np.bincount(ends[:, 0]) > 0, np.bincount(ends[:, 2]) > 0
+        else:
+            seen = np.bincount(ends[:, 0], weights=alive) > 0, np.bincount(ends[:, 2], weights=alive) > 0
+        return sorted(set(np.flatnonzero(seen[0]).tolist()) | set(np.flatnonzero(seen[1]).tolist()))
+
     def weight_of(self, key):
         """Stored weight for `key`, or None — without materialising the edge object."""
         s = self._slot.get(key)

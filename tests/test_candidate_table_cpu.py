@@ -40,6 +40,10 @@ def test_table_behaves_like_a_dict_under_random_edits():
             ends, w = table.columns()
             assert [tuple(r) for r in ends.tolist()] == [tuple(e[:4]) for e in plain.values()]
             assert w.tolist() == [e.weight for e in plain.values()]
+            raw_ends, raw_w, alive = table.raw()
+            live = np.ones(len(raw_w), bool) if alive is None else alive
+            assert raw_ends[live].tolist() == ends.tolist() and raw_w[live].tolist() == w.tolist()
+            assert table.robots_present() == sorted({e[0] for e in plain.values()} | {e[2] for e in plain.values()})
     assert len(table) == len(plain) and list(table) == list(plain)
     assert table == plain
     with pytest.raises(KeyError):

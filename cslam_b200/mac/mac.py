@@ -38,7 +38,8 @@ class MAC:
         ci, cj, cw = self._as_arrays(candidate_measurements)
         self._fixed = (fi, fj, fw)
         self.weights = cw
-        self.edge_list = np.stack([ci, cj], axis=1) if len(ci) else np.zeros((0, 2), dtype=np.int32)
+        self._cand_ij = (ci, cj)
+        self._edge_list = None      # [m, 2] view of the reference (mac.py:27), built on first use
         self._device = _resolve_device(device)
         h = ctypes.c_void_p()
         _lib.check(lib.cslam_mac_create(self.num_poses, len(fi), _lib.ptr(fi), _lib.ptr(fj),
@@ -85,6 +86,15 @@ class MAC:
                 "algorithmic_bytes": c.value}
 
     # ---- reference API -----------------------------------------------------
+    @property
+    def edge_list(self):
+        """[m, 2] int array of the candidate endpoints (mac.py:27); assembled on demand — the
+        solver works on the separate index arrays it was created from."""
+        if self._edge_list is None:
+            ci, cj = self._cand_ij
+            self._edge_list = np.stack([ci, cj], axis=1) if len(ci) else np.zeros((0, 2), dtype=np.int32)
+        return self._edge_list
+
     @property
     def L_odom(self):
         """scipy CSR Laplacian of the fixed edges (mac.py:22-23), built on demand."""

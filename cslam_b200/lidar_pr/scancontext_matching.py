@@ -23,13 +23,13 @@ from .. import _lib
 
 
 class ScanContextMatching(object):
-    """Nearest Neighbor matching of description vectors
-    """
+    """Pool of Scan Context descriptors with ring-key candidate search and column-shift
+    scoring (reference class of the same name)."""
 
     def __init__(self, shape=[20, 60], num_candidates=10, threshold=0.15, device=None):
-        """ Initialization
-            Default configs are the same as in the original paper
-        """
+        """shape = [rings, sectors] of a descriptor, num_candidates = ring-key neighbours scored
+        per query, threshold kept for signature compatibility (unused, as in the reference);
+        defaults as in the reference (:10)."""
         lib = _lib.load()
         _lib.require_device()
         self.shape = shape
@@ -101,12 +101,7 @@ class ScanContextMatching(object):
             self.nb_items += 1
 
     def add_item(self, descriptor, item):
-        """Add item to the matching list
-
-        Args:
-            descriptor (np.array): descriptor
-            item: identification info (e.g., int)
-        """
+        """Append one descriptor (flat or [rings, sectors]) under the caller's id `item` (:24-46)."""
         self.add_items(np.asarray(descriptor).reshape(1, -1), [item])
 
     # ---- search -------------------------------------------------------------------------
@@ -133,15 +128,8 @@ class ScanContextMatching(object):
         return (rows, sims, yaw, cand, cdist) if details else (rows, sims, yaw)
 
     def search(self, query, k):
-        """Search for nearest neighbors
-
-        Args:
-            query (np.array): descriptor to match
-            k (int): number of best matches to return
-
-        Returns:
-            list(int, np.array): best matches
-        """
+        """Best match of `query` as two one-element lists `[item], [similarity]`; `k` is accepted
+        and ignored like in the reference, which returns a single match (:48-89)."""
         if self.nb_items < 1:
             return [None], [None]
         rows, sims, yaw = self.search_batch(np.asarray(query).reshape(1, -1))
@@ -153,15 +141,7 @@ class ScanContextMatching(object):
         return [self.items[row]], [sims[0]]
 
     def search_best(self, query):
-        """Search for the nearest neighbor
-            Implementation for compatibily only
-
-        Args:
-            query (np.array): descriptor to match
-
-        Returns:
-            int, np.array: best match
-        """
+        """`(item, similarity)` of the best match, `(None, None)` for an empty pool (:91-104)."""
         if self.nb_items < 1:
             return None, None
         idxs, sims = self.search(query, 1)

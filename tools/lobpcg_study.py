@@ -1,0 +1,155 @@
+"""CPU study (numpy/scipy, no GPU) of the eigen-solver's ITERATION COUNT on the C5 graph: the
+GPU solver's algorithm (LOBPCG on 1-perp, block m, preconditioner = tridiagonal part of L, residual
+||L x - theta x||_1 / ||L||_inf < 1e-10) restated in numpy, and variants of it.  What an iteration
+costs is measured on the GPU (profiles/r1_rr_variants.txt); how many are needed is a property of
+the algorithm and can be explored here.
+
+    python tools/lobpcg_study.py [--scale 1.0]
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import scipy.sparse as sp
+from scipy.linalg import eigh, solve_banded
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle.inputs import mac_scale_graph  # noqa: E402
+
+
+def laplacian(n, i, j, w):
+    A = sp.coo_matrix((np.r_[w, w], (np.r_[i, j], np.r_[j, i])), shape=(n, n)).tocsr()
+    d = np.asarray(A.sum(axis=1)).ravel()
+    return (sp.diags(d) - A).tocsr()
+
+
+class TriPrec:
+    """x -> tridiag(L)^-1 x (banded solve)."""
+    def __init__(self, L):
+        n = L.shape[0]
+        self.ab = np.zeros((3, n))
+        self.ab[1] = L.diagonal()
+        off = L.diagonal(1)
+        self.ab[0, 1:] = off
+        self.ab[2, :-1] = off
+
+    def __call__(self, R):
+        return solve_banded((1, 1), self.ab, R)
+
+
+def lobpcg(L, m, prec, tol=1e-10, max_iters=3000, inner=0, inner_omega=None, X0=None, seed=7, want_x=False):
+    """Returns (theta0, iterations, SpMM count).  inner > 0: W = result of `inner` extra steps of
+    preconditioned Richardson/Chebyshev on (L - theta I) w = r starting from prec(r)."""
+    n = L.shape[0]
+    lnorm = abs(L).sum(axis=1).max()
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(n, m)) if X0 is None else X0.copy()
+    X -= X.mean(axis=0)
+    AX = L @ X
+    th, C = eigh(X.T @ AX, X.T @ X)
+    X, AX = X @ C, AX @ C
+    P = AP = None
+    spmm = 1
+    for it in range(max_iters):
+        R = AX - X * th
+        if np.abs(R[:, 0]).sum() / lnorm < tol:
+            return (th[0], it, spmm, X) if want_x else (th[0], it, spmm)
+        W = prec(R)
+        for s in range(inner):            # polynomial smoothing of the correction
+            Rw = R - (L @ W - W * th)      # residual of (L - theta) W = R
+            spmm += 1
+            W = W + (inner_omega if inner_omega else 1.0) * prec(Rw)
+        W -= W.mean(axis=0)
+        AW = L @ W
+        spmm += 1
+        S = [X, W] + ([P] if P is not None else [])
+        AS = [AX, AW] + ([AP] if P is not None else [])
+        S, AS = np.hstack(S), np.hstack(AS)
+        # column scaling like the GPU solve
+        d = 1.0 / np.sqrt((S * S).sum(axis=0))
+        GA, GB = (S.T @ AS) * np.outer(d, d), (S.T @ S) * np.outer(d, d)
+        try:
+            lam, Y = eigh(0.5 * (GA + GA.T), 0.5 * (GB + GB.T))
+        except np.linalg.LinAlgError:
+            S, AS = S[:, :2 * m], AS[:, :2 * m]
+            d = d[:2 * m]
+            GA, GB = (S.T @ AS) * np.outer(d, d), (S.T @ S) * np.outer(d, d)
+            lam, Y = eigh(0.5 * (GA + GA.T), 0.5 * (GB + GB.T))
+        Y = Y[:, :m] * d[:S.shape[1], None]
+        th = lam[:m]
+        Pn = S[:, m:] @ Y[m:]
+        APn = AS[:, m:] @ Y[m:]
+        X = X @ Y[:m] + Pn
+        AX = AX @ Y[:m] + APn
+        P, AP = Pn, APn
+    return (th[0], max_iters, spmm, X) if want_x else (th[0], max_iters, spmm)
+
+
+def frank_wolfe(n, fixed, cand, k, iters, **kw):
+    """The Frank-Wolfe loop of MAC.fw_subset (mac.py:191-233) around warm-started solves; returns the
+    LOBPCG iterations of every solve, the SpMM total and the final selection."""
+    ci, cj, cw = cand
+    w = np.zeros(len(cw))
+    w[np.argpartition(cw, -k)[-k:]] = 1.0
+    X = None
+    counts, spmm_total = [], 0
+    for it in range(iters):
+        act = np.flatnonzero(w > 1e-10)
+        L = laplacian(n, np.r_[fixed[0], ci[act]], np.r_[fixed[1], cj[act]], np.r_[fixed[2], w[act] * cw[act]])
+        th, its, spmm, X = lobpcg(L, prec=TriPrec(L), X0=X, want_x=True, **kw)
+        counts.append(its)
+        spmm_total += spmm
+        v = X[:, 0] / np.linalg.norm(X[:, 0])
+        g = cw * (v[ci] - v[cj]) ** 2
+        s = np.zeros(len(cw))
+        s[np.argpartition(g, -k)[-k:]] = 1.0
+        w = w + 2.0 / (it + 2.0) * (s - w)
+    return counts, spmm_total, np.sort(np.argpartition(w, -k)[-k:])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the C5 graph (poses, candidates)")
+    ap.add_argument("--k", type=int, default=1000)
+    ap.add_argument("--fw", type=int, default=0, help="run this many Frank-Wolfe iterations per variant instead")
+    a = ap.parse_args()
+    R, Pn, mc = 8, int(12500 * a.scale), int(1_000_000 * a.scale)
+    fixed, cand, n = mac_scale_graph(R, Pn, mc)
+    k = max(10, int(a.k * a.scale))
+    sel = np.argpartition(cand[2], -k)[-k:]
+    i = np.r_[fixed[0], cand[0][sel]]
+    j = np.r_[fixed[1], cand[1][sel]]
+    w = np.r_[fixed[2], cand[2][sel]]
+    L = laplacian(n, i, j, w)
+    prec = TriPrec(L)
+    if a.fw:
+        print(f"n = {n}, {mc} candidates, budget {k}: {a.fw} Frank-Wolfe iterations, warm-started solves")
+        base = None
+        for label, kw in (("block 2 (the GPU solver)", dict(m=2)), ("block 1", dict(m=1)),
+                          ("block 2 + 1 smoothing step", dict(m=2, inner=1)),
+                          ("block 1 + 1 smoothing step", dict(m=1, inner=1))):
+            t0 = time.time()
+            counts, spmm, selection = frank_wolfe(n, fixed, cand, k, a.fw, **kw)
+            base = selection if base is None else base
+            print(f"  {label:30s} LOBPCG iterations {sum(counts):5d} (first {counts[0]}, then mean {np.mean(counts[1:]):.0f})  "
+                  f"SpMM {spmm:5d}  selection differs in {len(set(base) ^ set(selection))} edges  {time.time() - t0:.0f} s", flush=True)
+        return
+    print(f"n = {n}, nnz = {L.nnz}, first Frank-Wolfe Laplacian (greedy start, {k} active candidates)")
+    ref = None
+    for label, kw in (("block 2, tridiagonal (the GPU solver)", dict(m=2)),
+                      ("block 1", dict(m=1)),
+                      ("block 3", dict(m=3)),
+                      ("block 4", dict(m=4)),
+                      ("block 2 + 1 smoothing step", dict(m=2, inner=1)),
+                      ("block 2 + 2 smoothing steps", dict(m=2, inner=2)),
+                      ("block 2 + 4 smoothing steps", dict(m=2, inner=4))):
+        t0 = time.time()
+        th, it, spmm = lobpcg(L, prec=prec, **kw)
+        ref = th if ref is None else ref
+        print(f"  {label:40s} iterations {it:5d}  SpMM {spmm:5d}  lambda2 {th:.12e}  (d {abs(th - ref):.1e})  {time.time() - t0:.1f} s")
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,50 @@ class TriPrec:
         return solve_banded((1, 1), self.ab, R)
 
 
+def chain_hats(n, robots, poses, h):
+    """Prolongation Z [n, nc]: piecewise-linear hat functions along every robot's pose chain, one
+    coarse node every h poses (plus the chain end)."""
+    rows, cols, vals, col = [], [], [], 0
+    for r in range(robots):
+        base = r * poses
+        nodes = np.arange(0, poses, h)
+        if nodes[-1] != poses - 1:
+            nodes = np.r_[nodes, poses - 1]
+        for a in range(len(nodes) - 1):
+            x0, x1 = nodes[a], nodes[a + 1]
+            idx = np.arange(x0, x1 + (1 if a == len(nodes) - 2 else 0))
+            t = (idx - x0) / (x1 - x0)
+            rows += list(base + idx) * 2
+            cols += [col + a] * len(idx) + [col + a + 1] * len(idx)
+            vals += list(1 - t) + list(t)
+        col += len(nodes)
+    return sp.csr_matrix((vals, (rows, cols)), shape=(n, col))
+
+
+class ShiftInvert:
+    """x -> (L + sigma I)^-1 x by sparse LU: what an ideal preconditioner at shift 0 would give."""
+    def __init__(self, L, sigma):
+        import scipy.sparse.linalg as spl
+        self.lu = spl.splu((L + sigma * sp.identity(L.shape[0])).tocsc())
+
+    def __call__(self, R):
+        return self.lu.solve(R)
+
+
+class TwoLevel:
+    """Multiplicative two-level preconditioner: exact coarse solve on span(Z), then one
+    tridiagonal smoothing step on the remaining residual."""
+    def __init__(self, L, Z):
+        import scipy.sparse.linalg as spl
+        self.L, self.Z, self.tri = L, Z, TriPrec(L)
+        Lc = (Z.T @ L @ Z).tocsc()
+        self.lu = spl.splu((Lc + 1e-9 * sp.identity(Lc.shape[0])).tocsc())
+
+    def __call__(self, R):
+        y = self.Z @ self.lu.solve(self.Z.T @ R)
+        return y + self.tri(R - self.L @ y)
+
+
 def lobpcg(L, m, prec, tol=1e-10, max_iters=3000, inner=0, inner_omega=None, X0=None, seed=7, want_x=False):
     """Returns (theta0, iterations, SpMM count).  inner > 0: W = result of `inner` extra steps of
     preconditioned Richardson/Chebyshev on (L - theta I) w = r starting from prec(r)."""
@@ -87,7 +131,7 @@ def lobpcg(L, m, prec, tol=1e-10, max_iters=3000, inner=0, inner_omega=None, X0=
     return (th[0], max_iters, spmm, X) if want_x else (th[0], max_iters, spmm)
 
 
-def frank_wolfe(n, fixed, cand, k, iters, **kw):
+def frank_wolfe(n, fixed, cand, k, iters, make_prec=TriPrec, **kw):
     """The Frank-Wolfe loop of MAC.fw_subset (mac.py:191-233) around warm-started solves; returns the
     LOBPCG iterations of every solve, the SpMM total and the final selection."""
     ci, cj, cw = cand
@@ -98,7 +142,7 @@ def frank_wolfe(n, fixed, cand, k, iters, **kw):
     for it in range(iters):
         act = np.flatnonzero(w > 1e-10)
         L = laplacian(n, np.r_[fixed[0], ci[act]], np.r_[fixed[1], cj[act]], np.r_[fixed[2], w[act] * cw[act]])
-        th, its, spmm, X = lobpcg(L, prec=TriPrec(L), X0=X, want_x=True, **kw)
+        th, its, spmm, X = lobpcg(L, prec=make_prec(L), X0=X, want_x=True, **kw)
         counts.append(its)
         spmm_total += spmm
         v = X[:, 0] / np.linalg.norm(X[:, 0])
@@ -127,9 +171,13 @@ def main():
     if a.fw:
         print(f"n = {n}, {mc} candidates, budget {k}: {a.fw} Frank-Wolfe iterations, warm-started solves")
         base = None
+        hats = {h: chain_hats(n, R, Pn, h) for h in (128, 64, 32)}
         for label, kw in (("block 2 (the GPU solver)", dict(m=2)), ("block 1", dict(m=1)),
                           ("block 2 + 1 smoothing step", dict(m=2, inner=1)),
-                          ("block 1 + 1 smoothing step", dict(m=1, inner=1))):
+                          ("block 1 + 1 smoothing step", dict(m=1, inner=1)),
+                          ("block 2, two-level h=128", dict(m=2, make_prec=lambda L: TwoLevel(L, hats[128]))),
+                          ("block 2, two-level h=64", dict(m=2, make_prec=lambda L: TwoLevel(L, hats[64]))),
+                          ("block 2, two-level h=32", dict(m=2, make_prec=lambda L: TwoLevel(L, hats[32])))):
             t0 = time.time()
             counts, spmm, selection = frank_wolfe(n, fixed, cand, k, a.fw, **kw)
             base = selection if base is None else base
@@ -144,9 +192,15 @@ def main():
                       ("block 4", dict(m=4)),
                       ("block 2 + 1 smoothing step", dict(m=2, inner=1)),
                       ("block 2 + 2 smoothing steps", dict(m=2, inner=2)),
-                      ("block 2 + 4 smoothing steps", dict(m=2, inner=4))):
+                      ("block 2 + 4 smoothing steps", dict(m=2, inner=4)),
+                      ("block 2, two-level h=128 (coarse+smooth)", dict(m=2, prec=TwoLevel(L, chain_hats(n, R, Pn, 128)))),
+                      ("block 2, two-level h=64", dict(m=2, prec=TwoLevel(L, chain_hats(n, R, Pn, 64)))),
+                      ("block 2, two-level h=32", dict(m=2, prec=TwoLevel(L, chain_hats(n, R, Pn, 32)))),
+                      ("block 2, exact (L + 1e-5 I)^-1", dict(m=2, prec=ShiftInvert(L, 1e-5)))):
         t0 = time.time()
-        th, it, spmm = lobpcg(L, prec=prec, **kw)
+        kw = dict(kw)
+        kw.setdefault("prec", prec)
+        th, it, spmm = lobpcg(L, **kw)
         ref = th if ref is None else ref
         print(f"  {label:40s} iterations {it:5d}  SpMM {spmm:5d}  lambda2 {th:.12e}  (d {abs(th - ref):.1e})  {time.time() - t0:.1f} s")
 

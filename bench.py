@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--mac-candidates", type=int, default=1000000)
     ap.add_argument("--mac-budget", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the top-k recall check against the oracle")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--profile-mode", action="store_true",
                     help="only the device-resident timed loop (for ncu launch lists; prints no bench line)")
@@ -298,6 +299,37 @@ def run_reference(args):
         "wall_s": time.time() - t0}))
 
 
+def nns_parity(pool, dim, k, dev, nq=4, chunk=100000):
+    """BASELINE.json's metric asks for the top-k match recall against the reference next to the
+    throughput: `nq` fresh queries are searched on the GPU and scored again, against EVERY row of the
+    same pool, by the oracle's restatement of the reference arithmetic (oracle/nns.py, float32
+    queries like the descriptors of the bench).  Outside the timed region; rank 0, one GPU."""
+    import torch
+    from oracle.nns import NNSOracle, lists_match_modulo_ties
+    g = torch.Generator(device=dev).manual_seed(99)
+    q = torch.rand((nq, dim), generator=g, device=dev)
+    q = (q / q.norm(dim=1, keepdim=True)).float().contiguous()
+    idx, sims = pool.search_batch_device(q, k)
+    idx, sims, qh = idx.cpu().numpy().astype(np.int64), sims.cpu().numpy(), q.cpu().numpy()
+    n = int(pool.n)
+    full = np.empty((nq, n))
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        orc = NNSOracle(dim)
+        orc.data, orc.n = pool.read_rows(s, m), m
+        for t in range(nq):
+            full[t, s:s + m] = orc.similarities_vec(qh[t])
+    hits, same, dmax = 0, 0, 0.0
+    for t in range(nq):
+        ref = np.argsort(full[t])[::-1][:idx.shape[1]]
+        hits += len(set(ref.tolist()) & set(idx[t].tolist()))
+        same += int(lists_match_modulo_ties(list(idx[t]), list(ref), full[t]))
+        dmax = max(dmax, float(np.abs(sims[t] - full[t][idx[t]]).max()))
+    return {"nns_queries_checked": nq, "nns_top_k": int(idx.shape[1]), "nns_recall_at_k": hits / float(idx.size),
+            "nns_ranked_lists_identical": same, "nns_max_abs_dsim": dmax, "pool_rows_scored": n,
+            "against": "oracle/nns.py: reference arithmetic over every pool row"}
+
+
 # -------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -494,6 +526,11 @@ def run_ours(args):
     }
     if mac is not None:
         line["mac_stats"] = mac.stats()
+    if rank == 0 and world == 1 and not args.no_parity:
+        try:
+            line["parity"] = nns_parity(pool, args.dim, K, dev)
+        except Exception as e:   # never lose the measurement line to the checker
+            line["parity"] = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, sample, parts = cpu_reference(args, args.cpu_seconds)
         line["cpu_baseline"] = {"value": v, "unit": "keyframes/s", "cores": os.cpu_count(), "kind": "port",

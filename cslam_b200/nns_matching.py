@@ -75,6 +75,13 @@ class NearestNeighborsMatching(object):
             _lib.check(_lib.load().cslam_nns_read_rows(self._h, 0, self.n, _lib.ptr(out)))
         return out
 
+    def read_rows(self, start, count):
+        """float32 [count, dim] copy of pool rows [start, start + count)."""
+        out = np.empty((int(count), self.dim), dtype=np.float32)
+        if count > 0:
+            _lib.check(_lib.load().cslam_nns_read_rows(self._h, int(start), int(count), _lib.ptr(out)))
+        return out
+
     # -- reference methods ---------------------------------------------------
     def add_item(self, vector, item):
         """Add item to the matching list (nns_matching.py:23-40)."""

@@ -47,3 +47,42 @@ def test_product_arm_needs_a_gpu():
     p = _run("--steps", "1", "--warmup", "0")
     assert p.returncode != 0
     assert "no CPU fallback" in (p.stderr + p.stdout)
+
+
+def test_nns_parity_block_with_a_stand_in_pool():
+    """The recall check bench.py attaches to its line (`parity`), driven with a CPU stand-in for
+    the GPU pool: an exact pool gives recall 1 and identical ranked lists, a pool that returns a
+    wrong neighbour is caught."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle.nns import NNSOracle
+
+    class Pool:
+        def __init__(self, rows, spoil=False):
+            self.rows, self.n, self.spoil = rows.astype(np.float32), len(rows), spoil
+
+        def read_rows(self, start, count):
+            return self.rows[start:start + count].copy()
+
+        def search_batch_device(self, q, k):
+            orc = NNSOracle(self.rows.shape[1])
+            orc.data, orc.n = self.rows, self.n
+            idx, sims = [], []
+            for row in q.numpy():
+                full = orc.similarities_vec(row)
+                order = np.argsort(full)[::-1][:k].copy()
+                if self.spoil:
+                    order[-1] = np.argsort(full)[0]           # the worst row instead of the k-th best
+                idx.append(order)
+                sims.append(full[order])
+            return torch.tensor(np.array(idx), dtype=torch.int32), torch.tensor(np.array(sims))
+
+    rng = np.random.default_rng(0)
+    rows = rng.random((2500, 32))
+    good = bench.nns_parity(Pool(rows), 32, 10, torch.device("cpu"), nq=3, chunk=1000)
+    assert good["nns_recall_at_k"] == 1.0 and good["nns_ranked_lists_identical"] == 3
+    assert good["nns_max_abs_dsim"] == 0.0 and good["pool_rows_scored"] == 2500 and good["nns_top_k"] == 10
+    bad = bench.nns_parity(Pool(rows, spoil=True), 32, 10, torch.device("cpu"), nq=3, chunk=1000)
+    assert bad["nns_recall_at_k"] == pytest.approx(0.9) and bad["nns_ranked_lists_identical"] == 0

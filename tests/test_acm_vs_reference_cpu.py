@@ -86,3 +86,37 @@ def test_bookkeeping_matches_reference_on_random_graphs():
             me.add_match(Edge(*key, 0.99))
             ref.add_match(RefEdge(*key, 0.99))
             assert set(ref.candidate_edges) == set(me.candidate_edges)
+
+
+def test_bulk_add_matches_equals_the_reference_class_fed_one_by_one():
+    """`add_matches` (candidate table, bulk) against the REFERENCE class receiving the same matches
+    through its own `add_match` one at a time: same dictionary (keys, stored spelling, weights,
+    order), same nb_poses — including reversed-key overwrites, equal weights and blacklisted pairs."""
+    sys.path.insert(0, REF)
+    try:
+        from cslam.algebraic_connectivity_maximization import (
+            AlgebraicConnectivityMaximization as RefACM, EdgeInterRobot as RefEdge)
+    finally:
+        sys.path.remove(REF)
+    from cslam_b200.algebraic_connectivity_maximization import AlgebraicConnectivityMaximization as ACM
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        R = int(rng.integers(2, 6))
+        ref, me = RefACM(robot_id=0, max_nb_robots=R), ACM(robot_id=0, max_nb_robots=R)
+        for rnd in range(3):
+            n = int(rng.integers(1, 120))
+            r0 = rng.integers(0, R, n)
+            r1 = (r0 + rng.integers(1, R, n)) % R
+            k0, k1 = rng.integers(0, 5, n), rng.integers(0, 5, n)
+            w = np.round(rng.random(n), 1)
+            for t in range(n):
+                ref.add_match(RefEdge(int(r0[t]), int(k0[t]), int(r1[t]), int(k1[t]), float(w[t])))
+            me.add_matches(r0, k0, r1, k1, w)
+            assert [(k, tuple(v)) for k, v in ref.candidate_edges.items()] == \
+                [(k, tuple(v)) for k, v in me.candidate_edges.items()], (trial, rnd)
+            assert ref.nb_poses == me.nb_poses
+            gone = list(ref.candidate_edges.values())[:3]
+            ref.remove_candidate_edges([RefEdge(*e) for e in gone])
+            me.remove_candidate_edges(list(me.candidate_edges.values())[:3])
+            assert set(ref.candidate_edges) == set(me.candidate_edges)
+            assert ref.already_considered_matches == me.already_considered_matches

@@ -120,3 +120,42 @@ def test_bulk_add_matches_equals_the_reference_class_fed_one_by_one():
             me.remove_candidate_edges(list(me.candidate_edges.values())[:3])
             assert set(ref.candidate_edges) == set(me.candidate_edges)
             assert ref.already_considered_matches == me.already_considered_matches
+
+
+def test_columnar_select_candidates_equals_the_reference_end_to_end(monkeypatch):
+    """Whole `select_candidates` of this package (candidate table, vectorised set-up) against the
+    REFERENCE `select_candidates` running its own MAC (scipy/networkx) on small multi-robot graphs.
+    The GPU solver is replaced by the oracle's restatement of MAC here (no GPU in the build
+    container); what is compared is everything around it: inclusion, offsets, rekeying, the greedy
+    start, recovery of the (robot, keyframe) edges and the removal of the selection, over
+    successive rounds."""
+    sys.path.insert(0, REF)
+    try:
+        from cslam.algebraic_connectivity_maximization import (
+            AlgebraicConnectivityMaximization as RefACM, EdgeInterRobot as RefEdge)
+    finally:
+        sys.path.remove(REF)
+    from cslam_b200.algebraic_connectivity_maximization import (
+        AlgebraicConnectivityMaximization as ACM, EdgeInterRobot as Edge)
+    from oracle.inputs import multi_robot_graph
+    from oracle.mac import MACOracle
+
+    def oracle_solver(self, fixed, candidates, w_init, budget):
+        assert isinstance(fixed, tuple) and isinstance(candidates, tuple)      # the columnar path
+        mac = MACOracle.from_arrays(fixed, candidates, self.total_nb_poses)
+        return mac.fw_subset(w_init, budget, max_iters=self.max_iters)[0]
+
+    monkeypatch.setattr(ACM, "run_mac_solver", oracle_solver)
+    for R, P, m, k, seed in ((3, 15, 40, 5, 0), (4, 12, 60, 6, 1)):
+        fixed, cand = multi_robot_graph(R, P, m, seed)
+        ref, me = RefACM(robot_id=0, max_nb_robots=R), ACM(robot_id=0, max_nb_robots=R)
+        ref.set_graph([RefEdge(*e) for e in fixed], [RefEdge(*e) for e in cand])
+        me.set_graph([Edge(*e) for e in fixed], [Edge(*e) for e in cand])
+        in_range = {r: True for r in range(R)}
+        for rnd in range(2):
+            a = ref.select_candidates(k, in_range, greedy_initialization=True)
+            b = me.select_candidates(k, in_range, greedy_initialization=True)
+            assert sorted(tuple(e)[:4] for e in a) == sorted(tuple(e)[:4] for e in b) and len(b) == k
+            assert set(ref.candidate_edges) == set(me.candidate_edges)
+            assert ref.already_considered_matches == me.already_considered_matches
+            assert ref.offsets == me.offsets and ref.total_nb_poses == me.total_nb_poses

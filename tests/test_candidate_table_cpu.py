@@ -159,3 +159,32 @@ def test_helpers_accept_both_forms():
     cols = (np.array([0, 1], np.int32), np.array([5, 9], np.int32), np.array([0.25, 0.5]))
     assert _count(cols) == 2 and list(_weights_of(cols)) == [0.25, 0.5]
     assert ACM().greedy_initialization(1, cols).tolist() == [0.0, 1.0]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_bulk_path_reproduces_the_reference_golden_sequences(seed):
+    """tests/golden/candidates.npz holds the REFERENCE class's candidate dictionary after seeded
+    rounds of add_match / remove_candidate_edges / candidate_edges_to_fixed
+    (oracle/make_golden_candidates.py); `add_matches` + the candidate table must land on the same
+    dictionary (keys, stored spelling, weights, ORDER), nb_poses, blacklist and fixed edges."""
+    import os
+    from oracle.make_golden_candidates import scenario
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "candidates.npz"))
+    R, rounds = scenario(seed)
+    acm = ACM(robot_id=0, max_nb_robots=R)
+
+    def snap():
+        return np.array([list(k) + list(v) for k, v in acm.candidate_edges.items()],
+                        dtype=np.float64).reshape(-1, 9)
+
+    for rnd, (m, n_remove, n_fix) in enumerate(rounds):
+        acm.add_matches(m[:, 0].astype(int), m[:, 1].astype(int), m[:, 2].astype(int), m[:, 3].astype(int), m[:, 4])
+        assert np.array_equal(snap(), gold[f"s{seed}_r{rnd}_after_add"])
+        assert [acm.nb_poses[r] for r in range(R)] == gold[f"s{seed}_r{rnd}_nb_poses"].tolist()
+        oldest = list(acm.candidate_edges.values())
+        acm.remove_candidate_edges(oldest[:n_remove])
+        acm.candidate_edges_to_fixed(list(oldest[n_remove:n_remove + n_fix]))
+        assert np.array_equal(snap(), gold[f"s{seed}_r{rnd}_after_edit"])
+        assert sorted(acm.already_considered_matches) == [tuple(r) for r in gold[f"s{seed}_r{rnd}_considered"].tolist()]
+        assert np.array_equal(np.array([list(e) for e in acm.fixed_edges], dtype=np.float64).reshape(-1, 5),
+                              gold[f"s{seed}_r{rnd}_fixed"])

@@ -651,6 +651,13 @@ struct cslam_nns {
   int sample_rows = 32768;
 
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
+  // Cross-stream ordering of everything that touches the pool or the search workspace: the
+  // last operation's stream and an event recorded behind it.  An operation on another stream
+  // first waits for that event (nns_enter), so appends, growth copies and searches issued on
+  // the caller's streams and on the handle's own stream execute in call order.
+  cudaEvent_t ev_order = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool has_order = false;
   int last_coarse_launches = 0;
   bool timing_valid = false;
 };
@@ -658,7 +665,24 @@ struct cslam_nns {
 namespace cslam {
 namespace {
 
-int nns_reserve_rows(cslam_nns* h, int64_t need) {
+// Make stream `s` wait for the handle's previous operation if that ran on another stream.
+int nns_enter(cslam_nns* h, cudaStream_t s) {
+  if (h->has_order && h->last_stream != s) CSLAM_CUDA(cudaStreamWaitEvent(s, h->ev_order, 0));
+  return CSLAM_OK;
+}
+
+// Mark the end of an operation issued on `s`.
+int nns_leave(cslam_nns* h, cudaStream_t s) {
+  CSLAM_CUDA(cudaEventRecord(h->ev_order, s));
+  h->last_stream = s;
+  h->has_order = true;
+  return CSLAM_OK;
+}
+
+// Growth copies run on the stream of the append that needs them (`s`, already ordered behind
+// the handle's previous operation by nns_enter), so rows appended earlier on that stream are
+// complete before they are moved.
+int nns_reserve_rows(cslam_nns* h, int64_t need, cudaStream_t s) {
   if (need <= h->cap) return CSLAM_OK;
   int64_t ncap = h->cap > 0 ? h->cap : 1024;
   while (ncap < need) ncap *= 2;
@@ -674,17 +698,17 @@ int nns_reserve_rows(cslam_nns* h, int64_t need) {
   CSLAM_TRY(dev_alloc(&ns, static_cast<size_t>(ncap) * h->dim_pad));
   CSLAM_TRY(dev_alloc(&nv, static_cast<size_t>(ncap)));
   CSLAM_CUDA(cudaMemsetAsync(ns, 0, static_cast<size_t>(ncap) * h->dim_pad * sizeof(__half),
-                             h->stream));
+                             s));
   if (h->n > 0) {
     CSLAM_CUDA(cudaMemcpyAsync(nd, h->d_data, static_cast<size_t>(h->n) * h->dim * sizeof(float),
-                               cudaMemcpyDeviceToDevice, h->stream));
+                               cudaMemcpyDeviceToDevice, s));
     CSLAM_CUDA(cudaMemcpyAsync(ns, h->d_shadow,
                                static_cast<size_t>(h->n) * h->dim_pad * sizeof(__half),
-                               cudaMemcpyDeviceToDevice, h->stream));
+                               cudaMemcpyDeviceToDevice, s));
     CSLAM_CUDA(cudaMemcpyAsync(nv, h->d_vv, static_cast<size_t>(h->n) * sizeof(float),
-                               cudaMemcpyDeviceToDevice, h->stream));
+                               cudaMemcpyDeviceToDevice, s));
   }
-  CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+  CSLAM_CUDA(cudaStreamSynchronize(s));
   dev_free(h->d_data);
   dev_free(h->d_shadow);
   dev_free(h->d_vv);
@@ -699,7 +723,7 @@ int nns_reserve_rows(cslam_nns* h, int64_t need) {
 
 int nns_append_device(cslam_nns* h, const float* d_rows, int64_t count, cudaStream_t s) {
   if (count <= 0) return CSLAM_OK;
-  CSLAM_TRY(nns_reserve_rows(h, h->n + count));
+  CSLAM_TRY(nns_reserve_rows(h, h->n + count, s));
   const int threads = 256;
   const int64_t blocks = (count * 32 + threads - 1) / threads;
   k_nns_append<<<static_cast<unsigned int>(blocks), threads, 0, s>>>(
@@ -711,12 +735,14 @@ int nns_append_device(cslam_nns* h, const float* d_rows, int64_t count, cudaStre
 
 int nns_flush(cslam_nns* h) {
   if (h->staged == 0) return CSLAM_OK;
+  CSLAM_TRY(nns_enter(h, h->stream));
   CSLAM_CUDA(cudaMemcpyAsync(h->d_stage, h->h_stage,
                              static_cast<size_t>(h->staged) * h->dim * sizeof(float),
                              cudaMemcpyHostToDevice, h->stream));
   CSLAM_TRY(nns_append_device(h, h->d_stage, h->staged, h->stream));
   // the pinned staging buffer is reused by the next add: wait for the copy
   CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+  CSLAM_TRY(nns_leave(h, h->stream));
   h->staged = 0;
   return CSLAM_OK;
 }
@@ -935,16 +961,19 @@ int nns_search_impl(cslam_nns* h, const void* d_queries, int dtype, int nq, int 
   }
   CSLAM_TRY(nns_flush(h));
   if (h->n == 0) {
+    CSLAM_TRY(nns_enter(h, s));
     const size_t tot = static_cast<size_t>(nq) * k;
     k_fill_empty<<<static_cast<unsigned int>((tot + 255) / 256), 256, 0, s>>>(d_out_idx,
                                                                              d_out_sims, tot);
     CSLAM_LAUNCH_CHECK();
+    CSLAM_TRY(nns_leave(h, s));
     if (out_info) {
       info[3] = g_launches.load() - launches0;
       memcpy(out_info, info, sizeof(info));
     }
     return CSLAM_OK;
   }
+  CSLAM_TRY(nns_enter(h, s));
   CSLAM_TRY(nns_reserve_queries(h, nq, k));
   const int nq_pad = (nq + kCoarseBM - 1) / kCoarseBM * kCoarseBM;
   if (dtype == CSLAM_DTYPE_F32) {
@@ -995,6 +1024,7 @@ int nns_search_impl(cslam_nns* h, const void* d_queries, int dtype, int nq, int 
     }
   }
   CSLAM_CUDA(cudaEventRecord(h->ev_t1, s));
+  CSLAM_TRY(nns_leave(h, s));
   h->timing_valid = true;
   info[3] = g_launches.load() - launches0;
   if (out_info) memcpy(out_info, info, sizeof(info));
@@ -1043,7 +1073,8 @@ int cslam_nns_create(int dim, int device, cslam_nns_t** out) {
     if (cudaMalloc(reinterpret_cast<void**>(&h->d_stage),
                    static_cast<size_t>(kStageRows) * dim * sizeof(float)) != cudaSuccess) { st = CSLAM_ERR_OOM; break; }
     if (cudaEventCreate(&h->ev_t0) != cudaSuccess || cudaEventCreate(&h->ev_t1) != cudaSuccess ||
-        cudaEventCreate(&h->ev_c0) != cudaSuccess || cudaEventCreate(&h->ev_c1) != cudaSuccess) { st = CSLAM_ERR_CUDA; break; }
+        cudaEventCreate(&h->ev_c0) != cudaSuccess || cudaEventCreate(&h->ev_c1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming) != cudaSuccess) { st = CSLAM_ERR_CUDA; break; }
   } while (0);
   if (st != CSLAM_OK) {
     set_error("nns_create: resource allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1058,6 +1089,7 @@ int cslam_nns_destroy(cslam_nns_t* h) {
   if (!h) return CSLAM_OK;
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->has_order) cudaEventSynchronize(h->ev_order);
   dev_free(h->d_data);
   dev_free(h->d_shadow);
   dev_free(h->d_vv);
@@ -1085,6 +1117,7 @@ int cslam_nns_destroy(cslam_nns_t* h) {
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
   if (h->ev_c0) cudaEventDestroy(h->ev_c0);
   if (h->ev_c1) cudaEventDestroy(h->ev_c1);
+  if (h->ev_order) cudaEventDestroy(h->ev_order);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return CSLAM_OK;
@@ -1117,8 +1150,11 @@ int cslam_nns_add_device(cslam_nns_t* h, const float* d_rows, int64_t count, voi
   CSLAM_REQUIRE(h && (d_rows || count == 0) && count >= 0, "nns_add_device: bad arguments");
   DeviceGuard g(h->device);
   CSLAM_TRY(nns_flush(h));
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
-  return nns_append_device(h, d_rows, count, s);
+  // NULL is CUDA's legacy default stream (torch's default stream), never a private one
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CSLAM_TRY(nns_enter(h, s));
+  CSLAM_TRY(nns_append_device(h, d_rows, count, s));
+  return nns_leave(h, s);
 }
 
 int64_t cslam_nns_size(cslam_nns_t* h) { return h ? h->n + h->staged : 0; }
@@ -1132,7 +1168,7 @@ int cslam_nns_read_rows(cslam_nns_t* h, int64_t start, int64_t count, float* out
                 static_cast<long long>(start), static_cast<long long>(start + count),
                 static_cast<long long>(h->n));
   if (count == 0) return CSLAM_OK;
-  CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->has_order) CSLAM_CUDA(cudaEventSynchronize(h->ev_order));
   CSLAM_CUDA(cudaMemcpy(out, h->d_data + start * h->dim,
                         static_cast<size_t>(count) * h->dim * sizeof(float),
                         cudaMemcpyDeviceToHost));
@@ -1145,7 +1181,7 @@ int cslam_nns_search_device(cslam_nns_t* h, const void* d_queries, int dtype, in
   CSLAM_REQUIRE(h && (nq == 0 || (d_queries && d_out_idx && d_out_sims)),
                 "nns_search_device: NULL argument");
   DeviceGuard g(h->device);
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);   // NULL = legacy default stream
   return nns_search_impl(h, d_queries, dtype, nq, k, d_out_idx, d_out_sims, s, out_info);
 }
 

@@ -16,9 +16,15 @@
  *     the ABI.
  *   - "host" variants take host pointers and perform the H2D / D2H copies
  *     themselves; "device" variants take device pointers valid on the
- *     handle's device and are asynchronous on the given stream
- *     (`stream` is a `cudaStream_t` passed as void*; NULL = the handle's own
- *     stream).
+ *     handle's device and are asynchronous on the given stream.  `stream`
+ *     is a `cudaStream_t` passed as void*; NULL is CUDA's legacy default
+ *     stream (which is what torch's default stream is), exactly as in the
+ *     CUDA runtime API — never a private stream of the library.  The inputs
+ *     must be ready in stream order on that stream; outputs are ready in
+ *     stream order on it.  Operations on one handle issued on different
+ *     streams (the caller's, or the handle's own stream that the "host"
+ *     variants use) execute in call order: every entry point makes its
+ *     stream wait for the handle's previous operation.
  *   - handles are not re-entrant (the reference is single-threaded:
  *     cslam/loop_closure_detection_node.py:106-110).
  *   - there is NO CPU fallback: without a CUDA device every compute call

@@ -117,7 +117,11 @@ def lists_match_modulo_ties(idx_a, idx_b, sims_full, tol=1e-6):
     the reference's own test, tests/test_sparse_matching.py:71-80)."""
     if len(idx_a) != len(idx_b):
         return False
+    sims_full = np.asarray(sims_full)
+    # a NaN / inf similarity compares False with everything and would let any list through
+    if not np.isfinite(sims_full).all():
+        return False
     for a, b in zip(idx_a, idx_b):
-        if a != b and abs(sims_full[a] - sims_full[b]) >= tol:
+        if a != b and not (abs(sims_full[a] - sims_full[b]) < tol):
             return False
     return True

@@ -56,6 +56,8 @@ SIGNATURES = {
     "cslam_mac_fiedler": (_i, [_vp, _vp, _P(_d), _vp, _P(_i)]),
     "cslam_mac_grad": (_i, [_vp, _vp, _vp]),
     "cslam_mac_fw_subset": (_i, [_vp, _vp, _i, _i, _d, _vp, _vp, _P(_d), _P(_i), _vp, _vp]),
+    "cslam_mac_fw_subset_sparse": (_i, [_vp, _i64, _vp, _vp, _i, _i, _d, _vp, _i64, _vp, _vp, _P(_i64),
+                                        _P(_d), _P(_i), _vp, _vp]),
     "cslam_mac_stats": (_i, [_vp, _P(_i64), _P(_i64), _P(_i)]),
     "cslam_mac_solver_timing": (_i, [_vp, _P(_d), _P(_i64), _P(_i64), _P(_i64)]),
     "cslam_debug_rayleigh_ritz": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _P(_i), _vp]),

@@ -25,11 +25,12 @@ edge-by-edge methods of the reference API remain and are used whenever `candidat
 replaced by a plain dict.
 """
 import bisect
+import logging
 from typing import NamedTuple
 
 import numpy as np
 
-from ._lib import CslamError
+from ._lib import CslamError, SingularLaplacianError
 from .candidate_table import CandidateTable
 from .mac.mac import MAC
 from .mac.utils import Edge
@@ -54,7 +55,10 @@ class EdgeInterRobot(NamedTuple):
     def __ne__(self, other):
         return not self == other
 
-    __hash__ = tuple.__hash__
+    def __hash__(self):
+        # hashes what __eq__ compares (the reference defines __eq__ only, which makes its class
+        # unhashable; here edges can live in sets/dicts without duplicating equal edges)
+        return hash(self._ends())
 
 
 def _largest(values, count):
@@ -118,6 +122,7 @@ class AlgebraicConnectivityMaximization(object):
         self.log_mac_edges = []
         self.last_mac = None        # solver object of the last run (stats / traces)
         self.last_mac_trials = 0    # re-initialisations the last run needed
+        self.last_mac_error = None  # non-singular solver failure of the last run, if any
 
     # ------------------------------------------------------------------ small helpers
     def edge_key(self, edge):
@@ -416,15 +421,25 @@ class AlgebraicConnectivityMaximization(object):
         (disconnected graph) re-draws the start with one more random pick each time, at most
         `nb_candidates_to_choose` times, then the start vector itself is the answer."""
         mac = self.last_mac = MAC(fixed_edges, candidate_edges, self.total_nb_poses)
+        self.last_mac_error = None
         answer = w_init.copy()
         for trial in range(nb_candidates_to_choose):
             try:
                 answer = mac.fw_subset(w_init, nb_candidates_to_choose, max_iters=self.max_iters)[0]
                 self.last_mac_trials = trial
                 return answer
-            except CslamError:    # the reference swallows SuperLU's "Factor is exactly singular"
+            except SingularLaplacianError:
+                # the reference swallows SuperLU's "Factor is exactly singular" (disconnected graph)
                 w_init = self.pseudo_greedy_initialization(nb_candidates_to_choose, trial + 1,
                                                            candidate_edges)
+            except CslamError as err:
+                # anything else (CUDA failure, out of memory, eigen-solver not converging) is not
+                # a property of the start vector: no retries, keep the greedy start, say why
+                self.last_mac_error = str(err)
+                logging.getLogger("cslam_b200.acm").warning(
+                    "MAC solver failed (%s); falling back to the greedy selection", err)
+                self.last_mac_trials = trial
+                return answer
         self.last_mac_trials = nb_candidates_to_choose
         return answer
 

@@ -64,14 +64,151 @@ struct Adj {
   size_t cap_nnz = 0;
 };
 
-__global__ void k_lap_fill(int64_t nnz, const int* __restrict__ src, const double* __restrict__ w,
-                           const double* __restrict__ cw, double tol, double* __restrict__ vals) {
-  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= nnz) return;
-  const int e = src[p];
-  const double we = w[e];
-  // combined_laplacian (mac.py:72-74): only w > tol contributes, with weight w_e * c_e
-  vals[p] = we > tol ? -__dmul_rn(we, cw[e]) : 0.0;
+// ---- support of w and its adjacency, maintained on the device --------------------------------
+// (reference: combined_laplacian rebuilds a COO->CSR matrix from Python lists in every
+//  Frank-Wolfe iteration, cslam/mac/mac.py:61-77, cslam/mac/utils.py:86-126)
+// sup[0 .. *cnt) = candidate ids with w != 0 (any order), flag[e] = 1 for those.
+
+// forget the current support (alpha = 1 makes w exactly s_i, mac.py:229-230)
+__global__ void k_sup_clear(const int* __restrict__ sup, int* cnt, unsigned char* __restrict__ flag) {
+  const int c = *cnt;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c; t += gridDim.x * blockDim.x)
+    flag[sup[t]] = 0;
+}
+
+__global__ void k_set_int(int* p, int v) { *p = v; }
+
+// append the entries of list[0..k) that are not in the support yet (entries are distinct)
+__global__ void k_sup_append(int k, const int* __restrict__ list, unsigned char* __restrict__ flag,
+                             int* __restrict__ sup, int* cnt) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= k) return;
+  const int e = list[t];
+  if (!flag[e]) {
+    flag[e] = 1;
+    sup[atomicAdd(cnt, 1)] = e;
+  }
+}
+
+// w[idx[t]] = val[t] (sparse start vector; entries distinct)
+__global__ void k_w_scatter(int n0, const int* __restrict__ idx, const double* __restrict__ val,
+                            double* __restrict__ w) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n0) w[idx[t]] = val[t];
+}
+
+// out[t] = w[sup[t]]
+__global__ void k_w_gather(const int* __restrict__ sup, const int* cnt, const double* __restrict__ w,
+                           double* __restrict__ out) {
+  const int c = *cnt;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c; t += gridDim.x * blockDim.x)
+    out[t] = w[sup[t]];
+}
+
+// degree of every vertex in the support graph (self loops cancel in a Laplacian)
+__global__ void k_act_count(const int* __restrict__ sup, const int* cnt, const int* __restrict__ ci,
+                            const int* __restrict__ cj, int* __restrict__ deg) {
+  const int c = *cnt;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c; t += gridDim.x * blockDim.x) {
+    const int e = sup[t];
+    const int i = ci[e], j = cj[e];
+    if (i == j) continue;
+    atomicAdd(&deg[i], 1);
+    atomicAdd(&deg[j], 1);
+  }
+}
+
+// indptr = exclusive scan of deg, deg is zeroed for reuse as the per-row fill cursor.  One block
+// walks the array in coalesced tiles of 1024 x 4 entries with a running carry (n is a few 100 k:
+// ~25 tiles; a grid-wide scan would cost more in launches than this does in time).
+__global__ void __launch_bounds__(1024) k_act_scan(int n, int* __restrict__ deg, int* __restrict__ indptr) {
+  __shared__ int sh_warp[32];
+  __shared__ int sh_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) sh_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 4096) {
+    const int r = base + 4 * tid;
+    int d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) d[u] = (r + u < n) ? deg[r + u] : 0;
+    const int tsum = d[0] + d[1] + d[2] + d[3];
+    int inc = tsum;                                  // inclusive scan across the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) sh_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int wv = sh_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, wv, o);
+        if (lane >= o) wv += v;
+      }
+      sh_warp[lane] = wv;                            // inclusive over warps
+    }
+    __syncthreads();
+    const int carry = sh_carry;
+    int run = carry + (warp > 0 ? sh_warp[warp - 1] : 0) + inc - tsum;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r + u < n) {
+        indptr[r + u] = run;
+        deg[r + u] = 0;
+        run += d[u];
+      }
+    __syncthreads();
+    if (tid == 1023) sh_carry = carry + sh_warp[31];
+    __syncthreads();
+  }
+  if (tid == 0) indptr[n] = sh_carry;
+}
+
+__global__ void k_act_fill(const int* __restrict__ sup, const int* cnt, const int* __restrict__ ci,
+                           const int* __restrict__ cj, const int* __restrict__ indptr,
+                           int* __restrict__ cursor, int* __restrict__ cols, int* __restrict__ src) {
+  const int c = *cnt;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c; t += gridDim.x * blockDim.x) {
+    const int e = sup[t];
+    const int i = ci[e], j = cj[e];
+    if (i == j) continue;
+    int p = indptr[i] + atomicAdd(&cursor[i], 1);
+    cols[p] = j;
+    src[p] = e;
+    p = indptr[j] + atomicAdd(&cursor[j], 1);
+    cols[p] = i;
+    src[p] = e;
+  }
+}
+
+// The atomic cursors leave the entries of a row in arbitrary order: sort every row by candidate
+// id (rows hold a handful of entries) so that the matrix - and with it the summation order of
+// the SpMM - is the same in every run, then fill in the Laplacian values (k_lap_fill's rule).
+__global__ void k_act_finish(int n, const int* __restrict__ indptr, int* __restrict__ cols,
+                             int* __restrict__ src, const double* __restrict__ w,
+                             const double* __restrict__ cw, double tol, double* __restrict__ vals) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int p0 = indptr[r], p1 = indptr[r + 1];
+  for (int p = p0 + 1; p < p1; ++p) {
+    const int e = src[p], c = cols[p];
+    int q = p - 1;
+    while (q >= p0 && src[q] > e) {
+      src[q + 1] = src[q];
+      cols[q + 1] = cols[q];
+      --q;
+    }
+    src[q + 1] = e;
+    cols[q + 1] = c;
+  }
+  for (int p = p0; p < p1; ++p) {
+    const int e = src[p];
+    const double we = w[e];
+    vals[p] = we > tol ? -__dmul_rn(we, cw[e]) : 0.0;
+  }
 }
 
 // diag[r] = -(sum of row r), sup[r] = L[r][r+1], rowabs[r] = |diag| + sum |offdiag|
@@ -1472,6 +1609,203 @@ __device__ __noinline__ bool rr_warp_elem(int s, int m, const double* GA, const 
   return true;
 }
 
+// ------------------------------------------------------------------ two-stage Rayleigh-Ritz
+// A cheaper small eigen-solve for the persistent solver (rr_impl = 2).  Instead of the full
+// (3m x 3m) problem on span[X W P] it solves, per column c, the 3 x 3 problem on
+// span{x_c, w_c, p_c} (one lane per column, everything in registers, serial cyclic Jacobi: 3
+// rotations a sweep) and then the m x m problem on the m resulting vectors, which restores the
+// mixing of the columns that keeps the second Ritz vector tracking the eigenvector across
+// Frank-Wolfe steps.  This is a Rayleigh-Ritz step on a SUBSET of the trial space, so every
+// iterate is still a legitimate LOBPCG iterate (theta is the exact Rayleigh quotient of the
+// returned vectors, convergence is to the same pair, the stopping test is unchanged); it needs
+// ~8 % more iterations on the C5 selection (tools/lobpcg_study.py --rr two-stage: 1124 vs 1043,
+// identical selections) for a solve that is ~4x shorter than the 6 x 6 one.
+// Basis order as everywhere: column index b * m + c (b = 0 X, 1 W, 2 P).  Warp 0 calls it.
+__device__ __forceinline__ void jrot3(double& app, double& aqq, double& apq, double& arp, double& arq,
+                                      double (&v)[3][3], int p, int q, double tol2) {
+  if (!(apq * apq > tol2 * fabs(app * aqq) && fabs(apq) > 1e-150)) return;
+  double c, sn;
+  jacobi_angle_fast(app, aqq, apq, c, sn);
+  if (sn == 0.0) return;
+  // exact update of the 2 x 2 block with the rounded (c, sn): keeps T symmetric and the rotation
+  // orthogonal to working precision; the remaining off-diagonal entry is left for the next sweep
+  const double npp = c * (c * app - sn * apq) - sn * (c * apq - sn * aqq);
+  const double nqq = sn * (sn * app + c * apq) + c * (sn * apq + c * aqq);
+  const double npq = c * (sn * app + c * apq) - sn * (sn * apq + c * aqq);
+  app = npp; aqq = nqq; apq = npq;
+  const double rp = arp, rq = arq;
+  arp = c * rp - sn * rq;
+  arq = sn * rp + c * rq;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double kp = v[k][p], kq = v[k][q];
+    v[k][p] = c * kp - sn * kq;
+    v[k][q] = sn * kp + c * kq;
+  }
+}
+
+// lowest pair of A y = th B y for the leading nb x nb blocks (1 <= nb <= 3) of symmetric A, B;
+// y is B-normalised.  false: B numerically singular.
+__device__ __forceinline__ bool geig3_lowest(int nb, const double (&Ain)[3][3], const double (&Bin)[3][3],
+                                             int max_sweeps, double tol2, double (&y)[3], double& th) {
+  double ds[3], A[3][3], B[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double d = i < nb ? Bin[i][i] : 1.0;
+    if (!(d > 0.0) || !isfinite(d)) return false;
+    ds[i] = rsqrt(d);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const bool in = i < nb && j < nb;
+      A[i][j] = in ? Ain[i][j] * ds[i] * ds[j] : (i == j ? 1e150 : 0.0);
+      B[i][j] = in ? Bin[i][j] * ds[i] * ds[j] : (i == j ? 1.0 : 0.0);
+    }
+  // Cholesky B = L L^T (unit diagonal after scaling), Li = 1 / L_ii
+  const double l10 = B[1][0], l20 = B[2][0];
+  const double d1 = B[1][1] - l10 * l10;
+  if (!(d1 > 1e-14)) return false;
+  const double i1 = rsqrt(d1);
+  const double l21 = (B[2][1] - l20 * l10) * i1;
+  const double d2 = B[2][2] - l20 * l20 - l21 * l21;
+  if (!(d2 > 1e-14)) return false;
+  const double i2 = rsqrt(d2);
+  // Y = L^-1 A (rows), T = Y L^-T (columns)
+  double Y[3][3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    Y[0][j] = A[0][j];
+    Y[1][j] = (A[1][j] - l10 * Y[0][j]) * i1;
+    Y[2][j] = (A[2][j] - l20 * Y[0][j] - l21 * Y[1][j]) * i2;
+  }
+  double T[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    T[i][0] = Y[i][0];
+    T[i][1] = (Y[i][1] - T[i][0] * l10) * i1;
+    T[i][2] = (Y[i][2] - T[i][0] * l20 - T[i][1] * l21) * i2;
+  }
+  double t00 = T[0][0], t11 = T[1][1], t22 = T[2][2];
+  double t01 = 0.5 * (T[0][1] + T[1][0]), t02 = 0.5 * (T[0][2] + T[2][0]), t12 = 0.5 * (T[1][2] + T[2][1]);
+  double v[3][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}};
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    const bool big = (t01 * t01 > tol2 * fabs(t00 * t11) && fabs(t01) > 1e-150) ||
+                     (t02 * t02 > tol2 * fabs(t00 * t22) && fabs(t02) > 1e-150) ||
+                     (t12 * t12 > tol2 * fabs(t11 * t22) && fabs(t12) > 1e-150);
+    if (!big) break;
+    jrot3(t00, t11, t01, t02, t12, v, 0, 1, tol2);   // (p, q) = (0, 1), third index 2: a_2p = t02, a_2q = t12
+    jrot3(t00, t22, t02, t01, t12, v, 0, 2, tol2);   // (0, 2), third index 1: a_1p = t01, a_1q = t12
+    jrot3(t11, t22, t12, t01, t02, v, 1, 2, tol2);   // (1, 2), third index 0: a_0p = t01, a_0q = t02
+  }
+  int col = 0;
+  double best = t00;
+  if (t11 < best) { best = t11; col = 1; }
+  if (t22 < best) { best = t22; col = 2; }
+  th = best;
+  const double z0 = col == 0 ? v[0][0] : (col == 1 ? v[0][1] : v[0][2]);
+  const double z1 = col == 0 ? v[1][0] : (col == 1 ? v[1][1] : v[1][2]);
+  const double z2 = col == 0 ? v[2][0] : (col == 1 ? v[2][1] : v[2][2]);
+  // y = diag(ds) L^-T z
+  const double y2 = z2 * i2;
+  const double y1 = (z1 - l21 * y2) * i1;
+  const double y0 = z0 - l10 * y1 - l20 * y2;
+  y[0] = y0 * ds[0];
+  y[1] = nb > 1 ? y1 * ds[1] : 0.0;
+  y[2] = nb > 2 ? y2 * ds[2] : 0.0;
+  return true;
+}
+
+__device__ __noinline__ bool rr_two_stage(int s, int m, const double* GA, const double* GB,
+                                          double (*C)[MAXM], double* theta, int max_sweeps, double tol2) {
+  static_assert(MAXM == 2 && MAXS == 6, "rr_two_stage is written for blocks of at most 2 vectors");
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int c = lane < m ? lane : 0;
+  const int nb = s / m;                      // 1 (X), 2 (X W) or 3 (X W P)
+  auto ga = [&](int i, int j) { return 0.5 * (GA[i * MAXS + j] + GA[j * MAXS + i]); };
+  auto gb = [&](int i, int j) { return 0.5 * (GB[i * MAXS + j] + GB[j * MAXS + i]); };
+  // ---- stage 1: lane c solves span{x_c, w_c, p_c}
+  double A3[3][3], B3[3][3], y[3], th = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const bool in = i < nb && j < nb;
+      A3[i][j] = in ? ga(i * m + c, j * m + c) : 0.0;
+      B3[i][j] = in ? gb(i * m + c, j * m + c) : 0.0;
+    }
+  const bool ok1 = geig3_lowest(nb, A3, B3, max_sweeps, tol2, y, th);
+  if (__any_sync(full, lane < m && !ok1)) return false;
+  if (m == 1) {
+    if (lane == 0) {
+#pragma unroll
+      for (int a2 = 0; a2 < MAXS; ++a2) C[a2][0] = 0.0;
+#pragma unroll
+      for (int b2 = 0; b2 < 3; ++b2)
+        if (b2 < nb) C[b2][0] = y[b2];
+      theta[0] = th;
+    }
+    __syncwarp();
+    return true;
+  }
+  // ---- stage 2: 2 x 2 problem on the two stage-1 vectors u_c = sum_b y_c[b] S[b * 2 + c]
+  double yo[3];                              // the other column's coefficients
+#pragma unroll
+  for (int b2 = 0; b2 < 3; ++b2) yo[b2] = __shfl_xor_sync(full, y[b2], 1);
+  const double tho = __shfl_xor_sync(full, th, 1);
+  bool ok2 = true;
+  if (lane == 0) {
+    // u_0^T G u_1 over the cross block (rows b*2, columns b'*2 + 1); u_c^T A u_c = th_c, u_c^T B u_c = 1
+    double a01 = 0.0, b01 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (i < nb && j < nb) {
+          a01 = fma(y[i] * yo[j], ga(i * 2, j * 2 + 1), a01);
+          b01 = fma(y[i] * yo[j], gb(i * 2, j * 2 + 1), b01);
+        }
+    // B2 = [[1, b01], [b01, 1]] = L L^T with L = [[1, 0], [b01, r]], r = sqrt(1 - b01^2)
+    const double r2 = 1.0 - b01 * b01;
+    ok2 = r2 > 1e-14;
+    if (ok2) {
+      const double ir = rsqrt(r2);
+      // T = L^-1 A2 L^-T, A2 = [[th0, a01], [a01, th1]]
+      double t00 = th, t01 = (a01 - b01 * th) * ir;
+      double t11 = (tho - 2.0 * b01 * a01 + b01 * b01 * th) * ir * ir;
+      double cs = 1.0, sn = 0.0;
+      jacobi_angle_fast(t00, t11, t01, cs, sn);
+      // eigenvalues of the 2 x 2 block with the rounded rotation (exact Rayleigh quotients)
+      const double e0 = cs * (cs * t00 - sn * t01) - sn * (cs * t01 - sn * t11);
+      const double e1 = sn * (sn * t00 + cs * t01) + cs * (sn * t01 + cs * t11);
+      // eigenvector columns of V = [[cs, sn], [-sn, cs]]; Y2 = L^-T V
+      double v00 = cs, v10 = -sn, v01 = sn, v11 = cs;
+      if (e1 < e0) {   // ascending order
+        const double t0 = v00, t1 = v10;
+        v00 = v01; v10 = v11; v01 = t0; v11 = t1;
+      }
+      const double y10 = v10 * ir, y11 = v11 * ir;          // second row of L^-T V
+      const double y00 = v00 - b01 * y10, y01 = v01 - b01 * y11;
+      theta[0] = fmin(e0, e1);
+      theta[1] = fmax(e0, e1);
+      // C[a][c'] = sum_c Y6[a][c] Y2[c][c'],  Y6[b*2 + c][c] = y_c[b]
+#pragma unroll
+      for (int b2 = 0; b2 < 3; ++b2) {
+        const bool in = b2 < nb;
+        C[b2 * 2 + 0][0] = in ? y[b2] * y00 : 0.0;
+        C[b2 * 2 + 0][1] = in ? y[b2] * y01 : 0.0;
+        C[b2 * 2 + 1][0] = in ? yo[b2] * y10 : 0.0;
+        C[b2 * 2 + 1][1] = in ? yo[b2] * y11 : 0.0;
+      }
+    }
+  }
+  ok2 = __shfl_sync(full, ok2 ? 1 : 0, 0) != 0;
+  __syncwarp();
+  return ok2;
+}
+
 // Test hook: one warp solves one small problem with one of the implementations, `reps` times,
 // and reports the cycles per solve (total and per section).
 __global__ void k_rr_debug(const double* GA, const double* GB, int s, int m, int impl, int sweeps,
@@ -1498,8 +1832,9 @@ __global__ void k_rr_debug(const double* GA, const double* GB, int s, int m, int
   bool ok = true;
   const long long t0 = clock64();
   for (int rep = 0; rep < reps; ++rep) {
-    ok = impl ? rr_warp_elem(s, m, sGA, sGB, sC, sth, sweeps, tol2, stab, sprof)
-              : rr_warp(S, s, m, sGA, sGB, sC, sth, sweeps, tol2, sprof);
+    ok = impl == 2 ? rr_two_stage(s, m, sGA, sGB, sC, sth, sweeps, tol2)
+         : impl  ? rr_warp_elem(s, m, sGA, sGB, sC, sth, sweeps, tol2, stab, sprof)
+                 : rr_warp(S, s, m, sGA, sGB, sC, sth, sweeps, tol2, sprof);
     __syncwarp();
   }
   const long long t1 = clock64();
@@ -1566,7 +1901,8 @@ struct PersistArgs {
   double *fA, *fB, *bA, *bB;       // [grid], [MAXM][grid] CTA aggregates of the two scans
   double *pres, *pcs, *pgram;      // [MAXM][grid], [MAXM][grid], [2*NPAIR][grid] partial sums
   double theta0[MAXM];
-  double tol, lnorm;
+  double tol;
+  const double* lnorm;   // ||L||_inf, device resident (written by prepare_matrix on the same stream)
   int max_iters, have_p;
   int init;              // 1: X in global memory is a raw start block: centre it, form AX = L X and
                          //    Rayleigh-Ritz it inside the kernel before the first iteration
@@ -1603,6 +1939,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     s_rrtab[5 * 32 + e] = g_rr_tab_b[e / 32][e % 32];
   }
   unsigned int epoch = 0;
+  const double lnorm_v = __ldg(a.lnorm);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x, nb_grid = gridDim.x;
@@ -1860,7 +2197,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     tick(6);
     // ---- phase 2: convergence test, exact forward walk, backward aggregates ----------------
     grid_sum2(a.pres, s_res);
-    res_out = s_res[0] / a.lnorm;
+    res_out = s_res[0] / lnorm_v;
     if (res_out < a.tol) { status = 0; break; }
     cta_prefix(a.fA, a.fB, false);
     double y[MAXM];
@@ -2097,6 +2434,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       int use = sdim;
       long long* rrp = (a.prof && b == 0) ? rrprof_acc : nullptr;
       auto solve = [&](int dim, long long* prof_to) {
+        if (a.rr_impl == 2) return rr_two_stage(dim, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps, a.rr_tol2);
         return a.rr_impl ? rr_warp_elem(dim, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps, a.rr_tol2, s_rrtab, prof_to)
                          : rr_warp(s_rr, dim, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps, a.rr_tol2, prof_to);
       };
@@ -2209,6 +2547,8 @@ struct FiedlerSolver {
   double *part = nullptr, *red = nullptr;  // reduction scratch / results
   double* h_red = nullptr;                 // pinned
   int* d_bad = nullptr;
+  double* d_lnorm = nullptr;   // ||L||_inf of the current matrix (device)
+  int* h_bad = nullptr;        // pinned copy of d_bad
   int T = 0;       // chunks
   int nblk = 0;    // 256-thread blocks over n
   int nblk_t = 0;  // 256-thread blocks over T
@@ -2228,6 +2568,7 @@ struct FiedlerSolver {
   long long* pprof = nullptr; // cycle counters (CSLAM_LOBPCG_PROF=1)
   bool warm = false;
   double lnorm = 0.0;
+  const int* extra_d2h_src = nullptr;   // optional device int copied to h_bad[1] with every solve result
   int last_iters = 0;
   bool jacobi = false;
   int64_t spmv_count = 0;
@@ -2268,6 +2609,8 @@ struct FiedlerSolver {
     CSLAM_TRY(dev_alloc(&red, 2 * NPAIR + 4 * MAXM + 4));
     CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_red), (2 * NPAIR + 4 * MAXM + 4) * sizeof(double)));
     CSLAM_TRY(dev_alloc(&d_bad, 1));
+    CSLAM_TRY(dev_alloc(&d_lnorm, 1));
+    CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_bad), 4 * sizeof(int)));
     int coop = 0;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
@@ -2323,7 +2666,7 @@ struct FiedlerSolver {
     pa.pres = ppres; pa.pcs = ppcs; pa.pgram = ppgram;
     for (int c = 0; c < MAXM; ++c) pa.theta0[c] = theta[c];
     pa.tol = tol;
-    pa.lnorm = lnorm;
+    pa.lnorm = d_lnorm;
     pa.max_iters = max_iters;
     pa.have_p = have_p ? 1 : 0;
     pa.init = init ? 1 : 0;
@@ -2341,7 +2684,7 @@ struct FiedlerSolver {
     }
     pa.cap0 = pa.cap1 = 6144;
     pa.rr_impl = getenv("CSLAM_RR_IMPL") ? atoi(getenv("CSLAM_RR_IMPL")) : 1;
-    pa.rr_sweeps = getenv("CSLAM_RR_SWEEPS") ? atoi(getenv("CSLAM_RR_SWEEPS")) : 3;
+    pa.rr_sweeps = getenv("CSLAM_RR_SWEEPS") ? atoi(getenv("CSLAM_RR_SWEEPS")) : (pa.rr_impl == 2 ? 4 : 3);
     pa.rr_tol2 = getenv("CSLAM_RR_TOL2") ? atof(getenv("CSLAM_RR_TOL2")) : 1e-32;
     const size_t dyn = static_cast<size_t>(pa.cap0 + pa.cap1) * (sizeof(double) + sizeof(int)) +
                        static_cast<size_t>(MAXM) * pa.rpb * sizeof(double);
@@ -2364,7 +2707,12 @@ struct FiedlerSolver {
     CSLAM_CUDA(cudaEventRecord(pev1, stream));
     count_launch();
     CSLAM_CUDA(cudaMemcpyAsync(h_red, pout, (MAXM + 3) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(h_red + MAXM + 3, d_lnorm, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (extra_d2h_src)   // a caller's scalar riding on this synchronisation (support size)
+      CSLAM_CUDA(cudaMemcpyAsync(h_bad + 1, extra_d2h_src, sizeof(int), cudaMemcpyDeviceToHost, stream));
     CSLAM_CUDA(cudaStreamSynchronize(stream));
+    lnorm = h_red[MAXM + 3];
     for (int c = 0; c < MAXM; ++c) theta[c] = h_red[c];
     *iters = static_cast<int>(h_red[MAXM]);
     *status = static_cast<int>(h_red[MAXM + 1]);
@@ -2404,6 +2752,9 @@ struct FiedlerSolver {
     pev0 = pev1 = nullptr;
     dev_free(fagg);
     dev_free(d_bad);
+    dev_free(d_lnorm);
+    if (h_bad) cudaFreeHost(h_bad);
+    h_bad = nullptr;
     if (h_red) cudaFreeHost(h_red);
     h_red = nullptr;
     for (Adj* a : {&fix, &act}) {
@@ -2443,31 +2794,6 @@ struct FiedlerSolver {
     return CSLAM_OK;
   }
 
-  // same from caller-owned PINNED arrays, without synchronising (the caller keeps them intact
-  // until the stream has been synchronised)
-  int upload_async(Adj& a, const int* indptr, const int* cols, const int* src, size_t nnz) {
-    if (!a.indptr) CSLAM_TRY(dev_alloc(&a.indptr, static_cast<size_t>(n) + 1));
-    if (nnz > a.cap_nnz) {
-      CSLAM_CUDA(cudaStreamSynchronize(stream));
-      dev_free(a.cols);
-      dev_free(a.src);
-      dev_free(a.vals);
-      const size_t cap = std::max<size_t>(nnz * 2, 1024);
-      CSLAM_TRY(dev_alloc(&a.cols, cap));
-      CSLAM_TRY(dev_alloc(&a.src, cap));
-      CSLAM_TRY(dev_alloc(&a.vals, cap));
-      a.cap_nnz = cap;
-    }
-    a.nnz = static_cast<int64_t>(nnz);
-    CSLAM_CUDA(cudaMemcpyAsync(a.indptr, indptr, (static_cast<size_t>(n) + 1) * sizeof(int),
-                               cudaMemcpyHostToDevice, stream));
-    if (nnz) {
-      CSLAM_CUDA(cudaMemcpyAsync(a.cols, cols, nnz * sizeof(int), cudaMemcpyHostToDevice, stream));
-      CSLAM_CUDA(cudaMemcpyAsync(a.src, src, nnz * sizeof(int), cudaMemcpyHostToDevice, stream));
-    }
-    return CSLAM_OK;
-  }
-
   int spmm(double* x, double* y, const double* colsum) {
     const int G = 4;
     const int blocks = (static_cast<int64_t>(n) * G + 255) / 256;
@@ -2479,14 +2805,17 @@ struct FiedlerSolver {
     return CSLAM_OK;
   }
 
-  // diag / tridiagonal factors / ||L||_inf for the current values
-  int prepare_matrix() {
+  // diag / tridiagonal factors / ||L||_inf for the current values.  Everything stays on the
+  // device (d_lnorm, d_bad); with `sync_host` the two scalars are read back and a tridiagonal
+  // part that is not positive definite is replaced by the diagonal here, otherwise the caller
+  // checks `h_bad` at its next synchronisation (persist_loop) and re-runs.
+  int prepare_matrix(bool sync_host) {
     k_lap_diag<<<nblk, 256, 0, stream>>>(n, fix.indptr, fix.cols, fix.vals,
                                          has_act ? act.indptr : nullptr, act.cols, act.vals, diag,
                                          sup, rowabs);
     CSLAM_LAUNCH_CHECK();
-    CSLAM_CUDA(cudaMemsetAsync(red, 0, sizeof(double), stream));
-    k_max_reduce<<<std::min(64, (n + 2047) / 2048), 256, 0, stream>>>(rowabs, n, red);
+    CSLAM_CUDA(cudaMemsetAsync(d_lnorm, 0, sizeof(double), stream));
+    k_max_reduce<<<std::min(64, (n + 2047) / 2048), 256, 0, stream>>>(rowabs, n, d_lnorm);
     CSLAM_LAUNCH_CHECK();
     CSLAM_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), stream));
     const int Tf = (n + FCH - 1) / FCH;
@@ -2497,19 +2826,23 @@ struct FiedlerSolver {
     CSLAM_LAUNCH_CHECK();
     k_fac_c<<<nblk_f, 256, 0, stream>>>(n, diag, sup, fagg, dpiv, lfac, d_bad);
     CSLAM_LAUNCH_CHECK();
-    int bad = 0;
-    CSLAM_CUDA(cudaMemcpyAsync(h_red, red, sizeof(double), cudaMemcpyDeviceToHost, stream));
-    CSLAM_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    jacobi = false;
+    if (!sync_host) return CSLAM_OK;
+    CSLAM_CUDA(cudaMemcpyAsync(h_red, d_lnorm, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CSLAM_CUDA(cudaMemcpyAsync(h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
     CSLAM_CUDA(cudaStreamSynchronize(stream));
     lnorm = h_red[0];
-    jacobi = bad != 0;
-    if (jacobi) {
-      // tridiagonal part not positive definite (can only happen for exotic weights): fall
-      // back to the diagonal preconditioner, i.e. l = 0, d = diag
-      CSLAM_CUDA(cudaMemcpyAsync(dpiv, diag, static_cast<size_t>(n) * sizeof(double),
-                                 cudaMemcpyDeviceToDevice, stream));
-      CSLAM_CUDA(cudaMemsetAsync(lfac, 0, (static_cast<size_t>(n) + 1) * sizeof(double), stream));
-    }
+    if (h_bad[0] != 0) CSLAM_TRY(use_diagonal_preconditioner());
+    return CSLAM_OK;
+  }
+
+  // tridiagonal part not positive definite (can only happen for exotic weights): fall back to
+  // the diagonal preconditioner, i.e. l = 0, d = diag
+  int use_diagonal_preconditioner() {
+    jacobi = true;
+    CSLAM_CUDA(cudaMemcpyAsync(dpiv, diag, static_cast<size_t>(n) * sizeof(double),
+                               cudaMemcpyDeviceToDevice, stream));
+    CSLAM_CUDA(cudaMemsetAsync(lfac, 0, (static_cast<size_t>(n) + 1) * sizeof(double), stream));
     return CSLAM_OK;
   }
 
@@ -2594,6 +2927,28 @@ struct FiedlerSolver {
     return CSLAM_OK;
   }
 
+  // Cold start block: same spirit as the reference's X0 = RandomState(7).normal (mac.py:58); any
+  // start converges to the same pair, the seed only fixes the iteration path.  The block depends
+  // only on (n, m, ld): drawn once per handle (200 k normal deviates cost ~3 ms of host time)
+  // and kept on the device.
+  int load_start_block() {
+    if (x0_n != n || x0_m != m || x0_ld != ld || !x0_dev) {
+      std::mt19937_64 gen(7);
+      std::normal_distribution<double> nd(0.0, 1.0);
+      std::vector<double> x0(static_cast<size_t>(MAXM) * ld, 0.0);
+      for (int c = 0; c < m; ++c)
+        for (int i = 0; i < n; ++i) x0[static_cast<size_t>(c) * ld + i] = nd(gen);
+      dev_free(x0_dev);
+      CSLAM_TRY(dev_alloc(&x0_dev, x0.size()));
+      CSLAM_CUDA(cudaMemcpyAsync(x0_dev, x0.data(), x0.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+      CSLAM_CUDA(cudaStreamSynchronize(stream));
+      x0_n = n; x0_m = m; x0_ld = ld;
+    }
+    CSLAM_CUDA(cudaMemcpyAsync(X, x0_dev, static_cast<size_t>(MAXM) * ld * sizeof(double),
+                               cudaMemcpyDeviceToDevice, stream));
+    return CSLAM_OK;
+  }
+
   // Solve for the Fiedler pair of the current matrix.  X keeps the result (column 0).
   int solve(double tol, int max_iters, double* lambda2) {
     const bool prof = getenv("CSLAM_MAC_PROF") != nullptr;
@@ -2602,7 +2957,8 @@ struct FiedlerSolver {
       return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
     };
     const double tp0 = prof ? now() : 0;
-    CSLAM_TRY(prepare_matrix());
+    const int persist_ch = persist_rows_per_thread();
+    CSLAM_TRY(prepare_matrix(/*sync_host=*/persist_ch == 0));
     const double tp1 = prof ? now() : 0;
     t_prepare += tp1 - tp0;
     if (n < 2) {
@@ -2610,37 +2966,35 @@ struct FiedlerSolver {
       return CSLAM_ERR_INVALID;
     }
     m = std::min(m, std::max(1, (n - 1) / 3));
-    if (!warm) {
-      // same spirit as the reference's X0 = RandomState(7).normal (mac.py:58); any start
-      // converges to the same pair, the seed only fixes the iteration path
-      // (the block depends only on (n, m, ld): drawn once per handle -- 200 k normal deviates cost
-      //  ~3 ms of host time per cold solve, i.e. per fw_subset -- and kept on the device)
-      if (x0_n != n || x0_m != m || x0_ld != ld || !x0_dev) {
-        std::mt19937_64 gen(7);
-        std::normal_distribution<double> nd(0.0, 1.0);
-        std::vector<double> x0(static_cast<size_t>(MAXM) * ld, 0.0);
-        for (int c = 0; c < m; ++c)
-          for (int i = 0; i < n; ++i) x0[static_cast<size_t>(c) * ld + i] = nd(gen);
-        dev_free(x0_dev);
-        CSLAM_TRY(dev_alloc(&x0_dev, x0.size()));
-        CSLAM_CUDA(cudaMemcpyAsync(x0_dev, x0.data(), x0.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
-        CSLAM_CUDA(cudaStreamSynchronize(stream));
-        x0_n = n; x0_m = m; x0_ld = ld;
-      }
-      CSLAM_CUDA(cudaMemcpyAsync(X, x0_dev, static_cast<size_t>(MAXM) * ld * sizeof(double),
-                                 cudaMemcpyDeviceToDevice, stream));
-    }
+    if (!warm) CSLAM_TRY(load_start_block());
     double theta[MAXM] = {};
     bool ok = true;
     bool have_p = false;
     int it = 0;
     last_path = 0;
     const double tp2 = prof ? now() : 0;
-    if (const int ch = persist_rows_per_thread()) {
+    if (const int ch = persist_ch) {
       // one cooperative kernel: start-up pass (centre X, AX = L X, Rayleigh-Ritz) + LOBPCG loop
       int status = 1;
-      const int pst = persist_loop(ch, tol, max_iters, theta, false, true, &it, &status);
+      int pst = persist_loop(ch, tol, max_iters, theta, false, true, &it, &status);
       if (pst != CSLAM_OK && pst != kPersistUnavailable) return pst;
+      if (pst == CSLAM_OK && h_bad[0] != 0) {
+        // the tridiagonal factorisation broke down (seen only now: no host round trip before
+        // the launch): solve again with the diagonal preconditioner
+        CSLAM_TRY(use_diagonal_preconditioner());
+        CSLAM_TRY(load_start_block());   // the failed attempt may have left anything in X
+        for (int c = 0; c < MAXM; ++c) theta[c] = 0.0;
+        pst = persist_loop(ch, tol, max_iters, theta, false, true, &it, &status);
+        if (pst != CSLAM_OK && pst != kPersistUnavailable) return pst;
+      }
+      if (pst == kPersistUnavailable) {
+        // continue on the multi-kernel path, which needs ||L||_inf on the host
+        CSLAM_CUDA(cudaMemcpyAsync(h_red, d_lnorm, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CSLAM_CUDA(cudaMemcpyAsync(h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CSLAM_CUDA(cudaStreamSynchronize(stream));
+        lnorm = h_red[0];
+        if (h_bad[0] != 0 && !jacobi) CSLAM_TRY(use_diagonal_preconditioner());
+      }
       if (pst == CSLAM_OK) {
       if (prof) t_loop += now() - tp2;
       last_path = 1;
@@ -2831,13 +3185,18 @@ struct cslam_mac {
   unsigned int *d_blk_eq = nullptr, *d_blk_sel = nullptr;
   int sel_blocks = 0, sel_per_block = 0;
   double* d_vec_tmp = nullptr;
-  // pinned staging of the active adjacency (rebuilt every Frank-Wolfe iteration)
-  int* hp_indptr = nullptr;
-  int* hp_cols = nullptr;
-  int* hp_src = nullptr;
+  // support of w (candidate ids with w != 0) and its adjacency, maintained on the device
+  unsigned char* d_flag = nullptr;   // [mc] 1 = in the support
+  int* d_sup = nullptr;              // [sup_cap]
+  int* d_sup_cnt = nullptr;          // [1]
+  int* d_deg = nullptr;              // [n] degree counters / fill cursors
+  double* d_supval = nullptr;        // [sup_cap] w gathered over the support
+  int* d_trace = nullptr;            // [trace_cap] per-iteration selections (optional output)
+  size_t sup_cap = 0, trace_cap = 0;
+  int* hp_sup = nullptr;             // pinned copies
+  double* hp_supval = nullptr;
   size_t hp_cap = 0;
-  std::vector<int> deg;
-  std::vector<int> sup_i, sup_j;   // endpoints of the current support (mac_set_active)
+  int sup_ub = 0;                    // host-side upper bound of *d_sup_cnt
   int fixed_components = 0;     // connected components of the fixed graph
   std::vector<int> fixed_root;  // component label per vertex (fixed graph)
   double tol = 1e-10;
@@ -2848,72 +3207,118 @@ struct cslam_mac {
 namespace cslam {
 namespace {
 
-int mac_set_active(cslam_mac* h, const std::vector<int>& support) {
-  // connectivity of fixed + active edges (reference: singular factorisation -> exception).
-  // The components of the fixed graph are computed once (mac_create); here only the
-  // active edges are merged over those component labels.
+// room for a support of `need` candidates (device list, gathered values, pinned copies, CSR)
+int mac_reserve_support(cslam_mac* h, size_t need) {
+  need = std::min<size_t>(std::max<size_t>(need, 1024), static_cast<size_t>(std::max<int64_t>(h->nc, 1)));
+  if (need > h->sup_cap) {
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    int* nsup = nullptr;
+    CSLAM_TRY(dev_alloc(&nsup, need));
+    if (h->d_sup && h->sup_cap)
+      CSLAM_CUDA(cudaMemcpy(nsup, h->d_sup, h->sup_cap * sizeof(int), cudaMemcpyDeviceToDevice));
+    dev_free(h->d_sup);
+    h->d_sup = nsup;
+    dev_free(h->d_supval);
+    CSLAM_TRY(dev_alloc(&h->d_supval, need));
+    h->sup_cap = need;
+  }
+  if (need > h->hp_cap) {
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->hp_sup) cudaFreeHost(h->hp_sup);
+    if (h->hp_supval) cudaFreeHost(h->hp_supval);
+    h->hp_sup = nullptr;
+    h->hp_supval = nullptr;
+    CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->hp_sup), need * sizeof(int)));
+    CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->hp_supval), need * sizeof(double)));
+    h->hp_cap = need;
+  }
+  Adj& a = h->fs.act;
+  if (!a.indptr) CSLAM_TRY(dev_alloc(&a.indptr, static_cast<size_t>(h->n) + 1));
+  if (2 * need > a.cap_nnz) {
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    dev_free(a.cols);
+    dev_free(a.src);
+    dev_free(a.vals);
+    CSLAM_TRY(dev_alloc(&a.cols, 2 * need));
+    CSLAM_TRY(dev_alloc(&a.src, 2 * need));
+    CSLAM_TRY(dev_alloc(&a.vals, 2 * need));
+    a.cap_nnz = 2 * need;
+  }
+  return CSLAM_OK;
+}
+
+// Connectivity of fixed + active edges (reference: singular factorisation -> exception ->
+// retry, cslam/algebraic_connectivity_maximization.py:448-466).  Only edges that are NUMERICALLY
+// present count: the Laplacian drops candidates with w <= 1e-10 (mac.py:72) and an edge of
+// weight 0 contributes nothing.  The components of the fixed graph are computed once
+// (mac_create); a connected fixed graph (every pose graph with its odometry chains bridged)
+// needs no work here at all.
+int mac_check_connected(cslam_mac* h, const int* support, const double* w_sup, size_t count) {
   int comps = h->fixed_components;
   if (comps > 1) {
     UnionFind uf(h->fixed_components);
-    for (int e : support)
+    for (size_t t = 0; t < count; ++t) {
+      const int e = support[t];
+      if (!(w_sup[t] > 1e-10) || w_sup[t] * h->cw[e] == 0.0) continue;
       if (uf.unite(h->fixed_root[h->ci[e]], h->fixed_root[h->cj[e]])) --comps;
+    }
   }
   if (comps != 1) {
     set_error("Laplacian is singular: graph of fixed + selected edges has %d connected components",
               comps);
     return CSLAM_ERR_SINGULAR;
   }
-  // CSR of the active candidates (both directions), counting sort by row; entry order within a
-  // row = support order (deterministic).  Built in pinned staging buffers and copied
-  // asynchronously: they are next rewritten after solve(), which synchronises the stream.
-  const int n = h->n;
-  const size_t nnz = 2 * support.size();
-  if (!h->hp_indptr) CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->hp_indptr), (static_cast<size_t>(n) + 1) * sizeof(int)));
-  if (nnz > h->hp_cap) {
-    if (h->hp_cols) cudaFreeHost(h->hp_cols);
-    if (h->hp_src) cudaFreeHost(h->hp_src);
-    h->hp_cols = h->hp_src = nullptr;
-    h->hp_cap = std::max<size_t>(2 * nnz, 4096);
-    CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->hp_cols), h->hp_cap * sizeof(int)));
-    CSLAM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->hp_src), h->hp_cap * sizeof(int)));
-  }
-  int* indptr = h->hp_indptr;
-  std::memset(indptr, 0, (static_cast<size_t>(n) + 1) * sizeof(int));
-  // endpoints of the support gathered once (the candidate arrays are 1M entries: every lookup
-  // by edge id is a cache miss) and used by both passes of the counting sort
-  h->sup_i.resize(support.size());
-  h->sup_j.resize(support.size());
-  for (size_t t = 0; t < support.size(); ++t) {
-    const int e = support[t];
-    const int i = h->ci[e], j = h->cj[e];
-    h->sup_i[t] = i;
-    h->sup_j[t] = j;
-    if (i == j) continue;   // self loops cancel in a Laplacian
-    indptr[i + 1]++;
-    indptr[j + 1]++;
-  }
-  for (int r = 0; r < n; ++r) indptr[r + 1] += indptr[r];
-  const size_t used = static_cast<size_t>(indptr[n]);
-  h->deg.assign(static_cast<size_t>(n), 0);
-  for (size_t t = 0; t < support.size(); ++t) {
-    const int i = h->sup_i[t], j = h->sup_j[t];
-    if (i == j) continue;
-    const int e = support[t];
-    int p = indptr[i] + h->deg[i]++;
-    h->hp_cols[p] = j;
-    h->hp_src[p] = e;
-    p = indptr[j] + h->deg[j]++;
-    h->hp_cols[p] = i;
-    h->hp_src[p] = e;
-  }
-  CSLAM_TRY(h->fs.upload_async(h->fs.act, indptr, h->hp_cols, h->hp_src, used));
-  h->fs.has_act = true;
-  if (h->fs.act.nnz > 0) {
-    const int blocks = static_cast<int>((h->fs.act.nnz + 255) / 256);
-    k_lap_fill<<<blocks, 256, 0, h->stream>>>(h->fs.act.nnz, h->fs.act.src, h->d_w, h->d_cw, 1e-10,
-                                              h->fs.act.vals);
+  return CSLAM_OK;
+}
+
+// Active adjacency (both directions of every support edge) built ON THE DEVICE from the
+// support list: degree count -> scan -> fill -> per-row sort by candidate id + values.
+// `ub` >= *d_sup_cnt sizes the launches.
+int mac_build_active(cslam_mac* h, int ub) {
+  cudaStream_t s = h->stream;
+  CSLAM_TRY(mac_reserve_support(h, static_cast<size_t>(std::max(ub, 1))));
+  if (h->fixed_components > 1) {
+    // rare (reference tests with disconnected robots): needs the support and its weights on the host
+    k_w_gather<<<std::max(1, (ub + 255) / 256), 256, 0, s>>>(h->d_sup, h->d_sup_cnt, h->d_w, h->d_supval);
     CSLAM_LAUNCH_CHECK();
+    int cnt = 0;
+    CSLAM_CUDA(cudaMemcpyAsync(&cnt, h->d_sup_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CSLAM_CUDA(cudaStreamSynchronize(s));
+    if (cnt > 0) {
+      CSLAM_CUDA(cudaMemcpyAsync(h->hp_sup, h->d_sup, cnt * sizeof(int), cudaMemcpyDeviceToHost, s));
+      CSLAM_CUDA(cudaMemcpyAsync(h->hp_supval, h->d_supval, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CSLAM_CUDA(cudaStreamSynchronize(s));
+    }
+    CSLAM_TRY(mac_check_connected(h, h->hp_sup, h->hp_supval, static_cast<size_t>(cnt)));
   }
+  Adj& a = h->fs.act;
+  const int gb = std::max(1, std::min(592, (ub + 255) / 256));
+  CSLAM_CUDA(cudaMemsetAsync(h->d_deg, 0, static_cast<size_t>(h->n) * sizeof(int), s));
+  k_act_count<<<gb, 256, 0, s>>>(h->d_sup, h->d_sup_cnt, h->d_ci, h->d_cj, h->d_deg);
+  CSLAM_LAUNCH_CHECK();
+  k_act_scan<<<1, 1024, 0, s>>>(h->n, h->d_deg, a.indptr);
+  CSLAM_LAUNCH_CHECK();
+  k_act_fill<<<gb, 256, 0, s>>>(h->d_sup, h->d_sup_cnt, h->d_ci, h->d_cj, a.indptr, h->d_deg, a.cols, a.src);
+  CSLAM_LAUNCH_CHECK();
+  k_act_finish<<<(h->n + 255) / 256, 256, 0, s>>>(h->n, a.indptr, a.cols, a.src, h->d_w, h->d_cw, 1e-10, a.vals);
+  CSLAM_LAUNCH_CHECK();
+  a.nnz = 2 * static_cast<int64_t>(ub);   // upper bound; the kernels read the row pointers
+  h->fs.has_act = true;
+  return CSLAM_OK;
+}
+
+// support := the given host list (cslam_mac_fiedler: a dense w from the caller)
+int mac_set_support_from_host(cslam_mac* h, const std::vector<int>& support) {
+  cudaStream_t s = h->stream;
+  CSLAM_TRY(mac_reserve_support(h, support.size()));
+  const int cnt = static_cast<int>(support.size());
+  if (cnt > 0) {
+    std::memcpy(h->hp_sup, support.data(), support.size() * sizeof(int));
+    CSLAM_CUDA(cudaMemcpyAsync(h->d_sup, h->hp_sup, support.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  }
+  k_set_int<<<1, 1, 0, s>>>(h->d_sup_cnt, cnt);
+  CSLAM_LAUNCH_CHECK();
+  h->sup_ub = cnt;
   return CSLAM_OK;
 }
 
@@ -3012,7 +3417,7 @@ int cslam_mac_create(int num_poses, int64_t n_fixed, const int32_t* fi, const in
     UnionFind uf(h->n);
     h->fixed_components = h->n;
     for (int64_t e = 0; e < n_fixed; ++e)
-      if (uf.unite(h->fi[e], h->fj[e])) --h->fixed_components;
+      if (h->fw[e] != 0.0 && uf.unite(h->fi[e], h->fj[e])) --h->fixed_components;   // a zero-weight edge connects nothing
     h->fixed_root.assign(static_cast<size_t>(h->n), 0);
     std::vector<int> label(static_cast<size_t>(h->n), -1);
     int next = 0;
@@ -3031,8 +3436,13 @@ int cslam_mac_create(int num_poses, int64_t n_fixed, const int32_t* fi, const in
       (st = dev_alloc(&h->d_slist, mc)) || (st = dev_alloc(&h->d_part, 1024)) ||
       (st = dev_alloc(&h->d_ctl, 1)) || (st = dev_alloc(&h->d_blk_eq, h->sel_blocks)) ||
       (st = dev_alloc(&h->d_blk_sel, h->sel_blocks)) ||
-      (st = dev_alloc(&h->d_vec_tmp, static_cast<size_t>(num_poses))))
+      (st = dev_alloc(&h->d_vec_tmp, static_cast<size_t>(num_poses))) ||
+      (st = dev_alloc(&h->d_flag, mc)) || (st = dev_alloc(&h->d_sup_cnt, 1)) ||
+      (st = dev_alloc(&h->d_deg, static_cast<size_t>(num_poses))))
     return fail(st);
+  cudaMemsetAsync(h->d_flag, 0, mc, h->stream);
+  cudaMemsetAsync(h->d_sup_cnt, 0, sizeof(int), h->stream);
+  h->fs.extra_d2h_src = h->d_sup_cnt;
   if (n_cand > 0) {
     cudaMemcpyAsync(h->d_ci, ci, n_cand * sizeof(int), cudaMemcpyHostToDevice, h->stream);
     cudaMemcpyAsync(h->d_cj, cj, n_cand * sizeof(int), cudaMemcpyHostToDevice, h->stream);
@@ -3051,9 +3461,14 @@ int cslam_mac_destroy(cslam_mac_t* h) {
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->fs.release();
-  if (h->hp_indptr) cudaFreeHost(h->hp_indptr);
-  if (h->hp_cols) cudaFreeHost(h->hp_cols);
-  if (h->hp_src) cudaFreeHost(h->hp_src);
+  if (h->hp_sup) cudaFreeHost(h->hp_sup);
+  if (h->hp_supval) cudaFreeHost(h->hp_supval);
+  dev_free(h->d_flag);
+  dev_free(h->d_sup);
+  dev_free(h->d_sup_cnt);
+  dev_free(h->d_deg);
+  dev_free(h->d_supval);
+  dev_free(h->d_trace);
   dev_free(h->d_ci);
   dev_free(h->d_cj);
   dev_free(h->d_cw);
@@ -3089,7 +3504,19 @@ int cslam_mac_fiedler(cslam_mac_t* h, const double* w, double* lambda2, double* 
   if (h->nc > 0)
     CSLAM_CUDA(cudaMemcpyAsync(h->d_w, w, h->nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   std::vector<int> sup = support_of(w, h->nc, 1e-10);
-  CSLAM_TRY(mac_set_active(h, sup));
+  {
+    std::vector<double> wsup(sup.size());
+    for (size_t t = 0; t < sup.size(); ++t) wsup[t] = w[sup[t]];
+    CSLAM_TRY(mac_check_connected(h, sup.data(), wsup.data(), sup.size()));
+  }
+  CSLAM_TRY(mac_set_support_from_host(h, sup));
+  {
+    const int fc = h->fixed_components;
+    h->fixed_components = 1;   // checked above with the caller's w: skip the device round trip
+    const int st = mac_build_active(h, h->sup_ub);
+    h->fixed_components = fc;
+    CSLAM_TRY(st);
+  }
   h->fs.warm = false;  // evaluate_fiedler_pair is stateless in the reference
   CSLAM_TRY(h->fs.solve(h->tol, h->max_lobpcg_iters, lambda2));
   h->total_lobpcg_iters += h->fs.last_iters;
@@ -3114,20 +3541,55 @@ int cslam_mac_grad(cslam_mac_t* h, const double* fiedler_vec, double* grad_out) 
   return CSLAM_OK;
 }
 
-int cslam_mac_fw_subset(cslam_mac_t* h, const double* w_init, int k, int max_iters,
-                        double duality_gap_tol, double* rounded_out, double* w_out, double* u_out,
-                        int* iters_out, int32_t* trace_sel, double* trace_f) {
-  CSLAM_REQUIRE(h && w_init && rounded_out && w_out && u_out, "mac_fw_subset: NULL argument");
+// Frank-Wolfe with a sparse start vector and sparse results; see include/cslam_b200.h.
+int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* init_idx,
+                               const double* init_val, int k, int max_iters, double duality_gap_tol,
+                               int32_t* sel_out, int64_t sup_capacity, int32_t* sup_idx_out,
+                               double* sup_val_out, int64_t* n_sup_out, double* u_out, int* iters_out,
+                               int32_t* trace_sel, double* trace_f) {
+  CSLAM_REQUIRE(h && (init_idx || n_init == 0) && (init_val || n_init == 0) && sel_out && u_out && n_sup_out,
+                "mac_fw_subset_sparse: NULL argument");
   CSLAM_REQUIRE(h->nc > 0, "mac_fw_subset: no candidate edges");
   CSLAM_REQUIRE(k >= 0 && k <= h->nc && max_iters >= 0, "mac_fw_subset: need 0 <= k <= m (k=%d)", k);
+  CSLAM_REQUIRE(n_init >= 0 && n_init <= h->nc, "mac_fw_subset: bad start vector size");
   DeviceGuard g(h->device);
   cudaStream_t s = h->stream;
   const int64_t mc = h->nc;
-  CSLAM_CUDA(cudaMemcpyAsync(h->d_w, w_init, mc * sizeof(double), cudaMemcpyHostToDevice, s));
-  std::vector<int> support = support_of(w_init, mc, 0.0);  // superset of {w > 1e-10}
-  std::vector<char> in_support(static_cast<size_t>(mc), 0);
-  for (int e : support) in_support[e] = 1;
-  std::vector<int> slist(static_cast<size_t>(std::max(k, 1)));
+  const size_t sup_max = static_cast<size_t>(std::min<int64_t>(mc, n_init + static_cast<int64_t>(k) * std::max(max_iters, 1)));
+  CSLAM_REQUIRE(sup_capacity >= static_cast<int64_t>(sup_max) || !sup_idx_out,
+                "mac_fw_subset_sparse: support outputs need room for %lld entries",
+                static_cast<long long>(sup_max));
+  CSLAM_TRY(mac_reserve_support(h, std::max<size_t>(sup_max, static_cast<size_t>(n_init))));
+  // ---- w := start vector, support := its non-zero entries -----------------------------------
+  CSLAM_CUDA(cudaMemsetAsync(h->d_w, 0, mc * sizeof(double), s));
+  CSLAM_CUDA(cudaMemsetAsync(h->d_flag, 0, static_cast<size_t>(mc), s));
+  k_set_int<<<1, 1, 0, s>>>(h->d_sup_cnt, 0);
+  CSLAM_LAUNCH_CHECK();
+  int n0 = 0;
+  for (int64_t t = 0; t < n_init; ++t) {
+    CSLAM_REQUIRE(init_idx[t] >= 0 && init_idx[t] < mc, "mac_fw_subset: start index out of range");
+    if (init_val[t] > 0.0) {       // (the dense path kept {w > 0}; zeros add nothing)
+      h->hp_sup[n0] = init_idx[t];
+      h->hp_supval[n0] = init_val[t];
+      ++n0;
+    }
+  }
+  if (n0 > 0) {
+    // staged through the pinned buffers; d_slist / d_g are free until the first gradient
+    CSLAM_CUDA(cudaMemcpyAsync(h->d_slist, h->hp_sup, n0 * sizeof(int), cudaMemcpyHostToDevice, s));
+    CSLAM_CUDA(cudaMemcpyAsync(h->d_g, h->hp_supval, n0 * sizeof(double), cudaMemcpyHostToDevice, s));
+    k_w_scatter<<<(n0 + 255) / 256, 256, 0, s>>>(n0, h->d_slist, h->d_g, h->d_w);
+    CSLAM_LAUNCH_CHECK();
+    k_sup_append<<<(n0 + 255) / 256, 256, 0, s>>>(n0, h->d_slist, h->d_flag, h->d_sup, h->d_sup_cnt);
+    CSLAM_LAUNCH_CHECK();
+  }
+  h->sup_ub = n0;
+  if (trace_sel && static_cast<size_t>(max_iters) * std::max(k, 1) > h->trace_cap) {
+    CSLAM_CUDA(cudaStreamSynchronize(s));
+    dev_free(h->d_trace);
+    h->trace_cap = static_cast<size_t>(max_iters) * std::max(k, 1);
+    CSLAM_TRY(dev_alloc(&h->d_trace, h->trace_cap));
+  }
   double u = INFINITY;
   h->fs.warm = false;
   int it = 0;
@@ -3139,13 +3601,18 @@ int cslam_mac_fw_subset(cslam_mac_t* h, const double* w_init, int k, int max_ite
     if (prof) cudaStreamSynchronize(s);
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   };
+  double* h_dual = h->fs.h_red + 2 * NPAIR;   // pinned scalar slot not used by the persistent path
   for (; it < max_iters; ++it) {
     // f_i, vec_i = evaluate_fiedler_pair(w_i)                               (mac.py:211)
     double t0 = prof ? now() : 0;
-    CSLAM_TRY(mac_set_active(h, support));
+    CSLAM_TRY(mac_build_active(h, h->sup_ub));
     double f = 0.0;
     double t1 = prof ? now() : 0;
     CSLAM_TRY(h->fs.solve(h->tol, h->max_lobpcg_iters, &f));
+    if (h->fs.last_path == 1) {   // exact support size came back with the solve result
+      h->sup_ub = h->fs.h_bad[1];
+      h->fs.act.nnz = 2 * static_cast<int64_t>(h->sup_ub);
+    }
     double t2 = prof ? now() : 0;
     t_act += t1 - t0;
     t_solve += t2 - t1;
@@ -3160,17 +3627,15 @@ int cslam_mac_fw_subset(cslam_mac_t* h, const double* w_init, int k, int max_ite
     CSLAM_LAUNCH_CHECK();
     k_sum_parts<<<1, 256, 0, s>>>(512, 1, h->d_part, h->d_part + 512);
     CSLAM_LAUNCH_CHECK();
-    double dual = 0.0;
-    CSLAM_CUDA(cudaMemcpyAsync(&dual, h->d_part + 512, sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (k > 0)
-      CSLAM_CUDA(cudaMemcpyAsync(slist.data(), h->d_slist, k * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CSLAM_CUDA(cudaMemcpyAsync(h_dual, h->d_part + 512, sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (trace_sel && k > 0)
+      CSLAM_CUDA(cudaMemcpyAsync(h->d_trace + static_cast<size_t>(it) * k, h->d_slist, k * sizeof(int),
+                                 cudaMemcpyDeviceToDevice, s));
     CSLAM_CUDA(cudaStreamSynchronize(s));
     double t3 = prof ? now() : 0;
     t_sel += t3 - t2;
-    u = std::min(u, f + dual);
+    u = std::min(u, f + *h_dual);
     if (trace_f) trace_f[it] = f;
-    if (trace_sel)
-      for (int t = 0; t < k; ++t) trace_sel[static_cast<size_t>(it) * k + t] = slist[t];
     if (u - f < duality_gap_tol) {  // (mac.py:223-225)
       gap_reached = true;
       break;
@@ -3179,37 +3644,59 @@ int cslam_mac_fw_subset(cslam_mac_t* h, const double* w_init, int k, int max_ite
     const double alpha = 2.0 / (it + 2.0);
     k_fw_update<<<blocks_m, 256, 0, s>>>(mc, alpha, h->d_s, h->d_w);
     CSLAM_LAUNCH_CHECK();
-    if (alpha == 1.0) {  // w becomes exactly s_i: previous support is wiped
-      for (int e : support) in_support[e] = 0;
-      support.clear();
+    if (alpha == 1.0) {  // w becomes exactly s_i: the previous support is wiped
+      k_sup_clear<<<std::max(1, std::min(592, (h->sup_ub + 255) / 256)), 256, 0, s>>>(h->d_sup, h->d_sup_cnt, h->d_flag);
+      CSLAM_LAUNCH_CHECK();
+      k_set_int<<<1, 1, 0, s>>>(h->d_sup_cnt, 0);
+      CSLAM_LAUNCH_CHECK();
+      h->sup_ub = 0;
     }
-    const size_t old_size = support.size();
-    for (int t = 0; t < k; ++t)   // slist is ascending, so the appended run is sorted
-      if (!in_support[slist[t]]) {
-        in_support[slist[t]] = 1;
-        support.push_back(slist[t]);
-      }
-    std::inplace_merge(support.begin(), support.begin() + old_size, support.end());
+    if (k > 0) {
+      k_sup_append<<<(k + 255) / 256, 256, 0, s>>>(k, h->d_slist, h->d_flag, h->d_sup, h->d_sup_cnt);
+      CSLAM_LAUNCH_CHECK();
+    }
+    h->sup_ub = static_cast<int>(std::min<int64_t>(mc, static_cast<int64_t>(h->sup_ub) + k));
     if (prof) t_host += now() - t3;
   }
   if (prof)
-    fprintf(stderr, "[cslam mac prof] set_active %.2f ms, solve %.2f ms (prepare %.2f, prologue %.2f, loop %.2f), grad+topk+dual %.2f ms, host update %.2f ms\n",
+    fprintf(stderr, "[cslam mac prof] build_active %.2f ms, solve %.2f ms (prepare %.2f, prologue %.2f, loop %.2f), grad+topk+dual %.2f ms, host update %.2f ms\n",
             t_act, t_solve, h->fs.t_prepare, h->fs.t_prologue, h->fs.t_loop, t_sel, t_host);
-  (void)gap_reached;
   if (iters_out) *iters_out = it + (gap_reached ? 1 : 0);
-  CSLAM_CUDA(cudaMemcpyAsync(w_out, h->d_w, mc * sizeof(double), cudaMemcpyDeviceToHost, s));
+  // ---- results: the support of w with its values, the per-iteration selections ---------------
+  const int ub = h->sup_ub;
+  k_w_gather<<<std::max(1, std::min(592, (ub + 255) / 256)), 256, 0, s>>>(h->d_sup, h->d_sup_cnt, h->d_w, h->d_supval);
+  CSLAM_LAUNCH_CHECK();
+  int cnt = 0;
+  CSLAM_CUDA(cudaMemcpyAsync(&cnt, h->d_sup_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (ub > 0) {
+    CSLAM_CUDA(cudaMemcpyAsync(h->hp_sup, h->d_sup, ub * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CSLAM_CUDA(cudaMemcpyAsync(h->hp_supval, h->d_supval, ub * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  const int done_iters = it + (gap_reached ? 1 : 0);
+  if (trace_sel && k > 0 && done_iters > 0)
+    CSLAM_CUDA(cudaMemcpyAsync(trace_sel, h->d_trace, static_cast<size_t>(done_iters) * k * sizeof(int),
+                               cudaMemcpyDeviceToHost, s));
   CSLAM_CUDA(cudaStreamSynchronize(s));
   *u_out = u;
+  // support in ascending candidate order (the device list is in arrival order)
+  std::vector<std::pair<int, double>> sup(static_cast<size_t>(cnt));
+  for (int t = 0; t < cnt; ++t) sup[t] = {h->hp_sup[t], h->hp_supval[t]};
+  std::sort(sup.begin(), sup.end());
+  *n_sup_out = cnt;
+  if (sup_idx_out)
+    for (int t = 0; t < cnt; ++t) {
+      sup_idx_out[t] = sup[t].first;
+      if (sup_val_out) sup_val_out[t] = sup[t].second;
+    }
   // round_solution_tiebreaker(w_i, k) (mac.py:168-189): top-k by (round(w, 10), weight).
-  // w is zero outside `support`; order the support by that key, fill up from the zeros.
-  std::fill(rounded_out, rounded_out + mc, 0.0);
+  // w is zero outside the support; order the support by that key, fill up from the zeros.
   if (k > 0) {
     struct Key { double w10; double weight; int e; };
     std::vector<Key> keys;
-    keys.reserve(support.size());
-    for (int e : support) {
-      const double w10 = std::nearbyint(w_out[e] * 1e10) / 1e10;  // np.round(w, 10)
-      if (w10 > 0.0) keys.push_back({w10, h->cw[e], e});
+    keys.reserve(sup.size());
+    for (auto& pr : sup) {
+      const double w10 = std::nearbyint(pr.second * 1e10) / 1e10;  // np.round(w, 10)
+      if (w10 > 0.0) keys.push_back({w10, h->cw[pr.first], pr.first});
     }
     auto better = [](const Key& a, const Key& b) {
       if (a.w10 != b.w10) return a.w10 > b.w10;
@@ -3224,8 +3711,40 @@ int cslam_mac_fw_subset(cslam_mac_t* h, const double* w_init, int k, int max_ite
         if (!taken[e]) keys.push_back({0.0, h->cw[e], static_cast<int>(e)});
     }
     std::partial_sort(keys.begin(), keys.begin() + k, keys.end(), better);
-    for (int t = 0; t < k; ++t) rounded_out[keys[t].e] = 1.0;
+    for (int t = 0; t < k; ++t) sel_out[t] = keys[t].e;
+    std::sort(sel_out, sel_out + k);
   }
+  return CSLAM_OK;
+}
+
+// Dense form with the reference's signature (mac.py:191-233): a thin wrapper that turns the
+// dense start vector into its non-zero entries and scatters the sparse results.
+int cslam_mac_fw_subset(cslam_mac_t* h, const double* w_init, int k, int max_iters,
+                        double duality_gap_tol, double* rounded_out, double* w_out, double* u_out,
+                        int* iters_out, int32_t* trace_sel, double* trace_f) {
+  CSLAM_REQUIRE(h && w_init && rounded_out && w_out && u_out, "mac_fw_subset: NULL argument");
+  CSLAM_REQUIRE(h->nc > 0, "mac_fw_subset: no candidate edges");
+  CSLAM_REQUIRE(k >= 0 && k <= h->nc && max_iters >= 0, "mac_fw_subset: need 0 <= k <= m (k=%d)", k);
+  const int64_t mc = h->nc;
+  std::vector<int32_t> idx;
+  std::vector<double> val;
+  for (int64_t e = 0; e < mc; ++e)
+    if (w_init[e] > 0.0) {
+      idx.push_back(static_cast<int32_t>(e));
+      val.push_back(w_init[e]);
+    }
+  const size_t cap = static_cast<size_t>(std::min<int64_t>(mc, static_cast<int64_t>(idx.size()) +
+                                                                   static_cast<int64_t>(k) * std::max(max_iters, 1)));
+  std::vector<int32_t> sel(static_cast<size_t>(std::max(k, 1))), sidx(std::max<size_t>(cap, 1));
+  std::vector<double> sval(std::max<size_t>(cap, 1));
+  int64_t ns = 0;
+  CSLAM_TRY(cslam_mac_fw_subset_sparse(h, static_cast<int64_t>(idx.size()), idx.data(), val.data(), k,
+                                       max_iters, duality_gap_tol, sel.data(), static_cast<int64_t>(sidx.size()),
+                                       sidx.data(), sval.data(), &ns, u_out, iters_out, trace_sel, trace_f));
+  std::fill(w_out, w_out + mc, 0.0);
+  for (int64_t t = 0; t < ns; ++t) w_out[sidx[t]] = sval[t];
+  std::fill(rounded_out, rounded_out + mc, 0.0);
+  for (int t = 0; t < k; ++t) rounded_out[sel[t]] = 1.0;
   return CSLAM_OK;
 }
 
@@ -3251,7 +3770,7 @@ int cslam_debug_rayleigh_ritz(const double* ga, const double* gb, int s, int m, 
                               int reps, int device, double* c_out, double* theta_out, int* ok_out,
                               int64_t* cycles_out) {
   CSLAM_REQUIRE(ga && gb && c_out && theta_out && ok_out, "debug_rayleigh_ritz: NULL argument");
-  CSLAM_REQUIRE(s >= 1 && s <= MAXS && m >= 1 && m <= MAXM && m <= s && reps >= 1 && impl >= 0 && impl <= 1,
+  CSLAM_REQUIRE(s >= 1 && s <= MAXS && m >= 1 && m <= MAXM && m <= s && reps >= 1 && impl >= 0 && impl <= 2,
                 "debug_rayleigh_ritz: bad sizes");
   if (cslam_device_count() <= 0) {
     set_error("debug_rayleigh_ritz: no CUDA device");

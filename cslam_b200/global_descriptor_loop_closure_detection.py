@@ -187,9 +187,14 @@ class GlobalDescriptorLoopClosureDetection(object):
         if len(keyframe_msgs) == 0:
             return []
         if not getattr(self.global_descriptor, "enable", False):
+            # descriptor network disabled (the reference's random-descriptor test mode,
+            # cosplace.py:102-105): keyframe by keyframe; same return value as the batched path
+            first = self.nb_inter_robot_matches
             for m in keyframe_msgs:
                 self.receive_keyframe(m)
-            return []
+            return [self.inter_robot_matches_buffer[i]
+                    for i in range(first, self.nb_inter_robot_matches)
+                    if i in self.inter_robot_matches_buffer]
         images = [image_from_msg(m.image) for m in keyframe_msgs]
         import torch
         if hasattr(images[0], "is_cuda"):
@@ -266,7 +271,16 @@ class GlobalDescriptorLoopClosureDetection(object):
         return msg
 
     def inter_robot_matches_timer_callback(self):
-        """Broadcast the matches some neighbour in range has not seen (reference :241-289)."""
+        """Broadcast the matches some neighbour in range has not seen (reference :241-289).
+
+        DELIBERATE DEVIATION (DESIGN.md "quirks"): with exactly two robots in range the
+        reference means to drop every match between those two ("should have already been
+        detected by the other robot", :254-263) but removes from the list it is iterating
+        over, which skips the element after each removal - about every second such match is
+        still transmitted.  Here all of them are dropped, as the comment in the reference
+        says; the receiver would only have overwritten its own identical candidate.
+        tests/test_frontend_gpu.py::test_two_robots_in_range_do_not_retransmit_mutual_matches
+        pins this."""
         if len(self.inter_robot_matches_buffer) == 0:
             return
         from_match_idx = self.neighbor_manager.select_from_which_match_to_send(

@@ -180,25 +180,42 @@ class MAC:
             rounded[np.argpartition(zipped, -k, order=['w', 'weight'])[-k:]] = 1.0
         return rounded
 
+    def fw_subset_sparse(self, init_idx, init_val, k, max_iters=5, duality_gap_tol=1e-8, trace=False):
+        """`fw_subset` without dense vectors: the start vector by its non-zero entries
+        (`init_idx`, `init_val`); returns (sel_idx, (sup_idx, sup_val), upper_bound) - the ascending
+        ids of the rounded selection and the non-zero entries of the unrounded iterate."""
+        init_idx = np.ascontiguousarray(init_idx, dtype=np.int32)
+        init_val = np.ascontiguousarray(init_val, dtype=np.float64)
+        assert init_idx.shape == init_val.shape and init_idx.ndim == 1
+        m, k = len(self.weights), int(k)
+        cap = max(1, min(m, len(init_idx) + k * max(int(max_iters), 1)))
+        sel = np.empty(max(k, 1), dtype=np.int32)
+        sup_idx = np.empty(cap, dtype=np.int32)
+        sup_val = np.empty(cap, dtype=np.float64)
+        n_sup, u, iters = ctypes.c_int64(), ctypes.c_double(), ctypes.c_int()
+        tsel = np.full((max(max_iters, 1), max(k, 1)), -1, dtype=np.int32) if trace else None
+        tf = np.full(max(max_iters, 1), np.nan) if trace else None
+        _lib.check(_lib.load().cslam_mac_fw_subset_sparse(
+            self._h, len(init_idx), _lib.ptr(init_idx), _lib.ptr(init_val), k, int(max_iters),
+            float(duality_gap_tol), _lib.ptr(sel), cap, _lib.ptr(sup_idx), _lib.ptr(sup_val),
+            ctypes.byref(n_sup), ctypes.byref(u), ctypes.byref(iters), _lib.ptr(tsel), _lib.ptr(tf)))
+        self.last_fw_iters = iters.value
+        self.last_trace = (tsel, tf) if trace else None
+        return sel[:k], (sup_idx[:n_sup.value], sup_val[:n_sup.value]), u.value
+
     def fw_subset(self, w_init, k, max_iters=5, duality_gap_tol=1e-8, trace=False):
         """Frank-Wolfe subset selection (mac.py:191-233), entirely on the GPU.
 
         returns (solution, unrounded, upper_bound) like the reference.
         """
-        w_init = np.ascontiguousarray(w_init, dtype=np.float64)
+        w_init = np.asarray(w_init, dtype=np.float64)
         m = len(self.weights)
         assert len(w_init) == m
-        k = int(k)
-        rounded = np.empty(m, dtype=np.float64)
-        w = np.empty(m, dtype=np.float64)
-        u = ctypes.c_double()
-        iters = ctypes.c_int()
-        tsel = np.full((max(max_iters, 1), max(k, 1)), -1, dtype=np.int32) if trace else None
-        tf = np.full(max(max_iters, 1), np.nan) if trace else None
-        _lib.check(_lib.load().cslam_mac_fw_subset(self._h, _lib.ptr(w_init), k, int(max_iters),
-                                                   float(duality_gap_tol), _lib.ptr(rounded),
-                                                   _lib.ptr(w), ctypes.byref(u), ctypes.byref(iters),
-                                                   _lib.ptr(tsel), _lib.ptr(tf)))
-        self.last_fw_iters = iters.value
-        self.last_trace = (tsel, tf) if trace else None
-        return rounded, w, u.value
+        idx = np.flatnonzero(w_init > 0.0)
+        sel, (sup_idx, sup_val), u = self.fw_subset_sparse(idx, w_init[idx], k, max_iters,
+                                                           duality_gap_tol, trace)
+        rounded = np.zeros(m)
+        rounded[sel] = 1.0
+        w = np.zeros(m)
+        w[sup_idx] = sup_val
+        return rounded, w, u

@@ -75,6 +75,28 @@ except ImportError:
         value: str = ""
 
 
+try:  # pragma: no cover
+    from cslam_common_interfaces.msg import RobotIdsAndOrigin  # noqa: F401
+except ImportError:
+    @dataclass
+    class RobotIds:
+        ids: List[int] = field(default_factory=list)
+
+    @dataclass
+    class RobotIdsAndOrigin:
+        """cslam_common_interfaces/RobotIdsAndOrigin: robots in range and, per robot, the robot
+        whose frame it currently expresses its estimates in (cslam/neighbors_manager.py:171-185)."""
+        robots: RobotIds = field(default_factory=RobotIds)
+        origins: RobotIds = field(default_factory=RobotIds)
+
+try:  # pragma: no cover
+    from std_msgs.msg import String  # noqa: F401
+except ImportError:
+    @dataclass
+    class String:
+        data: str = ""
+
+
 @dataclass
 class UInt32:
     """std_msgs/UInt32 stand-in (heartbeat payload = origin robot id)."""

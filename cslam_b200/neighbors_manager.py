@@ -6,7 +6,7 @@ the node handle (rclpy node or `cslam_b200.local_node.LocalNode`).
 """
 from time import time
 
-from .msgs import UInt32
+from .msgs import RobotIdsAndOrigin, String, UInt32
 
 
 class NeighborMonitor(object):
@@ -65,6 +65,12 @@ class NeighborManager(object):
                     node, rid, params['neighbor_management.enable_neighbor_monitoring'],
                     params['neighbor_management.init_delay_sec'],
                     params['neighbor_management.max_heartbeat_delay_sec'])
+        # the pose-graph back end asks who is in range before it starts an optimisation
+        # (src/back_end/decentralized_pgo.cpp:134-141) and waits for the answer (:25-29)
+        self.subscriber = node.create_subscription(
+            String, 'cslam/get_current_neighbors', self.get_current_neighbors_callback, 100)
+        self.neighbors_publisher = node.create_publisher(
+            RobotIdsAndOrigin, 'cslam/current_neighbors', 100)
 
     def _alive(self):
         return [rid for rid, m in self.neighbors_monitors.items() if m.is_alive()]
@@ -115,3 +121,14 @@ class NeighborManager(object):
         mon.last_keyframe_received = max(mon.last_keyframe_received,
                                          max(d.keyframe_id for d in descriptors))
         return fresh
+
+    def get_current_neighbors_callback(self, msg):
+        """Publish the robots currently in range (without the local one) and the origin robot
+        each of them reports in its heartbeat (neighbors_manager.py:171-185)."""
+        _, in_range = self.check_neighbors_in_range()
+        in_range.remove(self.robot_id)
+        out = RobotIdsAndOrigin()
+        out.robots.ids = list(in_range)
+        for i in in_range:
+            out.origins.ids.append(self.neighbors_monitors[i].origin_robot_id)
+        self.neighbors_publisher.publish(out)

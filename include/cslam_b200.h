@@ -154,6 +154,22 @@ int cslam_mac_grad(cslam_mac_t* h, const double* fiedler_vec, double* grad_out);
 int cslam_mac_fw_subset(cslam_mac_t* h, const double* w_init, int k, int max_iters,
                         double duality_gap_tol, double* rounded_out, double* w_out,
                         double* u_out, int* iters_out, int32_t* trace_sel, double* trace_f);
+/* The same with a SPARSE start vector and sparse results - what select_candidates needs
+ * (algebraic_connectivity_maximization.py:448-466,519-533): the start vector is the greedy 0/1
+ * vector with k ones (:205-218) and only the k selected edges are used afterwards, so no dense
+ * [n_cand] vector crosses the boundary.
+ *   init_idx/init_val [n_init]  the non-zero entries of w_init (distinct ids)
+ *   sel_out [k]                 ascending ids of the rounded selection (round_solution_tiebreaker)
+ *   sup_idx_out/sup_val_out     (nullable) the non-zero entries of the unrounded iterate w in
+ *                               ascending id order, *n_sup_out of them; sup_capacity must be at
+ *                               least min(n_cand, n_init + k * max(max_iters, 1))
+ * The support of w and the Laplacian of the active candidates are maintained and assembled on the
+ * device (mac.py:61-77, mac/utils.py:86-126 rebuild them from Python lists per iteration). */
+int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* init_idx,
+                               const double* init_val, int k, int max_iters, double duality_gap_tol,
+                               int32_t* sel_out, int64_t sup_capacity, int32_t* sup_idx_out,
+                               double* sup_val_out, int64_t* n_sup_out, double* u_out, int* iters_out,
+                               int32_t* trace_sel, double* trace_f);
 /* Totals since creation: LOBPCG iterations, SpMV columns applied, and whether the last
  * solve had to fall back from the tridiagonal to the diagonal preconditioner. */
 int cslam_mac_stats(cslam_mac_t* h, int64_t* lobpcg_iters, int64_t* spmv_columns,

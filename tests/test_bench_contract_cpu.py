@@ -81,8 +81,33 @@ def test_nns_parity_block_with_a_stand_in_pool():
 
     rng = np.random.default_rng(0)
     rows = rng.random((2500, 32))
-    good = bench.nns_parity(Pool(rows), 32, 10, torch.device("cpu"), nq=3, chunk=1000)
-    assert good["nns_recall_at_k"] == 1.0 and good["nns_ranked_lists_identical"] == 3
+    good = bench.nns_parity(Pool(rows), 32, 10, torch.device("cpu"), own_rows=5, nq_fresh=3, chunk=1000)
+    assert good["ok"] and good["nns_recall_at_k"] == 1.0 and good["nns_ranked_lists_identical"] == 8
     assert good["nns_max_abs_dsim"] == 0.0 and good["pool_rows_scored"] == 2500 and good["nns_top_k"] == 10
-    bad = bench.nns_parity(Pool(rows, spoil=True), 32, 10, torch.device("cpu"), nq=3, chunk=1000)
-    assert bad["nns_recall_at_k"] == pytest.approx(0.9) and bad["nns_ranked_lists_identical"] == 0
+    assert good["last_step_rows_find_themselves"] == 5
+    bad = bench.nns_parity(Pool(rows, spoil=True), 32, 10, torch.device("cpu"), own_rows=5, nq_fresh=3, chunk=1000)
+    assert not bad["ok"] and bad["nns_recall_at_k"] == pytest.approx(0.9) and bad["nns_ranked_lists_identical"] == 0
+    # what round 1's benchmark actually produced: zero / non-finite rows in the pool (descriptors
+    # read before they were written).  The checker must fail, not report "identical lists".
+    broken = rows.copy()
+    broken[-3:] = 0.0
+    z = bench.nns_parity(Pool(broken), 32, 10, torch.device("cpu"), own_rows=5, nq_fresh=3, chunk=1000)
+    assert not z["ok"] and (z["pool_zero_rows"] == 3 or not z["pool_and_scores_finite"])
+    broken[-3:] = np.inf
+    z = bench.nns_parity(Pool(broken), 32, 10, torch.device("cpu"), own_rows=5, nq_fresh=3, chunk=1000)
+    assert not z["ok"] and not z["pool_and_scores_finite"]
+    # exact duplicates in the pool (the rotating synthetic batches): recall counts ties as hits
+    dup = np.concatenate([rows, rows[-5:]])
+    d = bench.nns_parity(Pool(dup), 32, 10, torch.device("cpu"), own_rows=5, nq_fresh=3, chunk=1000)
+    assert d["ok"] and d["nns_recall_at_k"] == 1.0
+
+
+def test_lists_match_modulo_ties_rejects_non_finite_scores():
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle.nns import lists_match_modulo_ties
+    sims = np.array([0.9, 0.8, 0.7, 0.6])
+    assert lists_match_modulo_ties([0, 1], [0, 1], sims)
+    assert not lists_match_modulo_ties([0, 2], [0, 1], sims)
+    sims_nan = np.array([np.nan, np.nan, 0.7, 0.6])
+    assert not lists_match_modulo_ties([0, 2], [1, 3], sims_nan)

@@ -22,7 +22,7 @@ for label, eps in (("early", 3e-1), ("late", 1e-5)):
     GA = np.ascontiguousarray(S.T @ M @ S); GB = np.ascontiguousarray(S.T @ S)
     ref = eigh(GA, GB, eigvals_only=True)[:2]
     for sweeps in (3,):
-        for impl in (0, 1):
+        for impl in (0, 1, 2):
             C = np.zeros((6, 2)); t = np.zeros(2); ok = ctypes.c_int(); cyc = np.zeros(6, dtype=np.int64)
             _lib.check(lib.cslam_debug_rayleigh_ritz(_lib.ptr(GA), _lib.ptr(GB), 6, 2, impl, sweeps, 200, 0,
                                                      _lib.ptr(C), _lib.ptr(t), ctypes.byref(ok), _lib.ptr(cyc)))

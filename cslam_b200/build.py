@@ -21,6 +21,7 @@ SOURCES = [
     "vlad_tc.cu",
     "mac.cu",
     "scancontext.cu",
+    "swarm.cu",
 ]
 
 NVCC_FLAGS = [

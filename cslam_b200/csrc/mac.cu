@@ -1861,12 +1861,18 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     const unsigned int target = epoch * nblocks;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     unsigned int seen;
+    // (a __nanosleep back-off of 20-200 ns between polls changed nothing, measured: the time spent
+    //  here is the wait for the slowest CTA of the phase, not the polling itself)
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
     } while (seen < target);
   }
   __syncthreads();
 }
+
+// (Measured and dropped: an atomic-free variant - every CTA stores its epoch in its own slot and
+//  148 threads per CTA poll one slot each - made the solve 35 % SLOWER, 69.8 ms against 51.7 ms
+//  per selection: 148 x 148 polling loads per round swamp the L2 slice that holds the slots.)
 
 // ------------------------------------------------------------------ persistent LOBPCG
 // The whole LOBPCG iteration as ONE cooperative kernel: one CTA per SM, every thread owns CH
@@ -1907,7 +1913,7 @@ struct PersistArgs {
   int init;              // 1: X in global memory is a raw start block: centre it, form AX = L X and
                          //    Rayleigh-Ritz it inside the kernel before the first iteration
   double* out;           // [0..MAXM) theta, [MAXM] iterations, [MAXM+1] status, [MAXM+2] res
-  int rr_impl;           // small eigen-solve: 1 register-resident rr_warp_elem (default), 0 shared-memory rr_warp
+  int rr_impl;           // small eigen-solve: 2 two-stage rr_two_stage (default), 1 register-resident 6 x 6 rr_warp_elem, 0 shared-memory rr_warp
   int rr_sweeps;         // Jacobi sweep cap of the Rayleigh-Ritz solve
   double rr_tol2;        // squared relative off-diagonal level at which the Jacobi sweeps stop
   int cap0, cap1;        // shared-memory capacity (entries) for the CTA's slice of each adjacency
@@ -1940,6 +1946,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   }
   unsigned int epoch = 0;
   const double lnorm_v = __ldg(a.lnorm);
+#define GRID_SYNC() grid_barrier(a.barrier, epoch, nb_grid)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x, nb_grid = gridDim.x;
@@ -2127,7 +2134,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 #pragma unroll
         for (int c = 0; c < MAXM; ++c)
           if (c < m) a.X[static_cast<size_t>(c) * ld + row0 + j] = x[j][c];
-    grid_barrier(a.barrier, epoch, nb_grid);
+    GRID_SYNC();
 #pragma unroll
     for (int j = 0; j < CH; ++j)
       if (valid[j]) {
@@ -2162,7 +2169,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
         for (int c = 0; c < MAXM; ++c)
           if (valid[j] && c < m) loc[c] += x[j][c];
       block_sum2(loc, a.pcs);
-      grid_barrier(a.barrier, epoch, nb_grid);
+      GRID_SYNC();
     } else {
     // ---- phase 1: residual, forward aggregates -------------------------------------------
     double A = 1.0, B[MAXM];
@@ -2193,7 +2200,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       for (int c = 0; c < MAXM; ++c) a.fB[static_cast<size_t>(c) * nb_grid + b] = B[c];
     }
     tick(0);
-    grid_barrier(a.barrier, epoch, nb_grid);
+    GRID_SYNC();
     tick(6);
     // ---- phase 2: convergence test, exact forward walk, backward aggregates ----------------
     grid_sum2(a.pres, s_res);
@@ -2236,7 +2243,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       for (int c = 0; c < MAXM; ++c) a.bB[static_cast<size_t>(c) * nb_grid + b] = B[c];
     }
     tick(1);
-    grid_barrier(a.barrier, epoch, nb_grid);
+    GRID_SYNC();
     tick(6);
     // ---- phase 3: exact backward walk -> W = M^-1 r, column sums ------------------------------
     cta_prefix(a.bA, a.bB, true);
@@ -2262,7 +2269,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       }
     block_sum2(loc, a.pcs);
     tick(2);
-    grid_barrier(a.barrier, epoch, nb_grid);
+    GRID_SYNC();
     tick(6);
     }  // !init_pass
     // ---- phase 4: AW = L (W - mean), centre W, Gram partial sums ------------------------------
@@ -2407,7 +2414,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       __syncthreads();
     }
     tick(3);
-    grid_barrier(a.barrier, epoch, nb_grid);
+    GRID_SYNC();
     tick(6);
     // ---- phase 5: Rayleigh-Ritz (redundantly per CTA), basis update in registers --------------
     grid_sum_gram(a.pgram, s_G);
@@ -2527,6 +2534,273 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   }
 }
 
+#undef GRID_SYNC
+
+// ------------------------------------------------------------------ fused Frank-Wolfe tail
+// Everything between two eigen-solves of fw_subset (mac.py:212-230) in ONE cooperative kernel:
+//   grad_i = grad_from_fiedler(vec_i)                       -> g
+//   s_i = round_solution(grad_i, k): exact top-k by a 64-bit radix select (6 digit passes, one
+//        grid barrier each; every CTA picks the digit redundantly from the global histogram),
+//        ties at the k-th value taken in index order, ids written in ascending order
+//   u_i = min(u_i, f_i + grad_i @ (s_i - w_i)), gap test
+//   w_i += alpha (s_i - w_i), support of w extended by the new ids (cleared first when alpha = 1)
+// The multi-kernel form of the same steps (k_grad, k_sel_*, k_dual_part, k_fw_update,
+// k_sup_*: ~22 launches, two of them single-block) costs ~160 us per Frank-Wolfe iteration in
+// launch latency; this kernel is bounded by 8 grid barriers and ~70 MB of L2/HBM traffic.
+// Grid = one CTA per SM, CTA b owns the contiguous edge range [b * chunk, (b + 1) * chunk).
+struct FwState {          // device resident, one per MAC handle
+  double u;               // dual upper bound so far
+  double f;               // objective of the current iterate (copied from the solver's output)
+  double dual;            // grad @ (s - w) of this iteration
+  int done;               // 1: duality gap below tolerance, w was not updated
+  int pad;
+};
+
+struct SelectArgs {
+  long long mc;
+  int k, it, chunk;
+  const int *ci, *cj;
+  const double *cw, *v;
+  double *g, *w;
+  double alpha, gap_tol;
+  const double* f_src;          // solver output: theta[0]
+  unsigned int* hist;           // [6][2048], zero at launch
+  unsigned int* cnt_pairs;      // [grid][2] per-CTA (greater, equal) counts
+  double* part;                 // [grid][2] per-CTA partial sums
+  int* slist;                   // [k] ascending ids of s_i
+  int* trace;                   // nullable: [.., k] destination row of this iteration
+  unsigned char* flag;          // [mc] support membership
+  int* sup;
+  int* sup_cnt;
+  FwState* st;
+  unsigned int* barrier;        // zero at launch
+};
+
+__global__ void __launch_bounds__(256, 1) k_fw_select(SelectArgs a) {
+  constexpr int T = 256, BITS = 11, NB = 1 << BITS;
+  __shared__ __align__(16) unsigned int sh_hist[NB];
+  __shared__ long long sh_chunk[T];
+  __shared__ int sh_best_d;
+  __shared__ long long sh_best_acc;
+  __shared__ double sh_red[8][2];
+  __shared__ int sh_warp[8];
+  __shared__ int sh_base, sh_tie;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x, G = gridDim.x;
+  unsigned int epoch = 0;
+  const long long e0 = static_cast<long long>(b) * a.chunk;
+  const long long e1 = min(a.mc, e0 + a.chunk);
+  const int old_cnt = *a.sup_cnt;   // read before anybody may reset it (first barrier below)
+
+  // ---- pass 0 prologue: gradient of the own range, sum of g*w, (alpha = 1) clear the support flags
+  double acc_gw = 0.0;
+  for (long long e = e0 + tid; e < e1; e += T) {
+    // mac.py:123-129: kdelta = weight_k * (v_i - v_j); grad[k] = kdelta * (v_i - v_j)
+    const double d = __dsub_rn(a.v[a.ci[e]], a.v[a.cj[e]]);
+    const double ge = __dmul_rn(__dmul_rn(a.cw[e], d), d);
+    a.g[e] = ge;
+    acc_gw = fma(ge, a.w[e], acc_gw);
+  }
+
+  // ---- radix select of the k-th largest key
+  uint64_t prefix = 0, mask = 0;
+  long long remaining = a.k;
+  if (a.k > 0) {
+    int pass = 0;
+    for (int shift = 55; shift >= 0; shift -= BITS, ++pass) {
+      for (int i = tid; i < NB; i += T) sh_hist[i] = 0;
+      __syncthreads();
+      for (long long e = e0 + tid; e < e1; e += T) {
+        const uint64_t key = f64_to_key(a.g[e]);
+        if ((key & mask) == prefix) atomicAdd(&sh_hist[(key >> shift) & (NB - 1u)], 1u);
+      }
+      __syncthreads();
+      unsigned int* gh = a.hist + pass * NB;
+      for (int i = tid; i < NB; i += T)
+        if (sh_hist[i]) atomicAdd(&gh[i], sh_hist[i]);
+      grid_barrier(a.barrier, epoch, G);
+      // every CTA picks the digit from the complete histogram (same data, same result): the
+      // largest d >= 1 with (#keys in bins > d) + hist[d] >= remaining, else 0
+      constexpr int PER = NB / T;
+      for (int i = tid; i < NB; i += T) sh_hist[i] = __ldcg(gh + i);
+      if (tid == 0) { sh_best_d = 0; sh_best_acc = -1; }
+      __syncthreads();
+      long long mine = 0;
+      for (int j = 0; j < PER; ++j) mine += sh_hist[tid * PER + j];
+      sh_chunk[tid] = mine;
+      __syncthreads();
+      long long above = 0;
+      for (int t = tid + 1; t < T; ++t) above += sh_chunk[t];
+      long long acc = above;
+      int found = -1;
+      long long found_acc = 0;
+      for (int j = PER - 1; j >= 0; --j) {
+        const int d = tid * PER + j;
+        const long long hc = sh_hist[d];
+        if (found < 0 && d > 0 && acc + hc >= remaining) { found = d; found_acc = acc; }
+        acc += hc;
+      }
+      if (found > 0) atomicMax(&sh_best_d, found);
+      __syncthreads();
+      if (found > 0 && found == sh_best_d) sh_best_acc = found_acc;
+      if (tid == 0 && sh_best_d == 0) sh_best_acc = above + mine - sh_hist[0];
+      __syncthreads();
+      prefix |= static_cast<uint64_t>(sh_best_d) << shift;
+      mask |= static_cast<uint64_t>(NB - 1u) << shift;
+      remaining -= sh_best_acc;
+      __syncthreads();
+    }
+  }
+  const uint64_t kth = prefix;
+  const long long need_eq = a.k > 0 ? remaining : 0;   // ties at the k-th key to take, in index order
+
+  // ---- counts and partial sums of the own range
+  unsigned int c_gt = 0, c_eq = 0;
+  double acc_sel = 0.0;
+  if (a.k > 0)
+    for (long long e = e0 + tid; e < e1; e += T) {
+      const double ge = a.g[e];
+      const uint64_t key = f64_to_key(ge);
+      if (key > kth) { ++c_gt; acc_sel += ge; }
+      c_eq += key == kth;
+    }
+  // fixed-order CTA reductions
+  for (int o = 16; o > 0; o >>= 1) {
+    c_gt += __shfl_xor_sync(0xffffffffu, c_gt, o);
+    c_eq += __shfl_xor_sync(0xffffffffu, c_eq, o);
+  }
+  acc_sel = warp_sum(acc_sel);
+  acc_gw = warp_sum(acc_gw);
+  if (lane == 0) {
+    sh_warp[warp] = static_cast<int>(c_gt);
+    sh_chunk[warp] = c_eq;
+    sh_red[warp][0] = acc_sel;
+    sh_red[warp][1] = acc_gw;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int tg = 0, te = 0;
+    double s0 = 0.0, s1 = 0.0;
+    for (int q = 0; q < 8; ++q) {
+      tg += sh_warp[q];
+      te += static_cast<unsigned int>(sh_chunk[q]);
+      s0 += sh_red[q][0];
+      s1 += sh_red[q][1];
+    }
+    a.cnt_pairs[2 * b] = tg;
+    a.cnt_pairs[2 * b + 1] = te;
+    a.part[2 * b] = s0;
+    a.part[2 * b + 1] = s1;
+  }
+  grid_barrier(a.barrier, epoch, G);
+  // ---- every CTA: offsets of its range in the ordered output, the dual value, the gap test
+  long long tie_base = 0, out_base = 0;
+  double sum_sel = 0.0, sum_gw = 0.0;
+  // all per-CTA records in one round trip (one thread each), then a serial fixed-order pass
+  for (int q = tid; q < G; q += T) {
+    sh_hist[2 * q] = __ldcg(a.cnt_pairs + 2 * q);
+    sh_hist[2 * q + 1] = __ldcg(a.cnt_pairs + 2 * q + 1);
+    reinterpret_cast<double*>(sh_hist + 1024)[2 * q] = __ldcg(a.part + 2 * q);
+    reinterpret_cast<double*>(sh_hist + 1024)[2 * q + 1] = __ldcg(a.part + 2 * q + 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double* sp = reinterpret_cast<const double*>(sh_hist + 1024);
+    for (int q = 0; q < G; ++q) {
+      const long long qg = sh_hist[2 * q], qe = sh_hist[2 * q + 1];
+      if (q < b) {
+        long long take = need_eq - tie_base;
+        take = take < 0 ? 0 : (take > qe ? qe : take);
+        out_base += qg + take;
+        tie_base += qe;
+      }
+      sum_sel += sp[2 * q];
+      sum_gw += sp[2 * q + 1];
+    }
+    sh_base = static_cast<int>(out_base);
+    sh_tie = static_cast<int>(tie_base);
+    // grad @ (s - w) = sum of the selected gradients - grad @ w; the ties taken all equal the k-th value
+    double kth_val = 0.0;
+    if (need_eq > 0) {
+      const uint64_t u = (kth & 0x8000000000000000ull) ? (kth & 0x7fffffffffffffffull) : ~kth;
+      kth_val = __longlong_as_double(static_cast<long long>(u));
+    }
+    const double dual = (sum_sel + static_cast<double>(need_eq) * kth_val) - sum_gw;
+    const double f = *a.f_src;
+    const double u_prev = a.it == 0 ? INFINITY : a.st->u;
+    const double u_new = fmin(u_prev, f + dual);
+    sh_red[0][0] = (u_new - f < a.gap_tol) ? 1.0 : 0.0;
+    if (b == 0) {
+      a.st->u = u_new;
+      a.st->f = f;
+      a.st->dual = dual;
+      a.st->done = (u_new - f < a.gap_tol) ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  const bool done = sh_red[0][0] != 0.0;
+  int out = sh_base;
+  long long tie_rank = sh_tie;
+  __syncthreads();
+  if (a.alpha == 1.0 && !done) {
+    // w becomes exactly s_i: the previous support is forgotten (the decision is grid-uniform)
+    for (int t = b * T + tid; t < old_cnt; t += G * T) a.flag[a.sup[t]] = 0;
+    grid_barrier(a.barrier, epoch, G);
+    if (b == 0 && tid == 0) *a.sup_cnt = 0;
+    grid_barrier(a.barrier, epoch, G);
+  }
+  // ---- ordered walk of the own range: ids of s_i, Frank-Wolfe update of w, support
+  for (long long base = e0; base < e1; base += T) {
+    const long long e = base + tid;
+    bool sel = false, is_eq = false;
+    if (e < e1 && a.k > 0) {
+      const uint64_t key = f64_to_key(a.g[e]);
+      is_eq = key == kth;
+      sel = key > kth;
+    }
+    const unsigned meq = __ballot_sync(0xffffffffu, is_eq);
+    const unsigned mgt = __ballot_sync(0xffffffffu, sel);
+    if (lane == 0) {
+      sh_warp[warp] = __popc(meq);
+    }
+    __syncthreads();
+    long long my_tie = tie_rank + __popc(meq & ((1u << lane) - 1u));
+    int eq_total = 0;
+    for (int q = 0; q < 8; ++q) {
+      if (q < warp) my_tie += sh_warp[q];
+      eq_total += sh_warp[q];
+    }
+    sel = sel || (is_eq && my_tie < need_eq);
+    __syncthreads();
+    const unsigned msel = __ballot_sync(0xffffffffu, sel);
+    (void)mgt;
+    if (lane == 0) sh_warp[warp] = __popc(msel);
+    __syncthreads();
+    int pos = out + __popc(msel & ((1u << lane) - 1u));
+    int sel_total = 0;
+    for (int q = 0; q < 8; ++q) {
+      if (q < warp) pos += sh_warp[q];
+      sel_total += sh_warp[q];
+    }
+    if (sel) {
+      a.slist[pos] = static_cast<int>(e);
+      if (a.trace) a.trace[pos] = static_cast<int>(e);
+    }
+    if (e < e1 && !done) {
+      // mac.py:230: w_i = w_i + alpha * (s_i - w_i), same operation order, no contraction
+      const double we = a.w[e];
+      if (sel || we != 0.0) a.w[e] = __dadd_rn(we, __dmul_rn(a.alpha, __dsub_rn(sel ? 1.0 : 0.0, we)));
+      if (sel && !__ldcg(a.flag + e)) {
+        a.flag[e] = 1;
+        a.sup[atomicAdd(a.sup_cnt, 1)] = static_cast<int>(e);
+      }
+    }
+    out += sel_total;
+    tie_rank += eq_total;
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------ solver object
 constexpr int kPersistUnavailable = 1;   // internal status: fall back to the multi-kernel path
 
@@ -2561,6 +2835,7 @@ struct FiedlerSolver {
   unsigned int* pbar = nullptr;
   cudaEvent_t pev0 = nullptr, pev1 = nullptr;   // around every k_lobpcg_persist launch
   double persist_ms = 0.0;                      // summed CUDA-event durations
+  double persist_ms_last_selection = 0.0;       // same, reset by fw_subset (timeline report)
   int64_t persist_launches = 0, persist_iters = 0, persist_bytes = 0;
   double t_prepare = 0, t_prologue = 0, t_loop = 0;   // CSLAM_MAC_PROF
   double* x0_dev = nullptr;   // cached start block of cold solves
@@ -2673,6 +2948,7 @@ struct FiedlerSolver {
     pa.out = pout;
     pa.barrier = pbar;
     CSLAM_CUDA(cudaMemsetAsync(pbar, 0, sizeof(unsigned int), stream));
+
     pa.prof = pprof;
     void* args[] = {&pa};
     const void* fn = nullptr;
@@ -2683,7 +2959,7 @@ struct FiedlerSolver {
       default: set_error("fiedler: bad persistent variant %d", ch); return CSLAM_ERR_INVALID;
     }
     pa.cap0 = pa.cap1 = 6144;
-    pa.rr_impl = getenv("CSLAM_RR_IMPL") ? atoi(getenv("CSLAM_RR_IMPL")) : 1;
+    pa.rr_impl = getenv("CSLAM_RR_IMPL") ? atoi(getenv("CSLAM_RR_IMPL")) : 2;
     pa.rr_sweeps = getenv("CSLAM_RR_SWEEPS") ? atoi(getenv("CSLAM_RR_SWEEPS")) : (pa.rr_impl == 2 ? 4 : 3);
     pa.rr_tol2 = getenv("CSLAM_RR_TOL2") ? atof(getenv("CSLAM_RR_TOL2")) : 1e-32;
     const size_t dyn = static_cast<size_t>(pa.cap0 + pa.cap1) * (sizeof(double) + sizeof(int)) +
@@ -2721,6 +2997,7 @@ struct FiedlerSolver {
       float ms = 0.f;
       CSLAM_CUDA(cudaEventElapsedTime(&ms, pev0, pev1));
       persist_ms += ms;
+      persist_ms_last_selection += ms;
       persist_launches += 1;
       persist_iters += *iters;
       // one SpMM per iteration reads nnz*(8+4) + n*4 and moves m*n*16
@@ -3197,6 +3474,11 @@ struct cslam_mac {
   double* hp_supval = nullptr;
   size_t hp_cap = 0;
   int sup_ub = 0;                    // host-side upper bound of *d_sup_cnt
+  // fused Frank-Wolfe tail (k_fw_select)
+  FwState* d_fwstate = nullptr;
+  unsigned int *d_sel_hist = nullptr, *d_sel_pairs = nullptr, *d_sel_bar = nullptr;
+  double* d_sel_part = nullptr;
+  int fused_tail = -1;               // -1 unknown, 0 unavailable (multi-kernel path), 1 in use
   int fixed_components = 0;     // connected components of the fixed graph
   std::vector<int> fixed_root;  // component label per vertex (fixed graph)
   double tol = 1e-10;
@@ -3355,6 +3637,45 @@ int mac_topk(cslam_mac* h, int k) {
   return CSLAM_OK;
 }
 
+// grad -> top-k -> dual/gap -> w update -> support, one cooperative launch (k_fw_select).
+// Returns kPersistUnavailable when the grid cannot be made co-resident.
+int mac_fused_tail(cslam_mac* h, int k, int it, double alpha, double gap_tol, int* trace_row) {
+  cudaStream_t s = h->stream;
+  const int G = h->fs.num_sms;
+  if (G <= 0 || G > 192) return kPersistUnavailable;
+  SelectArgs a;
+  a.mc = h->nc;
+  a.k = k;
+  a.it = it;
+  a.chunk = static_cast<int>((h->nc + G - 1) / G);
+  a.ci = h->d_ci; a.cj = h->d_cj; a.cw = h->d_cw; a.v = h->fs.X;
+  a.g = h->d_g; a.w = h->d_w;
+  a.alpha = alpha;
+  a.gap_tol = gap_tol;
+  a.f_src = h->fs.pout;
+  a.hist = h->d_sel_hist;
+  a.cnt_pairs = h->d_sel_pairs;
+  a.part = h->d_sel_part;
+  a.slist = h->d_slist;
+  a.trace = trace_row;
+  a.flag = h->d_flag;
+  a.sup = h->d_sup;
+  a.sup_cnt = h->d_sup_cnt;
+  a.st = h->d_fwstate;
+  a.barrier = h->d_sel_bar;
+  CSLAM_CUDA(cudaMemsetAsync(h->d_sel_hist, 0, 6 * 2048 * sizeof(unsigned int), s));
+  CSLAM_CUDA(cudaMemsetAsync(h->d_sel_bar, 0, sizeof(unsigned int), s));
+  void* args[] = {&a};
+  const cudaError_t le = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_fw_select), dim3(G),
+                                                     dim3(256), args, 0, s);
+  if (le != cudaSuccess) {
+    cudaGetLastError();
+    return kPersistUnavailable;
+  }
+  count_launch();
+  return CSLAM_OK;
+}
+
 }  // namespace
 }  // namespace cslam
 
@@ -3438,6 +3759,9 @@ int cslam_mac_create(int num_poses, int64_t n_fixed, const int32_t* fi, const in
       (st = dev_alloc(&h->d_blk_sel, h->sel_blocks)) ||
       (st = dev_alloc(&h->d_vec_tmp, static_cast<size_t>(num_poses))) ||
       (st = dev_alloc(&h->d_flag, mc)) || (st = dev_alloc(&h->d_sup_cnt, 1)) ||
+      (st = dev_alloc(&h->d_fwstate, 1)) || (st = dev_alloc(&h->d_sel_hist, 6 * 2048)) ||
+      (st = dev_alloc(&h->d_sel_pairs, 2 * 192)) || (st = dev_alloc(&h->d_sel_part, 2 * 192)) ||
+      (st = dev_alloc(&h->d_sel_bar, 1)) ||
       (st = dev_alloc(&h->d_deg, static_cast<size_t>(num_poses))))
     return fail(st);
   cudaMemsetAsync(h->d_flag, 0, mc, h->stream);
@@ -3469,6 +3793,11 @@ int cslam_mac_destroy(cslam_mac_t* h) {
   dev_free(h->d_deg);
   dev_free(h->d_supval);
   dev_free(h->d_trace);
+  dev_free(h->d_fwstate);
+  dev_free(h->d_sel_hist);
+  dev_free(h->d_sel_pairs);
+  dev_free(h->d_sel_bar);
+  dev_free(h->d_sel_part);
   dev_free(h->d_ci);
   dev_free(h->d_cj);
   dev_free(h->d_cw);
@@ -3592,6 +3921,7 @@ int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* in
   }
   double u = INFINITY;
   h->fs.warm = false;
+  h->fs.persist_ms_last_selection = 0.0;
   int it = 0;
   bool gap_reached = false;
   const int blocks_m = static_cast<int>((mc + 255) / 256);
@@ -3601,14 +3931,30 @@ int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* in
     if (prof) cudaStreamSynchronize(s);
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   };
-  double* h_dual = h->fs.h_red + 2 * NPAIR;   // pinned scalar slot not used by the persistent path
+  // CSLAM_MAC_TIMELINE=1: CUDA events on the stream at the section boundaries of every iteration
+  // (no extra synchronisation): where the GPU-side time of a selection goes, gaps included
+  const bool timeline = getenv("CSLAM_MAC_TIMELINE") != nullptr;
+  std::vector<cudaEvent_t> tl;
+  auto mark = [&]() {
+    if (!timeline) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    tl.push_back(e);
+  };
+  double* h_dual = h->fs.h_red + 2 * NPAIR;   // pinned scalar slots not used by the persistent path
+  static_assert(sizeof(FwState) <= (4 * MAXM + 4) * sizeof(double), "FwState must fit the pinned slots");
+  if (getenv("CSLAM_FW_FUSED") && atoi(getenv("CSLAM_FW_FUSED")) == 0) h->fused_tail = 0;
   for (; it < max_iters; ++it) {
     // f_i, vec_i = evaluate_fiedler_pair(w_i)                               (mac.py:211)
     double t0 = prof ? now() : 0;
+    mark();                                   // 0: iteration start
     CSLAM_TRY(mac_build_active(h, h->sup_ub));
+    mark();                                   // 1: active adjacency built
     double f = 0.0;
     double t1 = prof ? now() : 0;
     CSLAM_TRY(h->fs.solve(h->tol, h->max_lobpcg_iters, &f));
+    mark();                                   // 2: solved (host has theta)
     if (h->fs.last_path == 1) {   // exact support size came back with the solve result
       h->sup_ub = h->fs.h_bad[1];
       h->fs.act.nnz = 2 * static_cast<int64_t>(h->sup_ub);
@@ -3617,6 +3963,38 @@ int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* in
     t_act += t1 - t0;
     t_solve += t2 - t1;
     h->total_lobpcg_iters += h->fs.last_iters;
+    const double alpha = 2.0 / (it + 2.0);
+    // the solver's theta lives in fs.pout on the persistent path only
+    bool fused = h->fused_tail != 0 && h->fs.last_path == 1;
+    if (fused) {
+      // grad_i, s_i, u_i, gap test, w_i update, support: one launch              (mac.py:212-230)
+      const int fst = mac_fused_tail(h, k, it, alpha, duality_gap_tol,
+                                     trace_sel ? h->d_trace + static_cast<size_t>(it) * k : nullptr);
+      if (fst == kPersistUnavailable) {
+        h->fused_tail = 0;
+        fused = false;
+      } else {
+        CSLAM_TRY(fst);
+        h->fused_tail = 1;
+        CSLAM_CUDA(cudaMemcpyAsync(h_dual, h->d_fwstate, sizeof(FwState), cudaMemcpyDeviceToHost, s));
+        mark();                               // 3: tail done
+        CSLAM_CUDA(cudaStreamSynchronize(s));
+        FwState fw;
+        std::memcpy(&fw, h_dual, sizeof(FwState));
+        double t3 = prof ? now() : 0;
+        t_sel += t3 - t2;
+        u = fw.u;
+        if (trace_f) trace_f[it] = f;
+        if (fw.done) {  // (mac.py:223-225)
+          gap_reached = true;
+          break;
+        }
+        h->sup_ub = static_cast<int>(std::min<int64_t>(mc, (alpha == 1.0 ? 0 : static_cast<int64_t>(h->sup_ub)) + k));
+        continue;
+      }
+    }
+    // ---- multi-kernel form of the same steps (cooperative launch unavailable, or the
+    //      multi-kernel eigen-solver ran)
     // grad_i = grad_from_fiedler(vec_i)                                     (mac.py:212)
     k_grad<<<blocks_m, 256, 0, s>>>(mc, h->d_ci, h->d_cj, h->d_cw, h->fs.X, h->d_g);
     CSLAM_LAUNCH_CHECK();
@@ -3641,7 +4019,6 @@ int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* in
       break;
     }
     // w_i = w_i + alpha * (s_i - w_i)                                       (mac.py:229-230)
-    const double alpha = 2.0 / (it + 2.0);
     k_fw_update<<<blocks_m, 256, 0, s>>>(mc, alpha, h->d_s, h->d_w);
     CSLAM_LAUNCH_CHECK();
     if (alpha == 1.0) {  // w becomes exactly s_i: the previous support is wiped
@@ -3661,6 +4038,27 @@ int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* in
   if (prof)
     fprintf(stderr, "[cslam mac prof] build_active %.2f ms, solve %.2f ms (prepare %.2f, prologue %.2f, loop %.2f), grad+topk+dual %.2f ms, host update %.2f ms\n",
             t_act, t_solve, h->fs.t_prepare, h->fs.t_prologue, h->fs.t_loop, t_sel, t_host);
+  if (timeline && tl.size() >= 4) {
+    cudaStreamSynchronize(s);
+    double seg[4] = {0, 0, 0, 0};
+    const size_t per = 4, nit = tl.size() / per;
+    for (size_t q = 0; q < nit; ++q) {
+      float ms = 0.f;
+      for (int k2 = 0; k2 < 3; ++k2) {
+        cudaEventElapsedTime(&ms, tl[q * per + k2], tl[q * per + k2 + 1]);
+        seg[k2] += ms;
+      }
+      if (q + 1 < nit) {
+        cudaEventElapsedTime(&ms, tl[q * per + 3], tl[(q + 1) * per]);
+        seg[3] += ms;
+      }
+    }
+    float tot = 0.f;
+    cudaEventElapsedTime(&tot, tl.front(), tl.back());
+    fprintf(stderr, "[cslam mac timeline] %zu iterations, %.2f ms first mark to last: build_active %.2f | prepare+solve+readback %.2f (persistent kernel alone %.2f) | tail %.2f | between iterations %.2f ms\n",
+            nit, tot, seg[0], seg[1], h->fs.persist_ms_last_selection, seg[2], seg[3]);
+    for (cudaEvent_t e : tl) cudaEventDestroy(e);
+  }
   if (iters_out) *iters_out = it + (gap_reached ? 1 : 0);
   // ---- results: the support of w with its values, the per-iteration selections ---------------
   const int ub = h->sup_ub;

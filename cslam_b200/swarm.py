@@ -50,7 +50,10 @@ class SwarmExchange(object):
         B, D = embeddings.shape
         packed = torch.empty((B, D + 1), dtype=torch.float64, device=embeddings.device)
         packed[:, :D] = embeddings
-        packed[:, D] = torch.as_tensor(kf_ids, dtype=torch.float64, device=embeddings.device)
+        ids = torch.as_tensor(kf_ids, dtype=torch.float64)
+        if embeddings.is_cuda:
+            ids = ids.pin_memory().to(embeddings.device, non_blocking=True)
+        packed[:, D] = ids
         out = self._all_gather(packed)
         return out[:, :, :D].float().contiguous(), out[:, :, D].long()
 
@@ -92,7 +95,9 @@ class SwarmLoopClosureMatching(object):
 
     def _append_ids(self, kf_ids, device):
         import torch
-        new = torch.as_tensor(kf_ids, dtype=torch.int64, device=device)
+        new = torch.as_tensor(kf_ids, dtype=torch.int64)
+        if torch.device(device).type == "cuda":
+            new = new.pin_memory().to(device, non_blocking=True)
         n = self.local_nnsm.n - len(kf_ids)
         if self._row_ids is None or self._row_ids.numel() < n + len(kf_ids):
             grown = torch.empty(max(1024, 2 * (n + len(kf_ids))), dtype=torch.int64, device=device)
@@ -137,35 +142,104 @@ class SwarmLoopClosureMatching(object):
             x_kf = torch.cat([x_kf, x_kf.new_full((R * B, pad), -1)], dim=1)
             x_sims = torch.cat([x_sims, x_sims.new_full((R * B, pad), float('nan'))], dim=1)
         g_kf, g_sims = self.exchange.all_gather_topk(x_kf, x_sims)      # [R(pool), R*B, kx]
-
-        g_kf = g_kf.cpu().numpy().reshape(R, R, B, kx)                  # [pool, query robot, b, j]
-        g_sims = g_sims.cpu().numpy().reshape(R, R, B, kx)
-        all_ids = all_ids.cpu().numpy()
-        thr = self.params['frontend.similarity_threshold']
+        thr = float(self.params['frontend.similarity_threshold'])
         # best match of every descriptor in every OTHER robot's pool, in the order the reference
-        # meets them (query robot, keyframe, pool robot); one bulk insert into the candidate table
-        top_kf = g_kf[:, :, :, 0].transpose(1, 2, 0)                    # [query robot, b, pool]
-        top_s = g_sims[:, :, :, 0].transpose(1, 2, 0)
-        robots = np.arange(R)
-        with np.errstate(invalid="ignore"):
-            hit = (top_kf >= 0) & (top_s >= thr) & (robots[:, None, None] != robots[None, None, :])
-        qq, bb, gg = np.nonzero(hit)
-        m_kf0, m_kf1, m_s = all_ids[qq, bb], top_kf[qq, bb, gg], top_s[qq, bb, gg]
+        # meets them (query robot, keyframe, pool robot): thresholded and compacted on the
+        # device, only the hits travel to the host; one bulk insert into the candidate table
+        own = slice(me * B, (me + 1) * B)
+        hits, intra_raw = self._filter_round(g_kf, g_sims, all_ids, thr, idx[own], kf[own], sims[own],
+                                             rows_before, k_intra if intra_on else 0)
+        qq = hits[:, 0].astype(np.int64)
+        m_kf0, gg, m_kf1, m_s = (hits[:, 1].astype(np.int64), hits[:, 2].astype(np.int64),
+                                 hits[:, 3].astype(np.int64), hits[:, 4])
         self.candidate_selector.add_matches(qq, m_kf0, gg, m_kf1, m_s)
         edges = [EdgeInterRobot(*e) for e in zip(qq.tolist(), m_kf0.tolist(), gg.tolist(),
                                                  m_kf1.tolist(), m_s.tolist())]
         intra = []
         if intra_on:
-            own_idx = idx[me * B:(me + 1) * B].cpu().numpy()
-            own_kf = kf[me * B:(me + 1) * B].cpu().numpy()
-            own_sims = sims[me * B:(me + 1) * B].cpu().numpy()
             for b in range(B):
-                keep = (own_idx[b] >= 0) & (own_idx[b] < rows_before + b)
-                intra.append((kf_ids[b], own_kf[b][keep][:k_intra].tolist(),
-                              own_sims[b][keep][:k_intra].tolist()))
-        self.last_all_ids = all_ids
-        self.last_exchange = (g_kf, g_sims)
+                cnt = int(intra_raw[b, 0])
+                intra.append((kf_ids[b], intra_raw[b, 1:1 + cnt].astype(np.int64).tolist(),
+                              intra_raw[b, 1 + k_intra:1 + k_intra + cnt].tolist()))
+        self._last = (all_ids, g_kf, g_sims, R, B, kx)
         return edges, intra
+
+    # the exchange buffers of the last round, materialised on the host only when asked for
+    @property
+    def last_all_ids(self):
+        return self._last[0].cpu().numpy()
+
+    @property
+    def last_exchange(self):
+        _, g_kf, g_sims, R, B, kx = self._last
+        return (g_kf.cpu().numpy().reshape(R, R, B, kx), g_sims.cpu().numpy().reshape(R, R, B, kx))
+
+    def _filter_round(self, g_kf, g_sims, all_ids, thr, own_idx, own_kf, own_sims, rows_before, k_intra):
+        """-> (hits float64 [n, 5] = (query robot, query kf, pool robot, matched kf, similarity),
+        intra float64 [B, 1 + 2 k_intra] = (count, kfs, sims)) on the host.
+        CUDA tensors: `cslam_swarm_hits` / `cslam_swarm_intra` on the current stream and ONE
+        device->host copy through a pinned buffer.  CPU tensors (the gloo tests of the exchange
+        logic, which run the collectives without a GPU): the same filters in numpy."""
+        import torch
+        R, RB, kx = g_kf.shape
+        B = RB // R
+        if not g_kf.is_cuda:
+            return self._filter_round_host(g_kf, g_sims, all_ids, thr, own_idx, own_kf, own_sims,
+                                           rows_before, k_intra)
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        cap = R * B * max(R - 1, 1)
+        n_hits = 1 + 5 * cap
+        n_intra = B * (1 + 2 * k_intra) if k_intra > 0 else 0
+        dev = g_kf.device
+        buf = getattr(self, "_round_buf", None)
+        if buf is None or buf[0].numel() < n_hits + n_intra or buf[0].device != dev:
+            buf = (torch.empty(n_hits + n_intra, dtype=torch.float64, device=dev),
+                   torch.empty(n_hits + n_intra, dtype=torch.float64).pin_memory())
+            self._round_buf = buf
+        d_out, h_out = buf
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        g_kf, g_sims, all_ids = g_kf.contiguous(), g_sims.contiguous(), all_ids.contiguous()
+        _lib.check(lib.cslam_swarm_hits(R, B, kx, _lib.ptr(g_kf), _lib.ptr(g_sims), _lib.ptr(all_ids), thr,
+                                        _lib.ptr(d_out), cap, stream))
+        if k_intra > 0:
+            own_idx, own_kf, own_sims = own_idx.contiguous(), own_kf.contiguous(), own_sims.contiguous()
+            _lib.check(lib.cslam_swarm_intra(B, own_idx.shape[1], k_intra, int(rows_before), _lib.ptr(own_idx),
+                                             _lib.ptr(own_kf), _lib.ptr(own_sims),
+                                             ctypes.c_void_p(d_out.data_ptr() + 8 * n_hits), stream))
+        h_out[:n_hits + n_intra].copy_(d_out[:n_hits + n_intra], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        host = h_out.numpy()
+        n = int(host[0])
+        hits = host[1:1 + 5 * n].reshape(n, 5).copy()
+        intra = host[n_hits:n_hits + n_intra].reshape(B, 1 + 2 * k_intra).copy() if k_intra > 0 else None
+        return hits, intra
+
+    @staticmethod
+    def _filter_round_host(g_kf, g_sims, all_ids, thr, own_idx, own_kf, own_sims, rows_before, k_intra):
+        R, RB, kx = g_kf.shape
+        B = RB // R
+        kf = g_kf.numpy().reshape(R, R, B, kx)[:, :, :, 0].transpose(1, 2, 0)      # [query robot, b, pool]
+        sm = g_sims.numpy().reshape(R, R, B, kx)[:, :, :, 0].transpose(1, 2, 0)
+        ids = all_ids.numpy()
+        robots = np.arange(R)
+        with np.errstate(invalid="ignore"):
+            hit = (kf >= 0) & (sm >= thr) & (robots[:, None, None] != robots[None, None, :])
+        qq, bb, gg = np.nonzero(hit)
+        hits = np.stack([qq, ids[qq, bb], gg, kf[qq, bb, gg], sm[qq, bb, gg]], axis=1).astype(np.float64) \
+            if len(qq) else np.zeros((0, 5))
+        intra = None
+        if k_intra > 0:
+            oi, ok, os_ = own_idx.numpy(), own_kf.numpy(), own_sims.numpy()
+            intra = np.zeros((B, 1 + 2 * k_intra))
+            for b in range(B):
+                keep = (oi[b] >= 0) & (oi[b] < rows_before + b)
+                kk, ss = ok[b][keep][:k_intra], os_[b][keep][:k_intra]
+                intra[b, 0] = len(kk)
+                intra[b, 1:1 + len(kk)] = kk
+                intra[b, 1 + k_intra:1 + k_intra + len(kk)] = ss
+        return hits, intra
 
     def select_candidates(self, number_of_candidates, is_neighbor_in_range,
                           greedy_initialization=True):

@@ -187,6 +187,24 @@ int cslam_fiedler_csr(int n, const int32_t* indptr, const int32_t* indices, cons
                       double tol, int block_size, int device, double* lambda2, double* vec_out,
                       int* iters_out);
 
+/* ---- (e) multi-robot round: filters on the all-gathered per-shard top-k ------------------ *
+ * Device pointers; async on `stream`.  Replace the host loops of
+ * cslam/loop_closure_sparse_matching.py:45-53,62-72 (similarity gate on the best match of a
+ * keyframe in every OTHER robot's pool) and :74-92 (intra-robot matches among the rows that
+ * were in the pool before the keyframe was added).
+ * cslam_swarm_hits: g_kf/g_sims [R pools][R*B queries][kx] as gathered (column 0 = best match,
+ *   keyframe id -1 / similarity NaN = empty pool), all_ids [R][B] keyframe ids of the queries.
+ *   out[0] = number of hits n, out[1 + 5 t ..] = (query robot, query keyframe, pool robot,
+ *   matched keyframe, similarity) of hit t in the reference's order (query robot, keyframe, pool
+ *   robot); at most `cap` hits are written.
+ * cslam_swarm_intra: idx/kf/sims [B][k_search] search results of the rank's own B keyframes
+ *   (pool rows, keyframe ids, similarities; best first) in the pool that already contains them;
+ *   out [B][1 + 2 k_keep] = (count, kept keyframe ids, kept similarities). */
+int cslam_swarm_hits(int R, int B, int kx, const int64_t* d_g_kf, const double* d_g_sims,
+                     const int64_t* d_all_ids, double threshold, double* d_out, int cap, void* stream);
+int cslam_swarm_intra(int B, int k_search, int k_keep, int64_t rows_before, const int64_t* d_idx,
+                      const int64_t* d_kf, const double* d_sims, double* d_out, void* stream);
+
 /* Test hook: the small generalised eigenproblem GA y = theta GB y (s x s, row-major with a
  * leading dimension of 6; 1 <= m <= 2 smallest pairs) that the eigen-solver solves once per
  * iteration, by one warp, `reps` times.  impl 1 = register-resident solver (entry-per-lane

@@ -1,5 +1,8 @@
-"""Run under torchrun on >= 2 GPUs: the NCCL multi-robot path (cslam_b200/swarm.py) against a
-single-GPU restatement with one pool per robot on rank 0.  Prints SWARM_OK on success."""
+"""Run under torchrun on >= 2 GPUs: the NCCL multi-robot path (cslam_b200/swarm.py, replacing the
+DDS broadcasts of cslam/global_descriptor_loop_closure_detection.py:198-289,407-433) against the
+ORACLE: one `oracle.nns.NNSOracle` pool per robot on rank 0, driven with the reference's
+per-keyframe sequence (cslam/loop_closure_sparse_matching.py:36-92).  Also checks that every rank
+ends up with the identical candidate table.  Prints SWARM_OK on success."""
 import os
 import sys
 
@@ -8,7 +11,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from cslam_b200.nns_matching import NearestNeighborsMatching
+from oracle.nns import NNSOracle
 from cslam_b200.swarm import SwarmExchange, SwarmLoopClosureMatching
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -37,12 +40,13 @@ for t, x in enumerate(stream):
 
 ok = True
 if rank == 0:
-    pools = [NearestNeighborsMatching(device=local) for _ in range(world)]
+    pools = [NNSOracle() for _ in range(world)]
     exp_edges, exp_intra = [], []
     for t, x in enumerate(stream):
         before = pools[0].n
         for r in range(world):
-            pools[r].add_items(x[r], list(range(t * B, (t + 1) * B)))
+            for b in range(B):
+                pools[r].add_item(x[r, b], t * B + b)
         for q in range(world):
             for b in range(B):
                 for g in range(world):
@@ -56,15 +60,21 @@ if rank == 0:
             keep = [i for i in ids if i < before + b][:5]
             exp_intra.append((t * B + b, keep))
     ok = [e[:4] for e in edges] == [e[:4] for e in exp_edges] and \
-        np.allclose([e[4] for e in edges], [e[4] for e in exp_edges], atol=1e-9) and intra == exp_intra
+        np.allclose([e[4] for e in edges], [e[4] for e in exp_edges], atol=1e-6) and intra == exp_intra
     print(f"edges {len(edges)} expected {len(exp_edges)} intra {len(intra)}")
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-keys = sorted(sw.candidate_selector.candidate_edges.keys())
-cnt = torch.tensor([len(keys)], device=dev)
-lo, hi = cnt.clone(), cnt.clone()
+# identical candidate tables on every rank: a digest of (key, weight) in key order
+import hashlib
+cand = sw.candidate_selector.candidate_edges
+keys = sorted(cand.keys())
+h = hashlib.sha256(repr([(k, float(cand[k].weight).hex()) for k in keys]).encode()).digest()
+dig = torch.tensor([int.from_bytes(h[:7], "big"), len(keys)], device=dev, dtype=torch.int64)
+lo, hi = dig.clone(), dig.clone()
 dist.all_reduce(lo, op=dist.ReduceOp.MIN)
 dist.all_reduce(hi, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print("SWARM_OK" if int(flag) == 1 and int(lo) == int(hi) and len(edges) > 0 else "SWARM_FAIL")
+    same = bool((lo == hi).all())
+    print(f"world {world}: candidate tables identical on all ranks: {same} ({len(keys)} candidates)")
+    print("SWARM_OK" if int(flag) == 1 and same and len(edges) > 0 else "SWARM_FAIL")
 dist.destroy_process_group()

@@ -83,7 +83,27 @@ class TwoLevel:
         return y + self.tri(R - self.L @ y)
 
 
-def lobpcg(L, m, prec, tol=1e-10, max_iters=3000, inner=0, inner_omega=None, X0=None, seed=7, want_x=False):
+def two_stage_rr(S, AS, m):
+    """The restricted Rayleigh-Ritz step of rr_two_stage (csrc/mac.cu): per column c the lowest
+    pair on span{x_c, w_c, p_c} (3 x 3), then the m x m problem on the results.  Returns
+    (theta [m], Y [3m, m]) like the full step."""
+    nb = S.shape[1] // m
+    Y6 = np.zeros((S.shape[1], m))
+    for c in range(m):
+        idx = [b * m + c for b in range(nb)]
+        Sc, ASc = S[:, idx], AS[:, idx]
+        d = 1.0 / np.sqrt((Sc * Sc).sum(axis=0))
+        GA, GB = (Sc.T @ ASc) * np.outer(d, d), (Sc.T @ Sc) * np.outer(d, d)
+        lam, Y = eigh(0.5 * (GA + GA.T), 0.5 * (GB + GB.T))
+        Y6[idx, c] = Y[:, 0] * d
+    U, AU = S @ Y6, AS @ Y6
+    GA, GB = U.T @ AU, U.T @ U
+    lam, Y2 = eigh(0.5 * (GA + GA.T), 0.5 * (GB + GB.T))
+    return lam[:m], Y6 @ Y2
+
+
+def lobpcg(L, m, prec, tol=1e-10, max_iters=3000, inner=0, inner_omega=None, X0=None, seed=7, want_x=False,
+           rr="full"):
     """Returns (theta0, iterations, SpMM count).  inner > 0: W = result of `inner` extra steps of
     preconditioned Richardson/Chebyshev on (L - theta I) w = r starting from prec(r)."""
     n = L.shape[0]
@@ -111,6 +131,14 @@ def lobpcg(L, m, prec, tol=1e-10, max_iters=3000, inner=0, inner_omega=None, X0=
         S = [X, W] + ([P] if P is not None else [])
         AS = [AX, AW] + ([AP] if P is not None else [])
         S, AS = np.hstack(S), np.hstack(AS)
+        if rr == "two-stage" and P is not None:
+            th, Y = two_stage_rr(S, AS, m)
+            Pn = S[:, m:] @ Y[m:]
+            APn = AS[:, m:] @ Y[m:]
+            X = X @ Y[:m] + Pn
+            AX = AX @ Y[:m] + APn
+            P, AP = Pn, APn
+            continue
         # column scaling like the GPU solve
         d = 1.0 / np.sqrt((S * S).sum(axis=0))
         GA, GB = (S.T @ AS) * np.outer(d, d), (S.T @ S) * np.outer(d, d)
@@ -172,7 +200,8 @@ def main():
         print(f"n = {n}, {mc} candidates, budget {k}: {a.fw} Frank-Wolfe iterations, warm-started solves")
         base = None
         hats = {h: chain_hats(n, R, Pn, h) for h in (128, 64, 32)}
-        for label, kw in (("block 2 (the GPU solver)", dict(m=2)), ("block 1", dict(m=1)),
+        for label, kw in (("block 2 (the GPU solver)", dict(m=2)), ("block 2, two-stage Rayleigh-Ritz", dict(m=2, rr="two-stage")),
+                          ("block 1", dict(m=1)),
                           ("block 2 + 1 smoothing step", dict(m=2, inner=1)),
                           ("block 1 + 1 smoothing step", dict(m=1, inner=1)),
                           ("block 2, two-level h=128", dict(m=2, make_prec=lambda L: TwoLevel(L, hats[128]))),

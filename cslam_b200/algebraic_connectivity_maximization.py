@@ -425,7 +425,12 @@ class AlgebraicConnectivityMaximization(object):
         answer = w_init.copy()
         for trial in range(nb_candidates_to_choose):
             try:
-                answer = mac.fw_subset(w_init, nb_candidates_to_choose, max_iters=self.max_iters)[0]
+                start = np.flatnonzero(w_init > 0.0)
+                chosen, _, _ = mac.fw_subset_sparse(start, np.asarray(w_init, dtype=np.float64)[start],
+                                                    nb_candidates_to_choose, max_iters=self.max_iters,
+                                                    want_support=False)
+                answer = np.zeros(len(w_init))
+                answer[chosen] = 1.0
                 self.last_mac_trials = trial
                 return answer
             except SingularLaplacianError:

@@ -1921,7 +1921,9 @@ struct PersistArgs {
   long long* prof;       // optional [8] cycle counters of CTA 0 (phases 1-5, RR, barriers)
 };
 
-template <int CH, int T>
+// MB = block size of the eigen-solver as a compile-time constant: every `c < m` guard below folds
+// away (fewer instructions in a loop body whose instruction fetch is a measured cost).
+template <int CH, int T, int MB>
 __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   constexpr int NW = T / 32;
   __shared__ double shA[32];
@@ -1950,7 +1952,8 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x, nb_grid = gridDim.x;
-  const int n = a.n, m = a.m, ld = a.ld;
+  const int n = a.n, ld = a.ld;
+  constexpr int m = MB;
   const int row0 = b * a.rpb + tid * CH;
   const int row_end = min(n, (b + 1) * a.rpb);
   // The matrix does not change during the solve: stage this CTA's (contiguous) slice of both
@@ -2536,6 +2539,299 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 
 #undef GRID_SYNC
 
+// ------------------------------------------------------------------ fused matrix set-up
+// Everything an eigen-solve needs from the current w in ONE cooperative kernel: the adjacency of
+// the active candidates from the support list (degree count -> scan -> fill -> per-row sort by
+// candidate id + Laplacian values: k_act_* above), the Laplacian diagonal and ||L||_inf
+// (k_lap_diag, k_max_reduce) and the LDL^T factorisation of its tridiagonal part (k_fac_a/b/c:
+// Moebius scan of the pivots).  Five grid barriers instead of twelve stream operations
+// (~220 us of launch latency per Frank-Wolfe iteration).  CTA b owns rows [b rpb, (b+1) rpb),
+// thread t the RPT consecutive rows from b rpb + t RPT on.
+struct PrepareArgs {
+  int n, rpb;
+  const int *ip0, *c0;
+  const double* v0;
+  int *ip1, *c1, *src1;
+  double* v1;
+  const int *sup, *sup_cnt, *ci, *cj;
+  const double *w, *cw;
+  int* deg;                 // [n] zero at entry and at exit
+  double *diag, *dpiv, *lfac, *lnorm;
+  int* bad;
+  int* ctot;                // [grid]
+  M2* cagg;                 // [grid]
+  unsigned int* barrier;    // zero at launch
+  unsigned long long* dbg;  // optional [8]: globaltimer ns of CTA 0 at the phase boundaries (accumulated)
+};
+
+// inclusive scan over the 256 threads of a CTA, product order later * earlier
+__device__ __forceinline__ M2 block_scan_m2(M2 acc, M2* sh_warp /*[8]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    M2 other;
+    other.a = __shfl_up_sync(0xffffffffu, acc.a, o);
+    other.b = __shfl_up_sync(0xffffffffu, acc.b, o);
+    other.c = __shfl_up_sync(0xffffffffu, acc.c, o);
+    other.d = __shfl_up_sync(0xffffffffu, acc.d, o);
+    if (lane >= o) acc = m2_mul(acc, other);
+  }
+  if (lane == 31) sh_warp[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    M2 run = sh_warp[0];
+    for (int q = 1; q < 8; ++q) {
+      run = m2_mul(sh_warp[q], run);
+      sh_warp[q] = run;
+    }
+  }
+  __syncthreads();
+  if (warp > 0) acc = m2_mul(acc, sh_warp[warp - 1]);
+  __syncthreads();
+  return acc;
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(256, 1) k_fw_prepare(PrepareArgs a) {
+  constexpr int T = 256;
+  __shared__ int sh_iw[8];
+  __shared__ int sh_ctot[192];
+  __shared__ M2 sh_m2[8];
+  __shared__ M2 sh_cta[T];
+  __shared__ double sh_max[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x, G = gridDim.x;
+  const int n = a.n;
+  unsigned int epoch = 0;
+  const int r_first = b * a.rpb + tid * RPT;
+  const int r_hi = min(n, (b + 1) * a.rpb);
+  unsigned long long t_prev = 0;
+  auto gt = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+  auto tick = [&](int slot) {
+    if (a.dbg && b == 0 && tid == 0) {
+      const unsigned long long t = gt();
+      if (slot >= 0) a.dbg[slot] += t - t_prev;
+      t_prev = t;
+    }
+  };
+  tick(-1);
+  // ---- A: degrees of the support graph
+  if (b == 0 && tid == 0) {
+    *a.lnorm = 0.0;
+    *a.bad = 0;
+  }
+  const int cnt = *a.sup_cnt;
+  for (int t = b * T + tid; t < cnt; t += G * T) {
+    const int e = a.sup[t];
+    const int i = a.ci[e], j = a.cj[e];
+    if (i == j) continue;   // self loops cancel in a Laplacian
+    atomicAdd(&a.deg[i], 1);
+    atomicAdd(&a.deg[j], 1);
+  }
+  grid_barrier(a.barrier, epoch, G);
+  tick(0);
+  // ---- B: row pointers = exclusive scan of the degrees
+  int d[RPT], tsum = 0;
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int r = r_first + j;
+    d[j] = r < r_hi ? __ldcg(a.deg + r) : 0;
+    tsum += d[j];
+  }
+  int inc = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) sh_iw[warp] = inc;
+  __syncthreads();
+  int wbase = 0, cta_total = 0;
+  for (int q = 0; q < 8; ++q) {
+    if (q < warp) wbase += sh_iw[q];
+    cta_total += sh_iw[q];
+  }
+  if (tid == 0) a.ctot[b] = cta_total;
+  grid_barrier(a.barrier, epoch, G);
+  for (int q = tid; q < G; q += T) sh_ctot[q] = __ldcg(a.ctot + q);
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int q = 0; q < G; ++q) {
+    if (q < b) base += sh_ctot[q];
+    total += sh_ctot[q];
+  }
+  int start[RPT];
+  {
+    int run = base + wbase + inc - tsum;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int r = r_first + j;
+      start[j] = run;
+      if (r < r_hi) {
+        a.ip1[r] = run;
+        a.deg[r] = 0;   // reused as the fill cursor
+        if (r == n - 1) a.ip1[n] = total;
+      }
+      run += d[j];
+    }
+  }
+  grid_barrier(a.barrier, epoch, G);
+  tick(1);
+  // ---- C: fill (entry order inside a row is whatever the atomics give; sorted in D)
+  for (int t = b * T + tid; t < cnt; t += G * T) {
+    const int e = a.sup[t];
+    const int i = a.ci[e], j = a.cj[e];
+    if (i == j) continue;
+    int p = __ldcg(a.ip1 + i) + atomicAdd(&a.deg[i], 1);
+    a.c1[p] = j;
+    a.src1[p] = e;
+    p = __ldcg(a.ip1 + j) + atomicAdd(&a.deg[j], 1);
+    a.c1[p] = i;
+    a.src1[p] = e;
+  }
+  grid_barrier(a.barrier, epoch, G);
+  tick(2);
+  // ---- D: own rows: sort by candidate id, Laplacian values, diagonal, pivot-recurrence chunk
+  // The CTA's rows own a CONTIGUOUS entry range [base, base + cta_total): staged in shared memory
+  // with one coalesced load (a thread walking its row in global memory pays one L2 round trip
+  // per entry: ~30 us for a hub pose with 40 active edges, and the whole grid waits for it),
+  // sorted there, values computed with one entry per thread, written back coalesced.
+  constexpr int ECAP = 2048;
+  __shared__ int sh_src[ECAP], sh_col[ECAP];
+  __shared__ double sh_val[ECAP];
+  const bool staged = cta_total <= ECAP;
+  int* esrc = staged ? sh_src - base : a.src1;      // indexable by the global entry position
+  int* ecol = staged ? sh_col - base : a.c1;
+  double* eval = staged ? sh_val - base : a.v1;
+  if (staged) {
+    for (int p = base + tid; p < base + cta_total; p += T) {
+      esrc[p] = __ldcg(a.src1 + p);
+      ecol[p] = __ldcg(a.c1 + p);
+    }
+    __syncthreads();
+  }
+  double dg[RPT], low[RPT], rmax = 0.0;
+  M2 acc = {1.0, 0.0, 0.0, 1.0};
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int r = r_first + j;
+    dg[j] = 0.0;
+    low[j] = 0.0;
+    if (r >= r_hi) continue;
+    const int p0 = start[j], p1 = start[j] + d[j];
+    // Shell sort (gaps 40, 13, 4, 1): rows are a handful of entries except for a few hub poses
+    // with dozens of active edges.  (Unstaged fallback: plain L1-cached accesses - nothing of
+    // these arrays was read by this SM before the grid barrier above, and the thread re-reads
+    // only its own stores; with ld.cg every compare was an L2 round trip, 390 us per launch.)
+    for (int gap = (p1 - p0 > 40) ? 40 : (p1 - p0 > 13) ? 13 : (p1 - p0 > 4) ? 4 : 1; gap >= 1;
+         gap = gap == 40 ? 13 : gap == 13 ? 4 : gap == 4 ? 1 : 0) {
+      for (int p = p0 + gap; p < p1; ++p) {
+        const int e = esrc[p], c = ecol[p];
+        int q = p - gap;
+        while (q >= p0 && esrc[q] > e) {
+          esrc[q + gap] = esrc[q];
+          ecol[q + gap] = ecol[q];
+          q -= gap;
+        }
+        esrc[q + gap] = e;
+        ecol[q + gap] = c;
+      }
+    }
+  }
+  __syncthreads();
+  // Laplacian values, one entry per thread and round (two gathers per entry: w, weight)
+  for (int p = base + tid; p < base + cta_total; p += T) {
+    const int e = esrc[p];
+    const double we = a.w[e];
+    // combined_laplacian (mac.py:72-74): only w > tol contributes, with weight w_e * c_e
+    const double v = we > 1e-10 ? -__dmul_rn(we, a.cw[e]) : 0.0;
+    eval[p] = v;
+    if (staged) {
+      a.src1[p] = e;
+      a.c1[p] = ecol[p];
+      a.v1[p] = v;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int r = r_first + j;
+    if (r >= r_hi) continue;
+    const int p0 = start[j], p1 = start[j] + d[j];
+    // row sum in the order of k_lap_diag (fixed entries, then active ones); L[r][r-1] summed in
+    // the same order as row r-1 sums L[r-1][r] (both rows list their common edges in edge order)
+    double s = 0.0, lo = 0.0;
+    for (int p = a.ip0[r]; p < a.ip0[r + 1]; ++p) {
+      const double v = a.v0[p];
+      s += v;
+      if (a.c0[p] == r - 1) lo += v;
+    }
+    for (int p = p0; p < p1; ++p) {
+      const double v = eval[p];
+      s += v;
+      if (ecol[p] == r - 1) lo += v;
+    }
+    a.deg[r] = 0;
+    a.diag[r] = -s;
+    dg[j] = -s;
+    low[j] = lo;
+    rmax = fmax(rmax, -2.0 * s);   // |diag| + sum |offdiag|
+    const M2 mi = {dg[j], -lo * lo, 1.0, 0.0};
+    acc = m2_mul(mi, acc);
+  }
+  for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+  if (lane == 0) sh_max[warp] = rmax;
+  const M2 inc_m = block_scan_m2(acc, sh_m2);     // (contains __syncthreads)
+  if (tid == 0) {
+    double m = sh_max[0];
+    for (int q = 1; q < 8; ++q) m = fmax(m, sh_max[q]);
+    atomicMax(reinterpret_cast<unsigned long long*>(a.lnorm),
+              static_cast<unsigned long long>(__double_as_longlong(m)));
+  }
+  sh_cta[tid] = inc_m;
+  if (tid == T - 1) a.cagg[b] = inc_m;
+  grid_barrier(a.barrier, epoch, G);
+  tick(3);
+  // ---- E: exact incoming pivot of every thread, re-walk
+  M2 mine = {1.0, 0.0, 0.0, 1.0};
+  if (tid < G) {
+    const double* src = reinterpret_cast<const double*>(a.cagg + tid);
+    mine.a = __ldcg(src);
+    mine.b = __ldcg(src + 1);
+    mine.c = __ldcg(src + 2);
+    mine.d = __ldcg(src + 3);
+  }
+  const M2 thread_excl = tid > 0 ? sh_cta[tid - 1] : M2{1.0, 0.0, 0.0, 1.0};
+  __syncthreads();
+  const M2 cta_inc = block_scan_m2(mine, sh_m2);
+  sh_cta[tid] = cta_inc;
+  __syncthreads();
+  M2 pre = thread_excl;
+  if (b > 0) pre = m2_mul(thread_excl, sh_cta[b - 1]);
+  double dprev = pre.a / pre.c;   // (d, 1) ~ P (d_{-1}, 1) with the start vector (1, 0)
+  bool any_bad = false;
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int r = r_first + j;
+    if (r >= r_hi) continue;
+    double dd, l;
+    if (r == 0) {
+      dd = dg[j];
+      l = 0.0;
+    } else {
+      l = low[j] / dprev;
+      dd = dg[j] - low[j] * l;
+    }
+    any_bad = any_bad || !(dd > 0.0) || !isfinite(dd);
+    a.dpiv[r] = dd;
+    a.lfac[r] = l;
+    dprev = dd;
+  }
+  if (any_bad) *a.bad = 1;
+  tick(4);
+  if (a.dbg && b == 0 && tid == 0) a.dbg[7] += 1;
+}
+
 // ------------------------------------------------------------------ fused Frank-Wolfe tail
 // Everything between two eigen-solves of fw_subset (mac.py:212-230) in ONE cooperative kernel:
 //   grad_i = grad_from_fiedler(vec_i)                       -> g
@@ -2574,6 +2870,7 @@ struct SelectArgs {
   int* sup_cnt;
   FwState* st;
   unsigned int* barrier;        // zero at launch
+  unsigned long long* dbg;      // optional [8..16): globaltimer ns of CTA 0 per phase (accumulated)
 };
 
 __global__ void __launch_bounds__(256, 1) k_fw_select(SelectArgs a) {
@@ -2581,37 +2878,48 @@ __global__ void __launch_bounds__(256, 1) k_fw_select(SelectArgs a) {
   __shared__ __align__(16) unsigned int sh_hist[NB];
   __shared__ long long sh_chunk[T];
   __shared__ int sh_best_d;
-  __shared__ long long sh_best_acc;
+  __shared__ long long sh_best_acc, sh_best_cnt;
   __shared__ double sh_red[8][2];
   __shared__ int sh_warp[8];
-  __shared__ int sh_base, sh_tie;
+  __shared__ int sh_base, sh_tie, sh_any;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x, G = gridDim.x;
   unsigned int epoch = 0;
   const long long e0 = static_cast<long long>(b) * a.chunk;
   const long long e1 = min(a.mc, e0 + a.chunk);
-  const int old_cnt = *a.sup_cnt;   // read before anybody may reset it (first barrier below)
+  const int old_cnt = *a.sup_cnt;   // read before anybody may change it (first barrier below)
+  unsigned long long t_prev = 0;
+  auto tick = [&](int slot) {
+    if (a.dbg && b == 0 && tid == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (slot >= 0) a.dbg[slot] += t - t_prev;
+      t_prev = t;
+    }
+  };
+  tick(-1);
 
-  // ---- pass 0 prologue: gradient of the own range, sum of g*w, (alpha = 1) clear the support flags
-  double acc_gw = 0.0;
+  // ---- gradient of the own range
   for (long long e = e0 + tid; e < e1; e += T) {
     // mac.py:123-129: kdelta = weight_k * (v_i - v_j); grad[k] = kdelta * (v_i - v_j)
     const double d = __dsub_rn(a.v[a.ci[e]], a.v[a.cj[e]]);
-    const double ge = __dmul_rn(__dmul_rn(a.cw[e], d), d);
-    a.g[e] = ge;
-    acc_gw = fma(ge, a.w[e], acc_gw);
+    a.g[e] = __dmul_rn(__dmul_rn(a.cw[e], d), d);
   }
-
-  // ---- radix select of the k-th largest key
+  tick(8);
+  // ---- radix select of the k-th largest key.  A pass ends the search early when the bucket of
+  //      the k-th key holds exactly the keys still needed: then "key >= bucket" IS the selection.
   uint64_t prefix = 0, mask = 0;
   long long remaining = a.k;
+  bool whole_bucket = false;
   if (a.k > 0) {
     int pass = 0;
-    for (int shift = 55; shift >= 0; shift -= BITS, ++pass) {
+    for (int shift = 55; shift >= 0 && !whole_bucket; shift -= BITS, ++pass) {
       for (int i = tid; i < NB; i += T) sh_hist[i] = 0;
       __syncthreads();
       for (long long e = e0 + tid; e < e1; e += T) {
         const uint64_t key = f64_to_key(a.g[e]);
+        // (warp-aggregating these with __match_any_sync was measured: 14.7 us instead of 8.0 us
+        //  for the first pass - the shared-memory atomic unit handles the hot bins better)
         if ((key & mask) == prefix) atomicAdd(&sh_hist[(key >> shift) & (NB - 1u)], 1u);
       }
       __syncthreads();
@@ -2645,25 +2953,39 @@ __global__ void __launch_bounds__(256, 1) k_fw_select(SelectArgs a) {
       if (found > 0 && found == sh_best_d) sh_best_acc = found_acc;
       if (tid == 0 && sh_best_d == 0) sh_best_acc = above + mine - sh_hist[0];
       __syncthreads();
+      if (tid == 0) sh_best_cnt = sh_hist[sh_best_d];
+      __syncthreads();
       prefix |= static_cast<uint64_t>(sh_best_d) << shift;
       mask |= static_cast<uint64_t>(NB - 1u) << shift;
       remaining -= sh_best_acc;
+      whole_bucket = sh_best_cnt == remaining && shift > 0;
       __syncthreads();
+      tick(pass == 0 ? 9 : 10);
     }
   }
+  // after an early exit `prefix` has zero low bits: every key of the bucket is >= it and all of
+  // them are taken; otherwise prefix is the k-th key itself and `remaining` ties are taken
   const uint64_t kth = prefix;
-  const long long need_eq = a.k > 0 ? remaining : 0;   // ties at the k-th key to take, in index order
+  const long long need_eq = (a.k > 0 && !whole_bucket) ? remaining : 0;
 
-  // ---- counts and partial sums of the own range
+  // ---- counts and partial sums: own range (selected gradients), support (grad @ w)
   unsigned int c_gt = 0, c_eq = 0;
-  double acc_sel = 0.0;
+  double acc_sel = 0.0, acc_gw = 0.0;
   if (a.k > 0)
     for (long long e = e0 + tid; e < e1; e += T) {
       const double ge = a.g[e];
       const uint64_t key = f64_to_key(ge);
-      if (key > kth) { ++c_gt; acc_sel += ge; }
-      c_eq += key == kth;
+      const bool gt = whole_bucket ? key >= kth : key > kth;
+      if (gt) { ++c_gt; acc_sel += ge; }
+      c_eq += (!whole_bucket && key == kth);
     }
+  // w is zero outside its support: grad @ w over the support list (g complete after the barriers
+  // of the radix passes; fixed assignment of entries to threads -> deterministic sum)
+  if (a.k == 0) grid_barrier(a.barrier, epoch, G);   // (the radix passes did not run: g must be complete)
+  for (int t = b * T + tid; t < old_cnt; t += G * T) {
+    const int e = a.sup[t];
+    acc_gw = fma(__ldcg(a.g + e), a.w[e], acc_gw);
+  }
   // fixed-order CTA reductions
   for (int o = 16; o > 0; o >>= 1) {
     c_gt += __shfl_xor_sync(0xffffffffu, c_gt, o);
@@ -2693,6 +3015,7 @@ __global__ void __launch_bounds__(256, 1) k_fw_select(SelectArgs a) {
     a.part[2 * b + 1] = s1;
   }
   grid_barrier(a.barrier, epoch, G);
+  tick(11);
   // ---- every CTA: offsets of its range in the ordered output, the dual value, the gap test
   long long tie_base = 0, out_base = 0;
   double sum_sel = 0.0, sum_gw = 0.0;
@@ -2742,27 +3065,24 @@ __global__ void __launch_bounds__(256, 1) k_fw_select(SelectArgs a) {
   int out = sh_base;
   long long tie_rank = sh_tie;
   __syncthreads();
-  if (a.alpha == 1.0 && !done) {
-    // w becomes exactly s_i: the previous support is forgotten (the decision is grid-uniform)
-    for (int t = b * T + tid; t < old_cnt; t += G * T) a.flag[a.sup[t]] = 0;
-    grid_barrier(a.barrier, epoch, G);
-    if (b == 0 && tid == 0) *a.sup_cnt = 0;
-    grid_barrier(a.barrier, epoch, G);
-  }
-  // ---- ordered walk of the own range: ids of s_i, Frank-Wolfe update of w, support
+  tick(12);
+  // ---- ordered walk of the own range: ascending ids of s_i; selected entries are marked in the
+  //      support flags (bit 1) for the sparse update below.  Rounds without a candidate are skipped.
   for (long long base = e0; base < e1; base += T) {
     const long long e = base + tid;
     bool sel = false, is_eq = false;
     if (e < e1 && a.k > 0) {
       const uint64_t key = f64_to_key(a.g[e]);
-      is_eq = key == kth;
-      sel = key > kth;
+      is_eq = !whole_bucket && key == kth;
+      sel = whole_bucket ? key >= kth : key > kth;
     }
+    if (tid == 0) sh_any = 0;
+    __syncthreads();
+    if (sel || is_eq) sh_any = 1;
+    __syncthreads();
+    if (!sh_any) continue;     // CTA-uniform
     const unsigned meq = __ballot_sync(0xffffffffu, is_eq);
-    const unsigned mgt = __ballot_sync(0xffffffffu, sel);
-    if (lane == 0) {
-      sh_warp[warp] = __popc(meq);
-    }
+    if (lane == 0) sh_warp[warp] = __popc(meq);
     __syncthreads();
     long long my_tie = tie_rank + __popc(meq & ((1u << lane) - 1u));
     int eq_total = 0;
@@ -2773,7 +3093,6 @@ __global__ void __launch_bounds__(256, 1) k_fw_select(SelectArgs a) {
     sel = sel || (is_eq && my_tie < need_eq);
     __syncthreads();
     const unsigned msel = __ballot_sync(0xffffffffu, sel);
-    (void)mgt;
     if (lane == 0) sh_warp[warp] = __popc(msel);
     __syncthreads();
     int pos = out + __popc(msel & ((1u << lane) - 1u));
@@ -2785,20 +3104,40 @@ __global__ void __launch_bounds__(256, 1) k_fw_select(SelectArgs a) {
     if (sel) {
       a.slist[pos] = static_cast<int>(e);
       if (a.trace) a.trace[pos] = static_cast<int>(e);
-    }
-    if (e < e1 && !done) {
-      // mac.py:230: w_i = w_i + alpha * (s_i - w_i), same operation order, no contraction
-      const double we = a.w[e];
-      if (sel || we != 0.0) a.w[e] = __dadd_rn(we, __dmul_rn(a.alpha, __dsub_rn(sel ? 1.0 : 0.0, we)));
-      if (sel && !__ldcg(a.flag + e)) {
-        a.flag[e] = 1;
-        a.sup[atomicAdd(a.sup_cnt, 1)] = static_cast<int>(e);
-      }
+      if (!done) a.flag[e] |= 2;     // only this thread touches flag[e] here
     }
     out += sel_total;
     tie_rank += eq_total;
     __syncthreads();
   }
+  tick(13);
+  if (done) return;   // grid-uniform: gap reached, w and its support stay as they are (mac.py:223-225)
+  grid_barrier(a.barrier, epoch, G);
+  // ---- w_i += alpha (s_i - w_i) (mac.py:229-230; same operation order, no contraction), sparse:
+  //      w is zero outside support + selection.  Old support entries first ...
+  for (int t = b * T + tid; t < old_cnt; t += G * T) {
+    const int e = a.sup[t];
+    const unsigned char fl = __ldcg(a.flag + e);
+    const double we = a.w[e];
+    a.w[e] = __dadd_rn(we, __dmul_rn(a.alpha, __dsub_rn((fl & 2) ? 1.0 : 0.0, we)));
+    if (a.alpha == 1.0) a.flag[e] = fl & 2;   // w becomes exactly s_i: the old support is forgotten
+  }
+  if (a.alpha == 1.0) {
+    grid_barrier(a.barrier, epoch, G);
+    if (b == 0 && tid == 0) *a.sup_cnt = 0;
+  }
+  grid_barrier(a.barrier, epoch, G);
+  // ... then the selected ones: new entries join the support with w = 0 + alpha (1 - 0)
+  for (int t = b * T + tid; t < a.k; t += G * T) {
+    const int e = __ldcg(a.slist + t);
+    const unsigned char fl = __ldcg(a.flag + e);
+    if (!(fl & 1)) {
+      a.w[e] = __dadd_rn(0.0, __dmul_rn(a.alpha, __dsub_rn(1.0, 0.0)));
+      a.sup[atomicAdd(a.sup_cnt, 1)] = e;
+    }
+    a.flag[e] = 1;
+  }
+  tick(14);
 }
 
 // ------------------------------------------------------------------ solver object
@@ -2844,6 +3183,7 @@ struct FiedlerSolver {
   bool warm = false;
   double lnorm = 0.0;
   const int* extra_d2h_src = nullptr;   // optional device int copied to h_bad[1] with every solve result
+  bool matrix_prepared = false;         // diag / factors / ||L||_inf already on the device (k_fw_prepare)
   int last_iters = 0;
   bool jacobi = false;
   int64_t spmv_count = 0;
@@ -2954,8 +3294,16 @@ struct FiedlerSolver {
     const void* fn = nullptr;
     int threads = 0;
     switch (ch) {
-      case 4: fn = reinterpret_cast<const void*>(&k_lobpcg_persist<4, 256>); threads = 256; break;
-      case 8: fn = reinterpret_cast<const void*>(&k_lobpcg_persist<8, 256>); threads = 256; break;
+      case 4:
+        fn = m == 2 ? reinterpret_cast<const void*>(&k_lobpcg_persist<4, 256, 2>)
+                    : reinterpret_cast<const void*>(&k_lobpcg_persist<4, 256, 1>);
+        threads = 256;
+        break;
+      case 8:
+        fn = m == 2 ? reinterpret_cast<const void*>(&k_lobpcg_persist<8, 256, 2>)
+                    : reinterpret_cast<const void*>(&k_lobpcg_persist<8, 256, 1>);
+        threads = 256;
+        break;
       default: set_error("fiedler: bad persistent variant %d", ch); return CSLAM_ERR_INVALID;
     }
     pa.cap0 = pa.cap1 = 6144;
@@ -3235,7 +3583,9 @@ struct FiedlerSolver {
     };
     const double tp0 = prof ? now() : 0;
     const int persist_ch = persist_rows_per_thread();
-    CSLAM_TRY(prepare_matrix(/*sync_host=*/persist_ch == 0));
+    if (matrix_prepared) jacobi = false;
+    else CSLAM_TRY(prepare_matrix(/*sync_host=*/persist_ch == 0));
+    matrix_prepared = false;
     const double tp1 = prof ? now() : 0;
     t_prepare += tp1 - tp0;
     if (n < 2) {
@@ -3479,6 +3829,13 @@ struct cslam_mac {
   unsigned int *d_sel_hist = nullptr, *d_sel_pairs = nullptr, *d_sel_bar = nullptr;
   double* d_sel_part = nullptr;
   int fused_tail = -1;               // -1 unknown, 0 unavailable (multi-kernel path), 1 in use
+  // fused matrix set-up (k_fw_prepare)
+  int* d_prep_ctot = nullptr;
+  M2* d_prep_cagg = nullptr;
+  unsigned int* d_prep_bar = nullptr;
+  int fused_prepare = -1;
+  bool deg_dirty = false;            // d_deg left non-zero by the multi-kernel adjacency build
+  unsigned long long* d_dbg = nullptr;   // CSLAM_MAC_TIMELINE: in-kernel phase timers of k_fw_prepare
   int fixed_components = 0;     // connected components of the fixed graph
   std::vector<int> fixed_root;  // component label per vertex (fixed graph)
   double tol = 1e-10;
@@ -3576,6 +3933,7 @@ int mac_build_active(cslam_mac* h, int ub) {
   Adj& a = h->fs.act;
   const int gb = std::max(1, std::min(592, (ub + 255) / 256));
   CSLAM_CUDA(cudaMemsetAsync(h->d_deg, 0, static_cast<size_t>(h->n) * sizeof(int), s));
+  h->deg_dirty = true;
   k_act_count<<<gb, 256, 0, s>>>(h->d_sup, h->d_sup_cnt, h->d_ci, h->d_cj, h->d_deg);
   CSLAM_LAUNCH_CHECK();
   k_act_scan<<<1, 1024, 0, s>>>(h->n, h->d_deg, a.indptr);
@@ -3637,6 +3995,55 @@ int mac_topk(cslam_mac* h, int k) {
   return CSLAM_OK;
 }
 
+// active adjacency + diagonal + ||L||_inf + tridiagonal factors in one cooperative launch
+// (k_fw_prepare).  kPersistUnavailable: not applicable here, use mac_build_active + prepare_matrix.
+int mac_fused_prepare(cslam_mac* h) {
+  FiedlerSolver& fs = h->fs;
+  const int G = fs.num_sms;
+  if (G <= 0 || G > 192 || h->fixed_components != 1 || fs.persist_rows_per_thread() == 0) return kPersistUnavailable;
+  const int rows = (h->n + G - 1) / G;
+  const int rpt = (rows + 255) / 256;
+  if (rpt > 8) return kPersistUnavailable;
+  cudaStream_t s = h->stream;
+  CSLAM_TRY(mac_reserve_support(h, static_cast<size_t>(std::max(h->sup_ub, 1))));
+  Adj& act = fs.act;
+  PrepareArgs a;
+  a.n = h->n;
+  a.rpb = rows;
+  a.ip0 = fs.fix.indptr; a.c0 = fs.fix.cols; a.v0 = fs.fix.vals;
+  a.ip1 = act.indptr; a.c1 = act.cols; a.src1 = act.src; a.v1 = act.vals;
+  a.sup = h->d_sup; a.sup_cnt = h->d_sup_cnt; a.ci = h->d_ci; a.cj = h->d_cj;
+  a.w = h->d_w; a.cw = h->d_cw;
+  a.deg = h->d_deg;
+  a.diag = fs.diag; a.dpiv = fs.dpiv; a.lfac = fs.lfac; a.lnorm = fs.d_lnorm;
+  a.bad = fs.d_bad;
+  a.ctot = h->d_prep_ctot;
+  a.cagg = h->d_prep_cagg;
+  a.barrier = h->d_prep_bar;
+  a.dbg = h->d_dbg;
+  CSLAM_CUDA(cudaMemsetAsync(h->d_prep_bar, 0, sizeof(unsigned int), s));
+  if (h->deg_dirty) {
+    CSLAM_CUDA(cudaMemsetAsync(h->d_deg, 0, static_cast<size_t>(h->n) * sizeof(int), s));
+    h->deg_dirty = false;
+  }
+  const void* fn = rpt <= 1   ? reinterpret_cast<const void*>(&k_fw_prepare<1>)
+                   : rpt <= 2 ? reinterpret_cast<const void*>(&k_fw_prepare<2>)
+                   : rpt <= 3 ? reinterpret_cast<const void*>(&k_fw_prepare<3>)
+                   : rpt <= 4 ? reinterpret_cast<const void*>(&k_fw_prepare<4>)
+                              : reinterpret_cast<const void*>(&k_fw_prepare<8>);
+  void* args[] = {&a};
+  const cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(G), dim3(256), args, 0, s);
+  if (le != cudaSuccess) {
+    cudaGetLastError();
+    return kPersistUnavailable;
+  }
+  count_launch();
+  act.nnz = 2 * static_cast<int64_t>(h->sup_ub);
+  fs.has_act = true;
+  fs.matrix_prepared = true;
+  return CSLAM_OK;
+}
+
 // grad -> top-k -> dual/gap -> w update -> support, one cooperative launch (k_fw_select).
 // Returns kPersistUnavailable when the grid cannot be made co-resident.
 int mac_fused_tail(cslam_mac* h, int k, int it, double alpha, double gap_tol, int* trace_row) {
@@ -3663,6 +4070,7 @@ int mac_fused_tail(cslam_mac* h, int k, int it, double alpha, double gap_tol, in
   a.sup_cnt = h->d_sup_cnt;
   a.st = h->d_fwstate;
   a.barrier = h->d_sel_bar;
+  a.dbg = h->d_dbg ? h->d_dbg + 0 : nullptr;
   CSLAM_CUDA(cudaMemsetAsync(h->d_sel_hist, 0, 6 * 2048 * sizeof(unsigned int), s));
   CSLAM_CUDA(cudaMemsetAsync(h->d_sel_bar, 0, sizeof(unsigned int), s));
   void* args[] = {&a};
@@ -3718,9 +4126,18 @@ int cslam_mac_create(int num_poses, int64_t n_fixed, const int32_t* fi, const in
     cslam_mac_destroy(h);
     return st;
   };
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
-    set_error("mac_create: stream creation failed");
-    return fail(CSLAM_ERR_CUDA);
+  {
+    // Highest stream priority: a selection is a chain of ~60 dependent launches (20 eigen-solves
+    // of ~2 ms with short kernels in between) that runs next to the keyframe stream of the same
+    // robot (descriptor network, searches).  With equal priorities the cooperative eigen-solver
+    // launch waits behind whole bursts of the other stream's kernels; with priority its CTAs are
+    // placed as soon as the running kernels drain and the other stream fills the gaps instead.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
+      set_error("mac_create: stream creation failed");
+      return fail(CSLAM_ERR_CUDA);
+    }
   }
   int st = h->fs.init(num_poses, device, h->stream);
   if (st != CSLAM_OK) return fail(st);
@@ -3761,10 +4178,12 @@ int cslam_mac_create(int num_poses, int64_t n_fixed, const int32_t* fi, const in
       (st = dev_alloc(&h->d_flag, mc)) || (st = dev_alloc(&h->d_sup_cnt, 1)) ||
       (st = dev_alloc(&h->d_fwstate, 1)) || (st = dev_alloc(&h->d_sel_hist, 6 * 2048)) ||
       (st = dev_alloc(&h->d_sel_pairs, 2 * 192)) || (st = dev_alloc(&h->d_sel_part, 2 * 192)) ||
-      (st = dev_alloc(&h->d_sel_bar, 1)) ||
+      (st = dev_alloc(&h->d_sel_bar, 1)) || (st = dev_alloc(&h->d_prep_ctot, 192)) ||
+      (st = dev_alloc(&h->d_prep_cagg, 192)) || (st = dev_alloc(&h->d_prep_bar, 1)) ||
       (st = dev_alloc(&h->d_deg, static_cast<size_t>(num_poses))))
     return fail(st);
   cudaMemsetAsync(h->d_flag, 0, mc, h->stream);
+  cudaMemsetAsync(h->d_deg, 0, static_cast<size_t>(num_poses) * sizeof(int), h->stream);
   cudaMemsetAsync(h->d_sup_cnt, 0, sizeof(int), h->stream);
   h->fs.extra_d2h_src = h->d_sup_cnt;
   if (n_cand > 0) {
@@ -3793,6 +4212,10 @@ int cslam_mac_destroy(cslam_mac_t* h) {
   dev_free(h->d_deg);
   dev_free(h->d_supval);
   dev_free(h->d_trace);
+  dev_free(h->d_dbg);
+  dev_free(h->d_prep_ctot);
+  dev_free(h->d_prep_cagg);
+  dev_free(h->d_prep_bar);
   dev_free(h->d_fwstate);
   dev_free(h->d_sel_hist);
   dev_free(h->d_sel_pairs);
@@ -3934,6 +4357,10 @@ int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* in
   // CSLAM_MAC_TIMELINE=1: CUDA events on the stream at the section boundaries of every iteration
   // (no extra synchronisation): where the GPU-side time of a selection goes, gaps included
   const bool timeline = getenv("CSLAM_MAC_TIMELINE") != nullptr;
+  if (timeline && !h->d_dbg) {
+    CSLAM_TRY(dev_alloc(&h->d_dbg, 16));
+    CSLAM_CUDA(cudaMemset(h->d_dbg, 0, 16 * sizeof(unsigned long long)));
+  }
   std::vector<cudaEvent_t> tl;
   auto mark = [&]() {
     if (!timeline) return;
@@ -3945,11 +4372,19 @@ int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* in
   double* h_dual = h->fs.h_red + 2 * NPAIR;   // pinned scalar slots not used by the persistent path
   static_assert(sizeof(FwState) <= (4 * MAXM + 4) * sizeof(double), "FwState must fit the pinned slots");
   if (getenv("CSLAM_FW_FUSED") && atoi(getenv("CSLAM_FW_FUSED")) == 0) h->fused_tail = 0;
+  h->fused_prepare = (getenv("CSLAM_FW_FUSED_PREPARE") && atoi(getenv("CSLAM_FW_FUSED_PREPARE")) == 0) ? 0 : -1;
   for (; it < max_iters; ++it) {
     // f_i, vec_i = evaluate_fiedler_pair(w_i)                               (mac.py:211)
     double t0 = prof ? now() : 0;
     mark();                                   // 0: iteration start
-    CSLAM_TRY(mac_build_active(h, h->sup_ub));
+    {
+      int pst = h->fused_prepare != 0 ? mac_fused_prepare(h) : kPersistUnavailable;
+      if (pst == kPersistUnavailable) {
+        h->fused_prepare = 0;
+        pst = mac_build_active(h, h->sup_ub);
+      }
+      CSLAM_TRY(pst);
+    }
     mark();                                   // 1: active adjacency built
     double f = 0.0;
     double t1 = prof ? now() : 0;
@@ -4038,6 +4473,17 @@ int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* in
   if (prof)
     fprintf(stderr, "[cslam mac prof] build_active %.2f ms, solve %.2f ms (prepare %.2f, prologue %.2f, loop %.2f), grad+topk+dual %.2f ms, host update %.2f ms\n",
             t_act, t_solve, h->fs.t_prepare, h->fs.t_prologue, h->fs.t_loop, t_sel, t_host);
+  if (timeline && h->d_dbg) {
+    cudaStreamSynchronize(s);
+    unsigned long long hd[16] = {};
+    cudaMemcpy(hd, h->d_dbg, sizeof(hd), cudaMemcpyDeviceToHost);
+    const double nl = static_cast<double>(std::max<unsigned long long>(hd[7], 1));
+    fprintf(stderr, "[cslam mac timeline] k_fw_prepare in-kernel us per launch (CTA 0, %llu launches): count %.1f scan %.1f indptr %.1f fill %.1f rows+chunk %.1f prefix+rewalk %.1f\n",
+            hd[7], hd[0] / nl / 1e3, hd[1] / nl / 1e3, 0.0, hd[2] / nl / 1e3, hd[3] / nl / 1e3, hd[4] / nl / 1e3);
+    fprintf(stderr, "[cslam mac timeline] k_fw_select in-kernel us per launch: gradient %.1f | radix pass 0 %.1f | later passes %.1f | counts+barrier %.1f | offsets+dual %.1f | walk %.1f | update %.1f\n",
+            hd[8] / nl / 1e3, hd[9] / nl / 1e3, hd[10] / nl / 1e3, hd[11] / nl / 1e3, hd[12] / nl / 1e3, hd[13] / nl / 1e3, hd[14] / nl / 1e3);
+    cudaMemset(h->d_dbg, 0, sizeof(hd));
+  }
   if (timeline && tl.size() >= 4) {
     cudaStreamSynchronize(s);
     double seg[4] = {0, 0, 0, 0};
@@ -4076,25 +4522,26 @@ int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* in
                                cudaMemcpyDeviceToHost, s));
   CSLAM_CUDA(cudaStreamSynchronize(s));
   *u_out = u;
-  // support in ascending candidate order (the device list is in arrival order)
-  std::vector<std::pair<int, double>> sup(static_cast<size_t>(cnt));
-  for (int t = 0; t < cnt; ++t) sup[t] = {h->hp_sup[t], h->hp_supval[t]};
-  std::sort(sup.begin(), sup.end());
   *n_sup_out = cnt;
-  if (sup_idx_out)
+  if (sup_idx_out) {
+    // support in ascending candidate order (the device list is in arrival order)
+    std::vector<std::pair<int, double>> sup(static_cast<size_t>(cnt));
+    for (int t = 0; t < cnt; ++t) sup[t] = {h->hp_sup[t], h->hp_supval[t]};
+    std::sort(sup.begin(), sup.end());
     for (int t = 0; t < cnt; ++t) {
       sup_idx_out[t] = sup[t].first;
       if (sup_val_out) sup_val_out[t] = sup[t].second;
     }
+  }
   // round_solution_tiebreaker(w_i, k) (mac.py:168-189): top-k by (round(w, 10), weight).
   // w is zero outside the support; order the support by that key, fill up from the zeros.
   if (k > 0) {
     struct Key { double w10; double weight; int e; };
     std::vector<Key> keys;
-    keys.reserve(sup.size());
-    for (auto& pr : sup) {
-      const double w10 = std::nearbyint(pr.second * 1e10) / 1e10;  // np.round(w, 10)
-      if (w10 > 0.0) keys.push_back({w10, h->cw[pr.first], pr.first});
+    keys.reserve(static_cast<size_t>(cnt));
+    for (int t = 0; t < cnt; ++t) {
+      const double w10 = std::nearbyint(h->hp_supval[t] * 1e10) / 1e10;  // np.round(w, 10)
+      if (w10 > 0.0) keys.push_back({w10, h->cw[h->hp_sup[t]], h->hp_sup[t]});
     }
     auto better = [](const Key& a, const Key& b) {
       if (a.w10 != b.w10) return a.w10 > b.w10;
@@ -4108,7 +4555,8 @@ int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* in
       for (int64_t e = 0; e < mc; ++e)
         if (!taken[e]) keys.push_back({0.0, h->cw[e], static_cast<int>(e)});
     }
-    std::partial_sort(keys.begin(), keys.begin() + k, keys.end(), better);
+    // the k best under a strict total order: selection, no full sort needed
+    std::nth_element(keys.begin(), keys.begin() + (k - 1), keys.end(), better);
     for (int t = 0; t < k; ++t) sel_out[t] = keys[t].e;
     std::sort(sel_out, sel_out + k);
   }

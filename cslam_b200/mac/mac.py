@@ -180,18 +180,20 @@ class MAC:
             rounded[np.argpartition(zipped, -k, order=['w', 'weight'])[-k:]] = 1.0
         return rounded
 
-    def fw_subset_sparse(self, init_idx, init_val, k, max_iters=5, duality_gap_tol=1e-8, trace=False):
+    def fw_subset_sparse(self, init_idx, init_val, k, max_iters=5, duality_gap_tol=1e-8, trace=False,
+                         want_support=True):
         """`fw_subset` without dense vectors: the start vector by its non-zero entries
         (`init_idx`, `init_val`); returns (sel_idx, (sup_idx, sup_val), upper_bound) - the ascending
-        ids of the rounded selection and the non-zero entries of the unrounded iterate."""
+        ids of the rounded selection and the non-zero entries of the unrounded iterate
+        (`want_support=False`: None instead - select_candidates only uses the selection)."""
         init_idx = np.ascontiguousarray(init_idx, dtype=np.int32)
         init_val = np.ascontiguousarray(init_val, dtype=np.float64)
         assert init_idx.shape == init_val.shape and init_idx.ndim == 1
         m, k = len(self.weights), int(k)
         cap = max(1, min(m, len(init_idx) + k * max(int(max_iters), 1)))
         sel = np.empty(max(k, 1), dtype=np.int32)
-        sup_idx = np.empty(cap, dtype=np.int32)
-        sup_val = np.empty(cap, dtype=np.float64)
+        sup_idx = np.empty(cap, dtype=np.int32) if want_support else None
+        sup_val = np.empty(cap, dtype=np.float64) if want_support else None
         n_sup, u, iters = ctypes.c_int64(), ctypes.c_double(), ctypes.c_int()
         tsel = np.full((max(max_iters, 1), max(k, 1)), -1, dtype=np.int32) if trace else None
         tf = np.full(max(max_iters, 1), np.nan) if trace else None
@@ -201,7 +203,8 @@ class MAC:
             ctypes.byref(n_sup), ctypes.byref(u), ctypes.byref(iters), _lib.ptr(tsel), _lib.ptr(tf)))
         self.last_fw_iters = iters.value
         self.last_trace = (tsel, tf) if trace else None
-        return sel[:k], (sup_idx[:n_sup.value], sup_val[:n_sup.value]), u.value
+        sup = (sup_idx[:n_sup.value], sup_val[:n_sup.value]) if want_support else None
+        return sel[:k], sup, u.value
 
     def fw_subset(self, w_init, k, max_iters=5, duality_gap_tol=1e-8, trace=False):
         """Frank-Wolfe subset selection (mac.py:191-233), entirely on the GPU.

@@ -60,6 +60,12 @@ SIGNATURES = {
                                         _P(_d), _P(_i), _vp, _vp]),
     "cslam_mac_stats": (_i, [_vp, _P(_i64), _P(_i64), _P(_i)]),
     "cslam_mac_solver_timing": (_i, [_vp, _P(_d), _P(_i64), _P(_i64), _P(_i64)]),
+    "cslam_keymap_create": (_i, [_i64, _i, _P(_vp)]),
+    "cslam_keymap_destroy": (_i, [_vp]),
+    "cslam_keymap_size": (_i64, [_vp]),
+    "cslam_keymap_lookup": (_i, [_vp, _vp, _i64, _vp]),
+    "cslam_keymap_insert": (_i, [_vp, _vp, _vp, _i64]),
+    "cslam_keymap_erase": (_i, [_vp, _vp, _i64, _vp]),
     "cslam_swarm_hits": (_i, [_i, _i, _i, _vp, _vp, _vp, _d, _vp, _i, _vp]),
     "cslam_swarm_intra": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "cslam_debug_rayleigh_ritz": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _P(_i), _vp]),

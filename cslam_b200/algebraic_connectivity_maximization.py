@@ -31,7 +31,7 @@ from typing import NamedTuple
 import numpy as np
 
 from ._lib import CslamError, SingularLaplacianError
-from .candidate_table import CandidateTable
+from .candidate_table import CandidateTable, keys_packable, pack_keys
 from .mac.mac import MAC
 from .mac.utils import Edge
 
@@ -239,8 +239,43 @@ class AlgebraicConnectivityMaximization(object):
         winner = np.minimum.reduceat(np.where(eligible & (sw == best_w[group]), pos, n), first)
         mask = (1 << _KF_BITS) - 1
         glo, ghi = slo[first], shi[first]
-        keys = list(zip((glo >> _KF_BITS).tolist(), (glo & mask).tolist(),
-                        (ghi >> _KF_BITS).tolist(), (ghi & mask).tolist()))
+        g_r0, g_k0, g_r1, g_k1 = glo >> _KF_BITS, glo & mask, ghi >> _KF_BITS, ghi & mask
+        # every accepted match raises nb_poses (:110-119); a refused (lighter) one names the same two
+        # vertices as the stored edge, so only blacklisted pairs must be left out (`blocked` below)
+        def raise_nb_poses(blocked):
+            live = ~blocked[group]
+            if np.any(live):
+                src = order[live]
+                for robots, frames in ((r0[src], k0[src]), (r1[src], k1[src])):
+                    top = np.zeros(self.max_nb_robots, dtype=np.int64)
+                    np.maximum.at(top, robots, frames + 1)
+                    for robot in np.flatnonzero(top).tolist():
+                        self.nb_poses[robot] = max(self.nb_poses[robot], int(top[robot]))
+
+        if not table.device_mode and self._device_index_wanted() and keys_packable(g_r0, g_k0, g_r1, g_k1):
+            table.use_device_index(self._index_device)
+        if table.device_mode and keys_packable(g_r0, g_k0, g_r1, g_k1):
+            # ---- device index: packed keys, one lookup kernel, one insert kernel, no tuples
+            key64 = pack_keys(g_r0, g_k0, g_r1, g_k1)
+            considered = self._considered_packed()
+            blocked = np.isin(key64, considered) if len(considered) else np.zeros(len(key64), dtype=bool)
+            keep = ~blocked
+            slots = table.lookup_packed(key64)
+            if len(table):
+                # a stored entry survives a batch of direct spellings that are not heavier
+                cand = np.flatnonzero(keep & (last_rev < 0) & (slots >= 0))
+                if len(cand):
+                    keep[cand[~(best_w[cand] > table._w[slots[cand]])]] = False
+            raise_nb_poses(blocked)
+            chosen = np.flatnonzero(keep)
+            if len(chosen) == 0:
+                return
+            chosen = chosen[np.argsort(order[first[chosen]], kind="stable")]   # new pairs in batch order
+            src = order[winner[chosen]]
+            table.put_rows_packed(key64[chosen], np.stack([r0[src], k0[src], r1[src], k1[src]], axis=1),
+                                  w[src], slots=slots[chosen])
+            return
+        keys = list(zip(g_r0.tolist(), g_k0.tolist(), g_r1.tolist(), g_k1.tolist()))
         considered = self.already_considered_matches
         blocked = np.zeros(len(keys), dtype=bool)
         if considered:
@@ -253,16 +288,7 @@ class AlgebraicConnectivityMaximization(object):
                 sw0 = stored(keys[g])
                 if sw0 is not None and not best_w[g] > sw0:
                     keep[g] = False
-        # every accepted match raised nb_poses (:110-119); a refused (lighter) one names the
-        # same two vertices as the stored edge, so only blacklisted pairs must be left out
-        live = ~blocked[group]
-        if np.any(live):
-            src = order[live]
-            for robots, frames in ((r0[src], k0[src]), (r1[src], k1[src])):
-                top = np.zeros(self.max_nb_robots, dtype=np.int64)
-                np.maximum.at(top, robots, frames + 1)
-                for robot in np.flatnonzero(top).tolist():
-                    self.nb_poses[robot] = max(self.nb_poses[robot], int(top[robot]))
+        raise_nb_poses(blocked)
         chosen = np.flatnonzero(keep)
         if len(chosen) == 0:
             return
@@ -270,6 +296,46 @@ class AlgebraicConnectivityMaximization(object):
         src = order[winner[chosen]]
         table.put_rows([keys[g] for g in chosen.tolist()],
                        np.stack([r0[src], k0[src], r1[src], k1[src]], axis=1), w[src])
+
+    # ---- device hash index of the candidate keys (candidate_table.py, csrc/keymap.cu)
+    def _device_index_wanted(self):
+        """Bulk inserts move the key -> slot map to the GPU when one is present (the per-edge
+        reference API works in either mode).  `frontend.candidate_index: host` keeps the dict."""
+        want = getattr(self, "_index_wanted", None)
+        if want is None:
+            want = False
+            if str(self.params.get("frontend.candidate_index", "auto")).lower() != "host":
+                try:
+                    from . import _lib
+                    want = _lib.device_count() > 0
+                except Exception:
+                    want = False
+            self._index_device = 0
+            if want:
+                try:
+                    import torch
+                    self._index_device = int(torch.cuda.current_device())
+                except Exception:
+                    pass
+            self._index_wanted = want
+        return want
+
+    def _considered_packed(self):
+        """`already_considered_matches` (a set of 4-tuples, like the reference's) as a sorted array
+        of packed keys; rebuilt when the set has grown."""
+        c = self.already_considered_matches
+        cache = getattr(self, "_considered_cache", None)
+        if cache is None or cache[0] != len(c):
+            if c:
+                arr = np.array(list(c), dtype=np.int64).reshape(-1, 4)
+                ok = (arr[:, 0] >= 0) & (arr[:, 0] < 256) & (arr[:, 2] >= 0) & (arr[:, 2] < 256) & \
+                     (arr[:, 1] >= 0) & (arr[:, 1] < (1 << 24)) & (arr[:, 3] >= 0) & (arr[:, 3] < (1 << 24))
+                arr = arr[ok]
+                packed = np.unique(pack_keys(arr[:, 0], arr[:, 1], arr[:, 2], arr[:, 3]))
+            else:
+                packed = np.zeros(0, dtype=np.uint64)
+            cache = self._considered_cache = (len(c), packed)
+        return cache[1]
 
     # ------------------------------------------------------------------ initial guesses
     def greedy_initialization(self, nb_candidates_to_choose, edges):

@@ -22,6 +22,7 @@ SOURCES = [
     "mac.cu",
     "scancontext.cu",
     "swarm.cu",
+    "keymap.cu",
 ]
 
 NVCC_FLAGS = [

@@ -187,6 +187,23 @@ int cslam_fiedler_csr(int n, const int32_t* indptr, const int32_t* indices, cons
                       double tol, int block_size, int device, double* lambda2, double* vec_out,
                       int* iters_out);
 
+/* ---- (f3) candidate graph: hash index of the edge keys on the device ---------------------- *
+ * Replaces the Python dict of cslam/algebraic_connectivity_maximization.py:58,150,174 for BULK
+ * maintenance of the candidate graph (add_match :559-572, remove_candidate_edges :178-190,
+ * candidate_edges_to_fixed :192-203): packed 64-bit edge key -> int32 slot of the columnar
+ * candidate table.  Open addressing in HBM, one kernel per batch; host arrays in and out.
+ * Keys 0xFFFFFFFFFFFFFFFE/F are reserved.                                                    */
+typedef struct cslam_keymap cslam_keymap_t;
+int cslam_keymap_create(int64_t capacity_hint, int device, cslam_keymap_t** out);
+int cslam_keymap_destroy(cslam_keymap_t* h);
+int64_t cslam_keymap_size(cslam_keymap_t* h);
+/* values_out[t] = slot stored for keys[t], or -1 */
+int cslam_keymap_lookup(cslam_keymap_t* h, const uint64_t* keys, int64_t n, int32_t* values_out);
+/* insert or overwrite; the keys of one call must be distinct */
+int cslam_keymap_insert(cslam_keymap_t* h, const uint64_t* keys, const int32_t* values, int64_t n);
+/* erase (missing keys are ignored); values_out (nullable) gets the erased slot or -1 */
+int cslam_keymap_erase(cslam_keymap_t* h, const uint64_t* keys, int64_t n, int32_t* values_out);
+
 /* ---- (e) multi-robot round: filters on the all-gathered per-shard top-k ------------------ *
  * Device pointers; async on `stream`.  Replace the host loops of
  * cslam/loop_closure_sparse_matching.py:45-53,62-72 (similarity gate on the best match of a

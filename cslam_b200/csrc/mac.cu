@@ -3248,6 +3248,7 @@ struct FiedlerSolver {
     return CSLAM_OK;
   }
 
+  static int threads_of(int ch) { return persist_threads(ch); }
   static int persist_threads(int ch) {
     return (ch == 4 || ch == 8) ? 256 : 0;   // 256-thread CTAs, 4 or 8 rows per thread
   }
@@ -3271,7 +3272,16 @@ struct FiedlerSolver {
     pa.n = n;
     pa.m = m;
     pa.ld = ld;
-    const int rows = (n + num_sms - 1) / num_sms;
+    // CTAs of the solver: as few as hold the rows at ~90 % fill (C5: 109 of 148 SMs, 918 rows each).
+    // The kernel is latency-bound, so fuller CTAs cost nothing, fewer CTAs make the grid barriers and
+    // the CTA-count-squared all-gathers cheaper, and the SMs left over run the kernels of the other
+    // streams (the keyframe stream of the same robot) WHILE a solve is running: measured on the
+    // benchmark step, 148 / 132 / 108 CTAs = 42.5 / 41.6 / 40.4 ms.  CSLAM_LOBPCG_CTAS overrides.
+    static const int ctas_env = getenv("CSLAM_LOBPCG_CTAS") ? atoi(getenv("CSLAM_LOBPCG_CTAS")) : 0;
+    const int64_t rows_cap = static_cast<int64_t>(threads_of(ch)) * ch;
+    int grid = static_cast<int>(std::min<int64_t>(num_sms, std::max<int64_t>(1, (n * 10 + rows_cap * 9 - 1) / (rows_cap * 9))));
+    if (ctas_env > 0 && ctas_env <= num_sms && static_cast<int64_t>(ctas_env) * rows_cap >= n) grid = ctas_env;
+    const int rows = (n + grid - 1) / grid;
     pa.rpb = (rows + ch - 1) / ch * ch;
     pa.ip0 = fix.indptr; pa.c0 = fix.cols; pa.v0 = fix.vals;
     pa.ip1 = has_act ? act.indptr : nullptr; pa.c1 = act.cols; pa.v1 = act.vals;
@@ -3319,7 +3329,7 @@ struct FiedlerSolver {
     }
     CSLAM_CUDA(cudaEventRecord(pev0, stream));
     {
-      const cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(num_sms), dim3(threads), args, dyn, stream);
+      const cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, dyn, stream);
       if (le != cudaSuccess) {
         // the grid cannot be made co-resident (GPU shared with another context, MPS limits, ...):
         // the grid barrier would deadlock, so this handle uses the multi-kernel solver from now on

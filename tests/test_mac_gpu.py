@@ -252,3 +252,52 @@ def test_two_stage_solver_gives_the_same_selection(monkeypatch):
         rounded, w, u = mac.fw_subset(w0.copy(), k, max_iters=20)
         assert np.array_equal(rounded, GOLD[f"{tag}_fw_rounded"])
         np.testing.assert_allclose(w, GOLD[f"{tag}_fw_w"], atol=1e-12)
+
+
+def test_fused_tail_edge_cases():
+    """k_fw_select / k_fw_prepare on the corner cases of mac.py:191-233: all gradients tied (equal
+    weights: the reference's own tests use them), k = m, an immediate duality-gap exit (w must come
+    back untouched, mac.py:223-225), and agreement of the fused kernels with the multi-kernel
+    sequences they replace."""
+    import os
+    from cslam_b200.mac.mac import MAC
+    from cslam_b200.mac.utils import Edge
+    rng = np.random.default_rng(4)
+    n = 60
+    fixed = [Edge(i, i + 1, 1.0) for i in range(n - 1)]
+    pairs = set()
+    while len(pairs) < 200:
+        i, j = (int(x) for x in rng.integers(0, n, 2))
+        if abs(i - j) > 1:
+            pairs.add((min(i, j), max(i, j)))
+    pairs = sorted(pairs)
+    for weights in (np.ones(len(pairs)), rng.random(len(pairs))):
+        cand = [Edge(i, j, float(w)) for (i, j), w in zip(pairs, weights)]
+        k = 12
+        w0 = np.zeros(len(cand))
+        w0[np.argpartition(weights, -k)[-k:]] = 1.0
+        results = {}
+        for mode in ("fused", "multi"):
+            os.environ["CSLAM_FW_FUSED"] = "1" if mode == "fused" else "0"
+            os.environ["CSLAM_FW_FUSED_PREPARE"] = "1" if mode == "fused" else "0"
+            try:
+                mac = MAC(fixed, cand, n)
+                results[mode] = mac.fw_subset(w0.copy(), k, max_iters=12, trace=True) + (mac.last_trace,)
+            finally:
+                os.environ.pop("CSLAM_FW_FUSED", None)
+                os.environ.pop("CSLAM_FW_FUSED_PREPARE", None)
+        (ra, wa, ua, ta), (rb, wb, ub, tb) = results["fused"], results["multi"]
+        assert np.array_equal(ta[0], tb[0]), "per-iteration selections differ between the two forms"
+        assert np.array_equal(ra, rb) and np.allclose(wa, wb, atol=1e-15) and abs(ua - ub) <= 1e-12 * abs(ub)
+        assert ra.sum() == k and abs(wa.sum() - k) < 1e-9
+        for it in range(12):
+            assert len(set(ta[0][it].tolist())) == k and list(ta[0][it]) == sorted(ta[0][it])
+    # k = m: everything is selected in every iteration
+    mac = MAC(fixed, cand, n)
+    r, w, u = mac.fw_subset(np.ones(len(cand)), len(cand), max_iters=3)
+    assert r.sum() == len(cand) and np.allclose(w, 1.0)
+    # immediate exit: with a huge gap tolerance the first iteration stops before the update
+    mac = MAC(fixed, cand, n)
+    r, w, u = mac.fw_subset(w0.copy(), k, max_iters=5, duality_gap_tol=1e9)
+    assert mac.last_fw_iters == 1 and np.array_equal(w, w0)
+    assert r.sum() == k

@@ -2368,6 +2368,9 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       }
     }
     tick(9);
+    // (Measured and dropped: computing the 35 of 42 Gram sums that do not need AW between issuing
+    //  and consuming the SpMM gathers - 35.8 instead of 34.9 ms per selection: the phase is bound
+    //  by the instruction count of the sums, not by the gather latency.)
     const int nbas = init_pass ? 1 : (have_p ? 3 : 2);
     const int sdim = nbas * m;
     {

@@ -122,6 +122,10 @@ __global__ void k_resample_h(const uint8_t* __restrict__ img, int B, int H, int 
 }
 
 // vertical pass + ToTensor (/255) + Normalize: out[b][c][y][x] float32
+// (Measured and dropped in round 2: both passes in one kernel per 16-row output tile with the input
+//  rows and the uint8 intermediate in shared memory - bit-identical, but 0.150 ms instead of 0.104 ms
+//  per 64 images: one byte-wide shared-memory load per tap and channel makes it LDS-bound; a
+//  register-blocked version, several outputs per thread from words unpacked once, is what it takes.)
 __global__ void k_resample_v(const uint8_t* __restrict__ tmp, int B, int crop_h, int out,
                              int ksize, const int* __restrict__ bounds,
                              const int* __restrict__ coef, float m0, float m1, float m2, float d0,

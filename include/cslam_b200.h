@@ -87,7 +87,9 @@ int cslam_nns_read_rows(cslam_nns_t* h, int64_t start, int64_t count, float* out
 /* Top-k search for `nq` queries ([nq, dim], F32 or F64).  (search, :42-61)
  * out_idx  [nq, k] int32 row ids, best first; unused slots = -1
  * out_sims [nq, k] float64 similarities; unused slots = NaN
- * Each query returns min(k, size) matches.  Exactly equal similarities are
+ * Each query returns min(k, size) matches.  A pool row of norm 0 (similarity NaN in the
+ * reference, ranked first by its argsort()[::-1]) scores 0 here and is not returned.
+ * Exactly equal similarities are
  * ordered by DESCENDING row id (the reference's np.argsort(sim)[::-1],
  * nns_matching.py:60, leaves the order of equal keys unspecified).
  * 1 <= k <= 1024.

@@ -3321,7 +3321,7 @@ struct FiedlerSolver {
     }
     pa.cap0 = pa.cap1 = 6144;
     pa.rr_impl = getenv("CSLAM_RR_IMPL") ? atoi(getenv("CSLAM_RR_IMPL")) : 2;
-    pa.rr_sweeps = getenv("CSLAM_RR_SWEEPS") ? atoi(getenv("CSLAM_RR_SWEEPS")) : (pa.rr_impl == 2 ? 4 : 3);
+    pa.rr_sweeps = getenv("CSLAM_RR_SWEEPS") ? atoi(getenv("CSLAM_RR_SWEEPS")) : 3;   // (2-stage solve: 4 / 3 / 2 sweeps = 1082 / 1082 / 1102 iterations per C5 selection)
     pa.rr_tol2 = getenv("CSLAM_RR_TOL2") ? atof(getenv("CSLAM_RR_TOL2")) : 1e-32;
     const size_t dyn = static_cast<size_t>(pa.cap0 + pa.cap1) * (sizeof(double) + sizeof(int)) +
                        static_cast<size_t>(MAXM) * pa.rpb * sizeof(double);

@@ -668,6 +668,13 @@ def run_ours(args):
                         "traffic": int(lt["dram_bytes_per_iteration"] * its_per_launch) if lt else None,
                         "traffic_source": lt.get("source"),
                         "l2_bytes_per_iteration": lt.get("l2_bytes_per_iteration"),
+                        # what actually bounds it (ncu, one cold solve): none of the throughput limits
+                        "l2": {"achieved_GBps": (lt["l2_bytes_per_iteration"] * st["iterations"] / (st["kernel_ms"] * 1e-3) / 1e9)
+                               if lt else None,
+                               "lts_throughput_pct_of_peak": lt.get("lts_throughput_pct_of_peak")},
+                        "issue_slots_busy_pct": lt.get("issue_slots_busy_pct"),
+                        "fp64_pipe_busy_pct": lt.get("fp64_pipe_busy_pct"),
+                        "warp_time_at_barriers_pct": lt.get("warp_time_at_barriers_pct"),
                         "peak_source": peak_src, "launch_us": per_launch_ms * 1e3,
                         "algorithmic_bytes": int(per_launch_bytes),
                         "lobpcg_iterations_per_launch": its_per_launch,

@@ -115,8 +115,11 @@ for (n, d, q, k) in ((1000000, 512, 64, 30), (1000000, 512, 64, 1), (1000000, 51
     dpad = (d + 63) // 64 * 64
     group = min(q, 256)          # queries served by the timed launch (one SM-pair sweep)
     tiles = (group + 127) // 128
+    # useful FLOPs count the REAL queries of the timed launch; the MMA also multiplies the zero
+    # rows that pad the last 128-query tile (reported separately, not as throughput)
     report(f"A6 k_nns_coarse_tc last group: pool {n}x{d}, {q} queries ({tiles} tile(s) per pool sweep), k={k}", cms,
-           n * dpad * 2 + tiles * 128 * dpad * 2, flops=2.0 * tiles * 128 * n * dpad,
-           extra={"search_total_ms": total, "queries_per_s": q / (total * 1e-3),
+           n * dpad * 2 + tiles * 128 * dpad * 2, flops=2.0 * group * n * dpad,
+           extra={"issued_TFLOP/s_incl_padding": 2.0 * tiles * 128 * n * dpad / (cms * 1e-3) / 1e12,
+                  "search_total_ms": total, "queries_per_s": q / (total * 1e-3),
                   "pool_sweeps": (q + 255) // 256, "info": nn.last_info.tolist()})
     del nn

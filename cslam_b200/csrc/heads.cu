@@ -15,6 +15,8 @@
 // into one pass over its input, not in tensor-core throughput.
 #include <math.h>
 
+#include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -428,20 +430,39 @@ k_pca_finish(const float* __restrict__ part, int B, int Dout, int ksplit,
 __global__ void __launch_bounds__(512)
 k_gem_head(const float* __restrict__ x, int C, int S, float p, float eps,
            const float* __restrict__ fc_w, const float* __restrict__ fc_b, int D,
-           float* __restrict__ out, int stage_map) {
-  extern __shared__ float gsm[];
+           float* __restrict__ out, int stage_map, float* __restrict__ g_out) {
+  extern __shared__ __align__(16) float gsm[];
   float* inv = gsm;            // [S]
   float* g = gsm + S;          // [C]
   float* y = g + C;            // [D]
   float* part = y + D;         // [8][S] partial sums of squares
-  float* xs = part + 8 * S;    // [C*S] staged feature map (stage_map only)
+  float* xs = gsm + (9 * S + C + D + 3) / 4 * 4;   // [C*S] staged feature map (stage_map only), 16-byte aligned
   __shared__ float sh[16];
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const float* xb = x + static_cast<size_t>(b) * C * S;
   if (stage_map) {
-    for (int e = tid; e < C * S; e += blockDim.x) xs[e] = xb[e];
+    // 16-byte loads, four in flight per thread: a one-load-per-iteration loop pays a full memory
+    // round trip per iteration (49 of them for a 512 x 7 x 7 map = ~35 us of the old 89 us)
+    const int n = C * S;
+    if ((reinterpret_cast<uintptr_t>(xb) & 15) == 0 && (n & 3) == 0) {
+      const float4* src = reinterpret_cast<const float4*>(xb);
+      float4* dst = reinterpret_cast<float4*>(xs);
+      const int n4 = n >> 2;
+      int e = tid;
+      for (; e + 3 * static_cast<int>(blockDim.x) < n4; e += 4 * blockDim.x) {
+        const float4 v0 = src[e], v1 = src[e + blockDim.x], v2 = src[e + 2 * blockDim.x], v3 = src[e + 3 * blockDim.x];
+        dst[e] = v0;
+        dst[e + blockDim.x] = v1;
+        dst[e + 2 * blockDim.x] = v2;
+        dst[e + 3 * blockDim.x] = v3;
+      }
+      for (; e < n4; e += blockDim.x) dst[e] = src[e];
+    } else {
+#pragma unroll 4
+      for (int e = tid; e < n; e += blockDim.x) xs[e] = xb[e];
+    }
     __syncthreads();
     xb = xs;   // generic pointer into shared memory
   }
@@ -475,7 +496,9 @@ k_gem_head(const float* __restrict__ x, int C, int S, float p, float eps,
     }
     const float mean = acc / static_cast<float>(S);
     g[c] = cube ? cbrtf(mean) : powf(mean, 1.0f / p);
+    if (g_out) g_out[static_cast<size_t>(b) * C + c] = g[c];
   }
+  if (g_out) return;   // batched form: Linear + L2Norm run in k_gem_fc / k_gem_norm (CTA-uniform)
   __syncthreads();
   // Linear: y[d] = fc_w[d, :] . g + fc_b[d]; one warp per output row
   for (int d = warp; d < D; d += nw) {
@@ -496,10 +519,111 @@ k_gem_head(const float* __restrict__ x, int C, int S, float p, float eps,
   for (int d = tid; d < D; d += blockDim.x) out[static_cast<size_t>(b) * D + d] = y[d] * r;
 }
 
+// Linear of the CosPlace head for a whole batch (network.py:27): a CTA owns a tile of DT output
+// rows x 8 images, stages its rows of the weight matrix (read ONCE per 8 images instead of once
+// per image: the per-image kernel above pulled the whole 1 MB matrix through one SM per image,
+// 89 us for 64 images) and the 8 pooled vectors in shared memory; one warp per (image, row)
+// dot product in the same summation order as the per-image kernel (bit-identical results).
+constexpr int GEM_IB = 8;
+__global__ void __launch_bounds__(512)
+k_gem_fc(const float* __restrict__ g, int B, int C, const float* __restrict__ fc_w,
+         const float* __restrict__ fc_b, int D, int DT, float* __restrict__ y) {
+  extern __shared__ __align__(16) float fsm[];
+  float* sw = fsm;                                  // [DT][C]
+  float* sg = fsm + static_cast<size_t>(DT) * C;    // [GEM_IB][C]
+  const int d0 = blockIdx.x * DT, b0 = blockIdx.y * GEM_IB;
+  const int nd = min(DT, D - d0), nbm = min(GEM_IB, B - b0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  // coalesced staging with several loads in flight per thread (a one-load-per-iteration loop pays
+  // a memory round trip per iteration: 45 us for the 64 iterations of a 64 x 512 tile)
+  auto stage = [&](float* dst, const float* src, int n) {
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 && (n & 3) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      const int n4 = n >> 2, step = blockDim.x;
+      int e = tid;
+      for (; e + 3 * step < n4; e += 4 * step) {
+        const float4 v0 = s4[e], v1 = s4[e + step], v2 = s4[e + 2 * step], v3 = s4[e + 3 * step];
+        d4[e] = v0;
+        d4[e + step] = v1;
+        d4[e + 2 * step] = v2;
+        d4[e + 3 * step] = v3;
+      }
+      for (; e < n4; e += step) d4[e] = s4[e];
+    } else {
+#pragma unroll 4
+      for (int e = tid; e < n; e += blockDim.x) dst[e] = src[e];
+    }
+  };
+  stage(sw, fc_w + static_cast<size_t>(d0) * C, nd * C);
+  stage(sg, g + static_cast<size_t>(b0) * C, nbm * C);
+  __syncthreads();
+  // one warp per output row, all images of the tile at once: the weight row is read once, the
+  // eight accumulators are independent chains (per (image, row) the order of the sum is unchanged)
+  for (int di = warp; di < nd; di += nw) {
+    float acc[GEM_IB];
+#pragma unroll
+    for (int bi = 0; bi < GEM_IB; ++bi) acc[bi] = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float wv = sw[di * C + c];
+#pragma unroll
+      for (int bi = 0; bi < GEM_IB; ++bi) acc[bi] = fmaf(wv, sg[bi * C + c], acc[bi]);   // rows >= nbm: stale data, never stored
+    }
+    const float bias = fc_b[d0 + di];
+#pragma unroll
+    for (int bi = 0; bi < GEM_IB; ++bi) {
+      const float v = warp_sum(acc[bi]);
+      if (lane == 0 && bi < nbm) y[static_cast<size_t>(b0 + bi) * D + d0 + di] = v + bias;
+    }
+  }
+}
+
+// final L2Norm of every row, same reduction order as the per-image kernel
+__global__ void __launch_bounds__(512) k_gem_norm(int D, float* __restrict__ y) {
+  __shared__ float sh[16];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  float* row = y + static_cast<size_t>(b) * D;
+  float n2 = 0.f;
+  for (int d = tid; d < D; d += blockDim.x) n2 = fmaf(row[d], row[d], n2);
+  n2 = warp_sum(n2);
+  if (lane == 0) sh[warp] = n2;
+  __syncthreads();
+  float t = 0.f;
+  for (int k = 0; k < nw; ++k) t += sh[k];
+  const float r = 1.0f / fmaxf(sqrtf(t), 1e-12f);
+  for (int d = tid; d < D; d += blockDim.x) row[d] *= r;
+}
+
 }  // namespace
 }  // namespace cslam
 
 using namespace cslam;
+
+// grow-only per-device scratch for the pooled vectors of the CosPlace head (the entry point has no
+// handle; the reference front end is single-threaded, the mutex only guards the bookkeeping)
+namespace cslam {
+namespace {
+int gem_scratch(size_t floats, float** out) {
+  static std::mutex mu;
+  static float* buf[64] = {};
+  static size_t cap[64] = {};
+  int dev = 0;
+  CSLAM_CUDA(cudaGetDevice(&dev));
+  CSLAM_REQUIRE(dev >= 0 && dev < 64, "gem_head_forward: device ordinal %d not supported", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (floats > cap[dev]) {
+    CSLAM_CUDA(cudaDeviceSynchronize());
+    if (buf[dev]) cudaFree(buf[dev]);
+    buf[dev] = nullptr;
+    cap[dev] = 0;
+    CSLAM_CUDA(cudaMalloc(reinterpret_cast<void**>(&buf[dev]), floats * sizeof(float)));
+    cap[dev] = floats;
+  }
+  *out = buf[dev];
+  return CSLAM_OK;
+}
+}  // namespace
+}  // namespace cslam
 
 struct cslam_preproc {
   int device = 0;
@@ -667,15 +791,35 @@ int cslam_gem_head_forward(const float* d_x, int batch, int channels, int locati
   CSLAM_REQUIRE(d_x && d_fc_w && d_fc_b && d_out, "gem_head_forward: NULL argument");
   CSLAM_REQUIRE(batch >= 0 && channels > 0 && locations > 0 && dout > 0, "gem_head_forward: bad sizes");
   if (batch == 0) return CSLAM_OK;
-  size_t smem = (static_cast<size_t>(locations) * 9 + channels + dout) * sizeof(float);
+  size_t smem = (static_cast<size_t>(locations) * 9 + channels + dout + 4) * sizeof(float);
   const size_t map_bytes = static_cast<size_t>(channels) * locations * sizeof(float);
   const int stage_map = smem + map_bytes <= 200 * 1024 ? 1 : 0;
   if (stage_map) smem += map_bytes;
   CSLAM_REQUIRE(smem <= 200 * 1024, "gem_head_forward: shapes need %zu B of shared memory", smem);
   CSLAM_CUDA(cudaFuncSetAttribute(k_gem_head, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
-  k_gem_head<<<batch, 512, smem, static_cast<cudaStream_t>(stream)>>>(
-      d_x, channels, locations, p, eps, d_fc_w, d_fc_b, dout, d_out, stage_map);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // batches: pooled vectors to a scratch buffer, then the Linear for 8 images per weight tile and
+  // the row normalisation (CSLAM_GEM_FUSED=1 or a single image: everything in the per-image kernel)
+  static const bool per_image = getenv("CSLAM_GEM_FUSED") && atoi(getenv("CSLAM_GEM_FUSED")) != 0;
+  const int dt = static_cast<int>(std::min<size_t>(64, (160 * 1024) / (static_cast<size_t>(channels) * sizeof(float)) > GEM_IB
+                                                           ? (160 * 1024) / (static_cast<size_t>(channels) * sizeof(float)) - GEM_IB
+                                                           : 0));
+  if (batch > 1 && !per_image && dt >= 1) {
+    float* d_g = nullptr;
+    CSLAM_TRY(gem_scratch(static_cast<size_t>(batch) * channels, &d_g));
+    k_gem_head<<<batch, 512, smem, s>>>(d_x, channels, locations, p, eps, d_fc_w, d_fc_b, dout, d_out, stage_map, d_g);
+    CSLAM_LAUNCH_CHECK();
+    const size_t fsm_bytes = static_cast<size_t>(dt + GEM_IB) * channels * sizeof(float);
+    CSLAM_CUDA(cudaFuncSetAttribute(k_gem_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm_bytes)));
+    const dim3 grid((dout + dt - 1) / dt, (batch + GEM_IB - 1) / GEM_IB);
+    k_gem_fc<<<grid, 512, fsm_bytes, s>>>(d_g, batch, channels, d_fc_w, d_fc_b, dout, dt, d_out);
+    CSLAM_LAUNCH_CHECK();
+    k_gem_norm<<<batch, 512, 0, s>>>(dout, d_out);
+    CSLAM_LAUNCH_CHECK();
+    return CSLAM_OK;
+  }
+  k_gem_head<<<batch, 512, smem, s>>>(d_x, channels, locations, p, eps, d_fc_w, d_fc_b, dout, d_out, stage_map, nullptr);
   CSLAM_LAUNCH_CHECK();
   return CSLAM_OK;
 }

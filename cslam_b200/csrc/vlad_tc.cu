@@ -65,17 +65,39 @@ k_vlad_assign(const float* __restrict__ x, int S, const float* __restrict__ conv
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float n2 = 0.f;    // threads < A_STILE: sum_c x[c][s]^2 of their location, channel order
+  // The next channel chunk is fetched into registers while the current one is being multiplied
+  // (the chunks were loaded and consumed strictly in turn before: 16 exposed memory round trips
+  // per CTA).  Same arithmetic in the same order.
+  constexpr int XU = A_CCH * A_STILE / A_THREADS, WU = VK * A_CCH / A_THREADS;
+  static_assert(A_CCH * A_STILE % A_THREADS == 0 && VK * A_CCH % A_THREADS == 0, "chunk sizes");
+  float rx[XU], rw[WU];
+  auto fetch = [&](int c0) {
+#pragma unroll
+    for (int u = 0; u < XU; ++u) {
+      const int e = tid + u * A_THREADS, c = e / A_STILE, s = e % A_STILE;
+      rx[u] = s < cnt ? xb[static_cast<size_t>(c0 + c) * S + s0 + s] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < WU; ++u) {
+      const int e = tid + u * A_THREADS, k = e / A_CCH, c = e % A_CCH;
+      rw[u] = conv_w[static_cast<size_t>(k) * VC + c0 + c];
+    }
+  };
+  fetch(0);
   for (int c0 = 0; c0 < VC; c0 += A_CCH) {
     __syncthreads();
-    for (int e = tid; e < A_CCH * A_STILE; e += A_THREADS) {
-      const int c = e / A_STILE, s = e % A_STILE;
-      sm.xs[c][s] = s < cnt ? xb[static_cast<size_t>(c0 + c) * S + s0 + s] : 0.f;
+#pragma unroll
+    for (int u = 0; u < XU; ++u) {
+      const int e = tid + u * A_THREADS;
+      sm.xs[e / A_STILE][e % A_STILE] = rx[u];
     }
-    for (int e = tid; e < VK * A_CCH; e += A_THREADS) {
-      const int k = e / A_CCH, c = e % A_CCH;
-      sm.ws[k][c] = conv_w[static_cast<size_t>(k) * VC + c0 + c];
+#pragma unroll
+    for (int u = 0; u < WU; ++u) {
+      const int e = tid + u * A_THREADS;
+      sm.ws[e / A_CCH][e % A_CCH] = rw[u];
     }
     __syncthreads();
+    if (c0 + A_CCH < VC) fetch(c0 + A_CCH);
     if (tid < A_STILE) {
 #pragma unroll 8
       for (int c = 0; c < A_CCH; ++c) n2 = fmaf(sm.xs[c][tid], sm.xs[c][tid], n2);

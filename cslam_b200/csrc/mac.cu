@@ -2876,14 +2876,17 @@ struct SelectArgs {
   unsigned long long* dbg;      // optional [8..16): globaltimer ns of CTA 0 per phase (accumulated)
 };
 
-__global__ void __launch_bounds__(256, 1) k_fw_select(SelectArgs a) {
-  constexpr int T = 256, BITS = 11, NB = 1 << BITS;
+// 1024 threads per CTA: every phase is a short loop of dependent memory round trips per thread, so
+// the warps in flight set the pace (256 threads: 65 us in-kernel at C5).
+constexpr int kSelThreadsFw = 1024;
+__global__ void __launch_bounds__(kSelThreadsFw, 1) k_fw_select(SelectArgs a) {
+  constexpr int T = kSelThreadsFw, NWS = T / 32, BITS = 11, NB = 1 << BITS;
   __shared__ __align__(16) unsigned int sh_hist[NB];
   __shared__ long long sh_chunk[T];
   __shared__ int sh_best_d;
   __shared__ long long sh_best_acc, sh_best_cnt;
-  __shared__ double sh_red[8][2];
-  __shared__ int sh_warp[8];
+  __shared__ double sh_red[NWS][2];
+  __shared__ int sh_warp[NWS];
   __shared__ int sh_base, sh_tie, sh_any;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x, G = gridDim.x;
@@ -2938,10 +2941,17 @@ __global__ void __launch_bounds__(256, 1) k_fw_select(SelectArgs a) {
       __syncthreads();
       long long mine = 0;
       for (int j = 0; j < PER; ++j) mine += sh_hist[tid * PER + j];
-      sh_chunk[tid] = mine;
+      // keys in the bins above this thread's: suffix sum over the threads (warp shuffles + warp totals)
+      long long suf = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long v = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += v;
+      }
+      if (lane == 0) sh_chunk[warp] = suf;
       __syncthreads();
-      long long above = 0;
-      for (int t = tid + 1; t < T; ++t) above += sh_chunk[t];
+      long long above = suf - mine;
+      for (int q = warp + 1; q < NWS; ++q) above += sh_chunk[q];
       long long acc = above;
       int found = -1;
       long long found_acc = 0;
@@ -3006,7 +3016,7 @@ __global__ void __launch_bounds__(256, 1) k_fw_select(SelectArgs a) {
   if (tid == 0) {
     unsigned int tg = 0, te = 0;
     double s0 = 0.0, s1 = 0.0;
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < NWS; ++q) {
       tg += sh_warp[q];
       te += static_cast<unsigned int>(sh_chunk[q]);
       s0 += sh_red[q][0];
@@ -3089,7 +3099,7 @@ __global__ void __launch_bounds__(256, 1) k_fw_select(SelectArgs a) {
     __syncthreads();
     long long my_tie = tie_rank + __popc(meq & ((1u << lane) - 1u));
     int eq_total = 0;
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < NWS; ++q) {
       if (q < warp) my_tie += sh_warp[q];
       eq_total += sh_warp[q];
     }
@@ -3100,7 +3110,7 @@ __global__ void __launch_bounds__(256, 1) k_fw_select(SelectArgs a) {
     __syncthreads();
     int pos = out + __popc(msel & ((1u << lane) - 1u));
     int sel_total = 0;
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < NWS; ++q) {
       if (q < warp) pos += sh_warp[q];
       sel_total += sh_warp[q];
     }
@@ -3117,28 +3127,29 @@ __global__ void __launch_bounds__(256, 1) k_fw_select(SelectArgs a) {
   if (done) return;   // grid-uniform: gap reached, w and its support stay as they are (mac.py:223-225)
   grid_barrier(a.barrier, epoch, G);
   // ---- w_i += alpha (s_i - w_i) (mac.py:229-230; same operation order, no contraction), sparse:
-  //      w is zero outside support + selection.  Old support entries first ...
+  //      w is zero outside support + selection.  Entries of the old support (selected or not) and
+  //      newly selected entries are disjoint sets, each touched by exactly one thread.
   for (int t = b * T + tid; t < old_cnt; t += G * T) {
     const int e = a.sup[t];
     const unsigned char fl = __ldcg(a.flag + e);
     const double we = a.w[e];
     a.w[e] = __dadd_rn(we, __dmul_rn(a.alpha, __dsub_rn((fl & 2) ? 1.0 : 0.0, we)));
-    if (a.alpha == 1.0) a.flag[e] = fl & 2;   // w becomes exactly s_i: the old support is forgotten
+    // alpha = 1: w becomes exactly s_i and the old support is forgotten (selected entries re-enter below)
+    a.flag[e] = a.alpha == 1.0 ? (fl & 2) : 1;
   }
   if (a.alpha == 1.0) {
     grid_barrier(a.barrier, epoch, G);
     if (b == 0 && tid == 0) *a.sup_cnt = 0;
+    grid_barrier(a.barrier, epoch, G);
   }
-  grid_barrier(a.barrier, epoch, G);
-  // ... then the selected ones: new entries join the support with w = 0 + alpha (1 - 0)
+  // new entries (selected, not in the support: flag == 2) join with w = 0 + alpha (1 - 0)
   for (int t = b * T + tid; t < a.k; t += G * T) {
     const int e = __ldcg(a.slist + t);
-    const unsigned char fl = __ldcg(a.flag + e);
-    if (!(fl & 1)) {
+    if (__ldcg(a.flag + e) == 2) {
       a.w[e] = __dadd_rn(0.0, __dmul_rn(a.alpha, __dsub_rn(1.0, 0.0)));
       a.sup[atomicAdd(a.sup_cnt, 1)] = e;
+      a.flag[e] = 1;
     }
-    a.flag[e] = 1;
   }
   tick(14);
 }
@@ -4088,7 +4099,7 @@ int mac_fused_tail(cslam_mac* h, int k, int it, double alpha, double gap_tol, in
   CSLAM_CUDA(cudaMemsetAsync(h->d_sel_bar, 0, sizeof(unsigned int), s));
   void* args[] = {&a};
   const cudaError_t le = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_fw_select), dim3(G),
-                                                     dim3(256), args, 0, s);
+                                                     dim3(kSelThreadsFw), args, 0, s);
   if (le != cudaSuccess) {
     cudaGetLastError();
     return kPersistUnavailable;

@@ -301,3 +301,20 @@ def test_fused_tail_edge_cases():
     r, w, u = mac.fw_subset(w0.copy(), k, max_iters=5, duality_gap_tol=1e9)
     assert mac.last_fw_iters == 1 and np.array_equal(w, w0)
     assert r.sum() == k
+
+
+def test_fw_subset_with_an_empty_budget_and_an_empty_start():
+    """k = 0 (mac.py:143-146: nothing is rounded up) and an all-zero start vector on a connected
+    fixed graph: no active edge, the solver runs on the odometry Laplacian alone."""
+    from cslam_b200.mac.mac import MAC
+    from cslam_b200.mac.utils import Edge
+    n = 50
+    fixed = [Edge(i, i + 1, 1.0) for i in range(n - 1)]
+    cand = [Edge(0, 30, 0.5), Edge(5, 45, 0.7), Edge(10, 20, 0.2)]
+    mac = MAC(fixed, cand, n)
+    r, w, u = mac.fw_subset(np.zeros(3), 0, max_iters=3)
+    assert r.sum() == 0 and not w.any()
+    lam_path = 2.0 * (1.0 - np.cos(np.pi / n))            # Fiedler value of a path graph
+    assert abs(mac.evaluate_objective(np.zeros(3)) - lam_path) < 1e-9
+    r, w, u = mac.fw_subset(np.zeros(3), 2, max_iters=4)
+    assert r.sum() == 2 and abs(w.sum() - 2) < 1e-12

@@ -1918,6 +1918,7 @@ struct PersistArgs {
   double rr_tol2;        // squared relative off-diagonal level at which the Jacobi sweeps stop
   int cap0, cap1;        // shared-memory capacity (entries) for the CTA's slice of each adjacency
   unsigned int* barrier; // grid barrier counter, zero at launch
+  const int* skip;       // nullable: non-zero = the Frank-Wolfe loop has ended, do nothing (queued launches)
   long long* prof;       // optional [8] cycle counters of CTA 0 (phases 1-5, RR, barriers)
 };
 
@@ -1946,6 +1947,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     s_rrtab[e] = g_rr_tab_a[e / 32][e % 32];
     s_rrtab[5 * 32 + e] = g_rr_tab_b[e / 32][e % 32];
   }
+  if (a.skip && *a.skip) return;   // grid-uniform
   unsigned int epoch = 0;
   const double lnorm_v = __ldg(a.lnorm);
 #define GRID_SYNC() grid_barrier(a.barrier, epoch, nb_grid)
@@ -2565,6 +2567,7 @@ struct PrepareArgs {
   M2* cagg;                 // [grid]
   unsigned int* barrier;    // zero at launch
   unsigned long long* dbg;  // optional [8]: globaltimer ns of CTA 0 at the phase boundaries (accumulated)
+  const int* skip;          // nullable: non-zero = the Frank-Wolfe loop has ended, do nothing
 };
 
 // inclusive scan over the 256 threads of a CTA, product order later * earlier
@@ -2606,6 +2609,7 @@ __global__ void __launch_bounds__(256, 1) k_fw_prepare(PrepareArgs a) {
   const int b = blockIdx.x, G = gridDim.x;
   const int n = a.n;
   unsigned int epoch = 0;
+  if (a.skip && *a.skip) return;   // grid-uniform
   const int r_first = b * a.rpb + tid * RPT;
   const int r_hi = min(n, (b + 1) * a.rpb);
   unsigned long long t_prev = 0;
@@ -2852,7 +2856,9 @@ struct FwState {          // device resident, one per MAC handle
   double f;               // objective of the current iterate (copied from the solver's output)
   double dual;            // grad @ (s - w) of this iteration
   int done;               // 1: duality gap below tolerance, w was not updated
-  int pad;
+  int bad;                // copy of the factorisation flag of this iteration (queued mode)
+  int sup_cnt;            // support size at the start of this iteration
+  int ran;                // 1 once the kernel has run for this iteration
 };
 
 struct SelectArgs {
@@ -2874,6 +2880,9 @@ struct SelectArgs {
   FwState* st;
   unsigned int* barrier;        // zero at launch
   unsigned long long* dbg;      // optional [8..16): globaltimer ns of CTA 0 per phase (accumulated)
+  int* done_flag;               // nullable: set when the gap test ends the loop; non-zero at entry = do nothing
+  const int* bad_src;           // nullable: the tridiagonal-factorisation flag of this iteration, copied into st
+  const FwState* prev_st;       // state of the previous iteration (nullable: st itself carries over)
 };
 
 // 1024 threads per CTA: every phase is a short loop of dependent memory round trips per thread, so
@@ -2893,6 +2902,7 @@ __global__ void __launch_bounds__(kSelThreadsFw, 1) k_fw_select(SelectArgs a) {
   unsigned int epoch = 0;
   const long long e0 = static_cast<long long>(b) * a.chunk;
   const long long e1 = min(a.mc, e0 + a.chunk);
+  if (a.done_flag && *a.done_flag) return;   // grid-uniform: an earlier iteration ended the loop
   const int old_cnt = *a.sup_cnt;   // read before anybody may change it (first barrier below)
   unsigned long long t_prev = 0;
   auto tick = [&](int slot) {
@@ -3063,7 +3073,7 @@ __global__ void __launch_bounds__(kSelThreadsFw, 1) k_fw_select(SelectArgs a) {
     }
     const double dual = (sum_sel + static_cast<double>(need_eq) * kth_val) - sum_gw;
     const double f = *a.f_src;
-    const double u_prev = a.it == 0 ? INFINITY : a.st->u;
+    const double u_prev = a.it == 0 ? INFINITY : (a.prev_st ? a.prev_st->u : a.st->u);
     const double u_new = fmin(u_prev, f + dual);
     sh_red[0][0] = (u_new - f < a.gap_tol) ? 1.0 : 0.0;
     if (b == 0) {
@@ -3071,6 +3081,9 @@ __global__ void __launch_bounds__(kSelThreadsFw, 1) k_fw_select(SelectArgs a) {
       a.st->f = f;
       a.st->dual = dual;
       a.st->done = (u_new - f < a.gap_tol) ? 1 : 0;
+      a.st->bad = a.bad_src ? *a.bad_src : 0;
+      a.st->sup_cnt = old_cnt;
+      a.st->ran = 1;
     }
   }
   __syncthreads();
@@ -3124,7 +3137,10 @@ __global__ void __launch_bounds__(kSelThreadsFw, 1) k_fw_select(SelectArgs a) {
     __syncthreads();
   }
   tick(13);
-  if (done) return;   // grid-uniform: gap reached, w and its support stay as they are (mac.py:223-225)
+  if (done) {   // grid-uniform: gap reached, w and its support stay as they are (mac.py:223-225)
+    if (a.done_flag && b == 0 && tid == 0) *a.done_flag = 1;   // (every CTA passed the entry check: barriers above)
+    return;
+  }
   grid_barrier(a.barrier, epoch, G);
   // ---- w_i += alpha (s_i - w_i) (mac.py:229-230; same operation order, no contraction), sparse:
   //      w is zero outside support + selection.  Entries of the old support (selected or not) and
@@ -3279,9 +3295,10 @@ struct FiedlerSolver {
     return 0;
   }
 
-  // LOBPCG main loop in one cooperative kernel; theta in/out, *iters, *status out
-  int persist_loop(int ch, double tol, int max_iters, double* theta, bool have_p, bool init,
-                   int* iters, int* status) {
+  // launch only (no read-back): results go to `out_rec` ([MAXM + 3] doubles), `skip` as in
+  // PersistArgs, the launch is bracketed by the two events
+  int persist_launch(int ch, double tol, int max_iters, const double* theta, bool have_p, bool init,
+                     double* out_rec, const int* skip, cudaEvent_t e0, cudaEvent_t e1) {
     PersistArgs pa;
     pa.n = n;
     pa.m = m;
@@ -3309,7 +3326,8 @@ struct FiedlerSolver {
     pa.max_iters = max_iters;
     pa.have_p = have_p ? 1 : 0;
     pa.init = init ? 1 : 0;
-    pa.out = pout;
+    pa.out = out_rec;
+    pa.skip = skip;
     pa.barrier = pbar;
     CSLAM_CUDA(cudaMemsetAsync(pbar, 0, sizeof(unsigned int), stream));
 
@@ -3337,11 +3355,7 @@ struct FiedlerSolver {
     const size_t dyn = static_cast<size_t>(pa.cap0 + pa.cap1) * (sizeof(double) + sizeof(int)) +
                        static_cast<size_t>(MAXM) * pa.rpb * sizeof(double);
     CSLAM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
-    if (!pev0) {
-      CSLAM_CUDA(cudaEventCreate(&pev0));
-      CSLAM_CUDA(cudaEventCreate(&pev1));
-    }
-    CSLAM_CUDA(cudaEventRecord(pev0, stream));
+    CSLAM_CUDA(cudaEventRecord(e0, stream));
     {
       const cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, dyn, stream);
       if (le != cudaSuccess) {
@@ -3352,8 +3366,38 @@ struct FiedlerSolver {
         return kPersistUnavailable;
       }
     }
-    CSLAM_CUDA(cudaEventRecord(pev1, stream));
+    CSLAM_CUDA(cudaEventRecord(e1, stream));
     count_launch();
+    return CSLAM_OK;
+  }
+
+  // bookkeeping of one finished launch (roofline entry of bench.py)
+  int persist_account(int iters, cudaEvent_t e0, cudaEvent_t e1, int64_t act_nnz) {
+    float ms = 0.f;
+    CSLAM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    spmv_count += static_cast<int64_t>(iters) * m;
+    persist_ms += ms;
+    persist_ms_last_selection += ms;
+    persist_launches += 1;
+    persist_iters += iters;
+    // one SpMM per iteration reads nnz*(8+4) + n*4 and moves m*n*16
+    const int64_t nnz = fix.nnz + act_nnz;
+    persist_bytes += static_cast<int64_t>(iters) * (nnz * 12 + static_cast<int64_t>(n) * 4 +
+                                                    static_cast<int64_t>(m) * n * 16);
+    return CSLAM_OK;
+  }
+
+  // LOBPCG main loop in one cooperative kernel; theta in/out, *iters, *status out
+  int persist_loop(int ch, double tol, int max_iters, double* theta, bool have_p, bool init,
+                   int* iters, int* status) {
+    if (!pev0) {
+      CSLAM_CUDA(cudaEventCreate(&pev0));
+      CSLAM_CUDA(cudaEventCreate(&pev1));
+    }
+    {
+      const int st = persist_launch(ch, tol, max_iters, theta, have_p, init, pout, nullptr, pev0, pev1);
+      if (st != CSLAM_OK) return st;
+    }
     CSLAM_CUDA(cudaMemcpyAsync(h_red, pout, (MAXM + 3) * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CSLAM_CUDA(cudaMemcpyAsync(h_red + MAXM + 3, d_lnorm, sizeof(double), cudaMemcpyDeviceToHost, stream));
     CSLAM_CUDA(cudaMemcpyAsync(h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -3364,20 +3408,7 @@ struct FiedlerSolver {
     for (int c = 0; c < MAXM; ++c) theta[c] = h_red[c];
     *iters = static_cast<int>(h_red[MAXM]);
     *status = static_cast<int>(h_red[MAXM + 1]);
-    spmv_count += static_cast<int64_t>(*iters) * m;
-    {
-      float ms = 0.f;
-      CSLAM_CUDA(cudaEventElapsedTime(&ms, pev0, pev1));
-      persist_ms += ms;
-      persist_ms_last_selection += ms;
-      persist_launches += 1;
-      persist_iters += *iters;
-      // one SpMM per iteration reads nnz*(8+4) + n*4 and moves m*n*16
-      const int64_t nnz = fix.nnz + (has_act ? act.nnz : 0);
-      persist_bytes += static_cast<int64_t>(*iters) * (nnz * 12 + static_cast<int64_t>(n) * 4 +
-                                                       static_cast<int64_t>(m) * n * 16);
-    }
-    return CSLAM_OK;
+    return persist_account(*iters, pev0, pev1, has_act ? act.nnz : 0);
   }
 
   void release() {
@@ -3858,6 +3889,14 @@ struct cslam_mac {
   M2* d_prep_cagg = nullptr;
   unsigned int* d_prep_bar = nullptr;
   int fused_prepare = -1;
+  // queued Frank-Wolfe loop: all iterations enqueued without a host round trip in between
+  double* d_recs = nullptr;          // [iters][8] solver records (theta, iterations, status, residual)
+  FwState* d_states = nullptr;       // [iters]
+  int* d_done = nullptr;
+  void* hp_recs = nullptr;           // pinned copies of both arrays
+  int recs_cap = 0;
+  std::vector<cudaEvent_t> fw_events;
+  int queued = -1;                   // -1 try, 0 off
   bool deg_dirty = false;            // d_deg left non-zero by the multi-kernel adjacency build
   unsigned long long* d_dbg = nullptr;   // CSLAM_MAC_TIMELINE: in-kernel phase timers of k_fw_prepare
   int fixed_components = 0;     // connected components of the fixed graph
@@ -4021,7 +4060,7 @@ int mac_topk(cslam_mac* h, int k) {
 
 // active adjacency + diagonal + ||L||_inf + tridiagonal factors in one cooperative launch
 // (k_fw_prepare).  kPersistUnavailable: not applicable here, use mac_build_active + prepare_matrix.
-int mac_fused_prepare(cslam_mac* h) {
+int mac_fused_prepare(cslam_mac* h, const int* skip = nullptr) {
   FiedlerSolver& fs = h->fs;
   const int G = fs.num_sms;
   if (G <= 0 || G > 192 || h->fixed_components != 1 || fs.persist_rows_per_thread() == 0) return kPersistUnavailable;
@@ -4044,6 +4083,7 @@ int mac_fused_prepare(cslam_mac* h) {
   a.ctot = h->d_prep_ctot;
   a.cagg = h->d_prep_cagg;
   a.barrier = h->d_prep_bar;
+  a.skip = skip;
   a.dbg = h->d_dbg;
   CSLAM_CUDA(cudaMemsetAsync(h->d_prep_bar, 0, sizeof(unsigned int), s));
   if (h->deg_dirty) {
@@ -4070,7 +4110,9 @@ int mac_fused_prepare(cslam_mac* h) {
 
 // grad -> top-k -> dual/gap -> w update -> support, one cooperative launch (k_fw_select).
 // Returns kPersistUnavailable when the grid cannot be made co-resident.
-int mac_fused_tail(cslam_mac* h, int k, int it, double alpha, double gap_tol, int* trace_row) {
+int mac_fused_tail(cslam_mac* h, int k, int it, double alpha, double gap_tol, int* trace_row,
+                   const double* f_src = nullptr, FwState* state = nullptr, int* done_flag = nullptr,
+                   const int* bad_src = nullptr) {
   cudaStream_t s = h->stream;
   const int G = h->fs.num_sms;
   if (G <= 0 || G > 192) return kPersistUnavailable;
@@ -4083,7 +4125,7 @@ int mac_fused_tail(cslam_mac* h, int k, int it, double alpha, double gap_tol, in
   a.g = h->d_g; a.w = h->d_w;
   a.alpha = alpha;
   a.gap_tol = gap_tol;
-  a.f_src = h->fs.pout;
+  a.f_src = f_src ? f_src : h->fs.pout;
   a.hist = h->d_sel_hist;
   a.cnt_pairs = h->d_sel_pairs;
   a.part = h->d_sel_part;
@@ -4092,7 +4134,10 @@ int mac_fused_tail(cslam_mac* h, int k, int it, double alpha, double gap_tol, in
   a.flag = h->d_flag;
   a.sup = h->d_sup;
   a.sup_cnt = h->d_sup_cnt;
-  a.st = h->d_fwstate;
+  a.st = state ? state : h->d_fwstate;
+  a.done_flag = done_flag;
+  a.bad_src = bad_src;
+  a.prev_st = (state && it > 0) ? state - 1 : nullptr;   // queued mode: one state per iteration, consecutive
   a.barrier = h->d_sel_bar;
   a.dbg = h->d_dbg ? h->d_dbg + 0 : nullptr;
   CSLAM_CUDA(cudaMemsetAsync(h->d_sel_hist, 0, 6 * 2048 * sizeof(unsigned int), s));
@@ -4105,6 +4150,93 @@ int mac_fused_tail(cslam_mac* h, int k, int it, double alpha, double gap_tol, in
     return kPersistUnavailable;
   }
   count_launch();
+  return CSLAM_OK;
+}
+
+// The whole Frank-Wolfe loop ENQUEUED in one go: set-up, eigen-solve and tail kernels of every
+// iteration are launched back to back without a host round trip in between; the kernels of the
+// iterations after the duality gap was reached return at once (device flag).  The host reads the
+// per-iteration records once at the end.  Anything unusual (a solve that did not converge, a
+// tridiagonal part that is not positive definite, a refused cooperative launch) returns
+// kPersistUnavailable: the caller starts over with one host synchronisation per iteration, which
+// handles those cases (fallback preconditioner, error codes).
+int mac_fw_queued(cslam_mac* h, int k, int max_iters, double gap_tol, bool want_trace, double* trace_f,
+                  double* u_out, int* it_out, bool* gap_reached) {
+  FiedlerSolver& fs = h->fs;
+  cudaStream_t s = h->stream;
+  constexpr int RS = 8;   // doubles per solver record
+  const int ch = fs.persist_rows_per_thread();
+  if (ch == 0 || max_iters <= 0) return kPersistUnavailable;
+  if (max_iters > h->recs_cap) {
+    CSLAM_CUDA(cudaStreamSynchronize(s));
+    dev_free(h->d_recs);
+    dev_free(h->d_states);
+    if (h->hp_recs) cudaFreeHost(h->hp_recs);
+    h->hp_recs = nullptr;
+    CSLAM_TRY(dev_alloc(&h->d_recs, static_cast<size_t>(max_iters) * RS));
+    CSLAM_TRY(dev_alloc(&h->d_states, static_cast<size_t>(max_iters)));
+    CSLAM_CUDA(cudaMallocHost(&h->hp_recs, static_cast<size_t>(max_iters) * (RS * sizeof(double) + sizeof(FwState))));
+    if (!h->d_done) CSLAM_TRY(dev_alloc(&h->d_done, 1));
+    h->recs_cap = max_iters;
+  }
+  while (static_cast<int>(h->fw_events.size()) < 2 * max_iters) {
+    cudaEvent_t e;
+    CSLAM_CUDA(cudaEventCreate(&e));
+    h->fw_events.push_back(e);
+  }
+  CSLAM_CUDA(cudaMemsetAsync(h->d_states, 0, static_cast<size_t>(max_iters) * sizeof(FwState), s));
+  CSLAM_CUDA(cudaMemsetAsync(h->d_done, 0, sizeof(int), s));
+  fs.warm = false;
+  fs.m = std::min(fs.m, std::max(1, (fs.n - 1) / 3));
+  double theta0[MAXM] = {};
+  for (int it = 0; it < max_iters; ++it) {
+    int st = mac_fused_prepare(h, h->d_done);
+    if (st == CSLAM_OK) {
+      fs.matrix_prepared = false;   // consumed here (fs.solve is bypassed)
+      fs.jacobi = false;
+      if (it == 0) st = fs.load_start_block();
+    }
+    if (st == CSLAM_OK)
+      st = fs.persist_launch(ch, h->tol, h->max_lobpcg_iters, theta0, false, true, h->d_recs + static_cast<size_t>(it) * RS,
+                             h->d_done, h->fw_events[2 * it], h->fw_events[2 * it + 1]);
+    if (st == CSLAM_OK) {
+      const double alpha = 2.0 / (it + 2.0);
+      st = mac_fused_tail(h, k, it, alpha, gap_tol, want_trace ? h->d_trace + static_cast<size_t>(it) * k : nullptr,
+                          h->d_recs + static_cast<size_t>(it) * RS, h->d_states + it, h->d_done, fs.d_bad);
+      h->sup_ub = static_cast<int>(std::min<int64_t>(h->nc, (alpha == 1.0 ? 0 : static_cast<int64_t>(h->sup_ub)) + k));
+    }
+    if (st != CSLAM_OK) {
+      cudaStreamSynchronize(s);     // drain what was queued before handing over
+      return st;
+    }
+  }
+  double* h_recs = static_cast<double*>(h->hp_recs);
+  FwState* h_states = reinterpret_cast<FwState*>(h_recs + static_cast<size_t>(max_iters) * RS);
+  CSLAM_CUDA(cudaMemcpyAsync(h_recs, h->d_recs, static_cast<size_t>(max_iters) * RS * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CSLAM_CUDA(cudaMemcpyAsync(h_states, h->d_states, static_cast<size_t>(max_iters) * sizeof(FwState), cudaMemcpyDeviceToHost, s));
+  CSLAM_CUDA(cudaStreamSynchronize(s));
+  fs.last_path = 1;
+  fs.warm = true;
+  *gap_reached = false;
+  int it = 0;
+  for (; it < max_iters; ++it) {
+    const FwState& fw = h_states[it];
+    if (!fw.ran) return kPersistUnavailable;   // cannot happen without an earlier `done`
+    const double* rec = h_recs + static_cast<size_t>(it) * RS;
+    const int iters = static_cast<int>(rec[MAXM]), status = static_cast<int>(rec[MAXM + 1]);
+    if (fw.bad || status == 1 || (status == 2 && iters < 0)) return kPersistUnavailable;
+    CSLAM_TRY(fs.persist_account(std::max(iters, 0), h->fw_events[2 * it], h->fw_events[2 * it + 1],
+                                 2 * static_cast<int64_t>(fw.sup_cnt)));
+    fs.last_iters = std::max(iters, 0);
+    h->total_lobpcg_iters += fs.last_iters;
+    if (trace_f) trace_f[it] = fw.f;
+    *u_out = fw.u;
+    if (fw.done) {
+      *gap_reached = true;
+      break;
+    }
+  }
+  *it_out = it;
   return CSLAM_OK;
 }
 
@@ -4236,6 +4368,11 @@ int cslam_mac_destroy(cslam_mac_t* h) {
   dev_free(h->d_deg);
   dev_free(h->d_supval);
   dev_free(h->d_trace);
+  dev_free(h->d_recs);
+  dev_free(h->d_states);
+  dev_free(h->d_done);
+  if (h->hp_recs) cudaFreeHost(h->hp_recs);
+  for (cudaEvent_t e : h->fw_events) cudaEventDestroy(e);
   dev_free(h->d_dbg);
   dev_free(h->d_prep_ctot);
   dev_free(h->d_prep_cagg);
@@ -4337,29 +4474,33 @@ int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* in
                 static_cast<long long>(sup_max));
   CSLAM_TRY(mac_reserve_support(h, std::max<size_t>(sup_max, static_cast<size_t>(n_init))));
   // ---- w := start vector, support := its non-zero entries -----------------------------------
-  CSLAM_CUDA(cudaMemsetAsync(h->d_w, 0, mc * sizeof(double), s));
-  CSLAM_CUDA(cudaMemsetAsync(h->d_flag, 0, static_cast<size_t>(mc), s));
-  k_set_int<<<1, 1, 0, s>>>(h->d_sup_cnt, 0);
-  CSLAM_LAUNCH_CHECK();
-  int n0 = 0;
-  for (int64_t t = 0; t < n_init; ++t) {
-    CSLAM_REQUIRE(init_idx[t] >= 0 && init_idx[t] < mc, "mac_fw_subset: start index out of range");
-    if (init_val[t] > 0.0) {       // (the dense path kept {w > 0}; zeros add nothing)
-      h->hp_sup[n0] = init_idx[t];
-      h->hp_supval[n0] = init_val[t];
-      ++n0;
+  auto init_state = [&]() -> int {
+    CSLAM_CUDA(cudaMemsetAsync(h->d_w, 0, mc * sizeof(double), s));
+    CSLAM_CUDA(cudaMemsetAsync(h->d_flag, 0, static_cast<size_t>(mc), s));
+    k_set_int<<<1, 1, 0, s>>>(h->d_sup_cnt, 0);
+    CSLAM_LAUNCH_CHECK();
+    int n0 = 0;
+    for (int64_t t = 0; t < n_init; ++t) {
+      CSLAM_REQUIRE(init_idx[t] >= 0 && init_idx[t] < mc, "mac_fw_subset: start index out of range");
+      if (init_val[t] > 0.0) {       // (the dense path kept {w > 0}; zeros add nothing)
+        h->hp_sup[n0] = init_idx[t];
+        h->hp_supval[n0] = init_val[t];
+        ++n0;
+      }
     }
-  }
-  if (n0 > 0) {
-    // staged through the pinned buffers; d_slist / d_g are free until the first gradient
-    CSLAM_CUDA(cudaMemcpyAsync(h->d_slist, h->hp_sup, n0 * sizeof(int), cudaMemcpyHostToDevice, s));
-    CSLAM_CUDA(cudaMemcpyAsync(h->d_g, h->hp_supval, n0 * sizeof(double), cudaMemcpyHostToDevice, s));
-    k_w_scatter<<<(n0 + 255) / 256, 256, 0, s>>>(n0, h->d_slist, h->d_g, h->d_w);
-    CSLAM_LAUNCH_CHECK();
-    k_sup_append<<<(n0 + 255) / 256, 256, 0, s>>>(n0, h->d_slist, h->d_flag, h->d_sup, h->d_sup_cnt);
-    CSLAM_LAUNCH_CHECK();
-  }
-  h->sup_ub = n0;
+    if (n0 > 0) {
+      // staged through the pinned buffers; d_slist / d_g are free until the first gradient
+      CSLAM_CUDA(cudaMemcpyAsync(h->d_slist, h->hp_sup, n0 * sizeof(int), cudaMemcpyHostToDevice, s));
+      CSLAM_CUDA(cudaMemcpyAsync(h->d_g, h->hp_supval, n0 * sizeof(double), cudaMemcpyHostToDevice, s));
+      k_w_scatter<<<(n0 + 255) / 256, 256, 0, s>>>(n0, h->d_slist, h->d_g, h->d_w);
+      CSLAM_LAUNCH_CHECK();
+      k_sup_append<<<(n0 + 255) / 256, 256, 0, s>>>(n0, h->d_slist, h->d_flag, h->d_sup, h->d_sup_cnt);
+      CSLAM_LAUNCH_CHECK();
+    }
+    h->sup_ub = n0;
+    return CSLAM_OK;
+  };
+  CSLAM_TRY(init_state());
   if (trace_sel && static_cast<size_t>(max_iters) * std::max(k, 1) > h->trace_cap) {
     CSLAM_CUDA(cudaStreamSynchronize(s));
     dev_free(h->d_trace);
@@ -4371,6 +4512,27 @@ int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* in
   h->fs.persist_ms_last_selection = 0.0;
   int it = 0;
   bool gap_reached = false;
+  bool queued_done = false;
+  if (getenv("CSLAM_FW_QUEUED") && atoi(getenv("CSLAM_FW_QUEUED")) == 0) h->queued = 0;
+  if (h->queued != 0 && h->fixed_components == 1 && max_iters > 0 && !getenv("CSLAM_MAC_PROF") &&
+      !getenv("CSLAM_MAC_TIMELINE") && !(getenv("CSLAM_FW_FUSED") && atoi(getenv("CSLAM_FW_FUSED")) == 0) &&
+      !(getenv("CSLAM_FW_FUSED_PREPARE") && atoi(getenv("CSLAM_FW_FUSED_PREPARE")) == 0)) {
+    // all iterations enqueued at once, one host synchronisation per selection (mac_fw_queued)
+    const int qst = mac_fw_queued(h, k, max_iters, duality_gap_tol, trace_sel != nullptr, trace_f, &u, &it, &gap_reached);
+    if (qst == CSLAM_OK) {
+      queued_done = true;
+    } else if (qst == kPersistUnavailable) {
+      // start over with one synchronisation per iteration (handles fallbacks and error codes)
+      CSLAM_TRY(init_state());
+      u = INFINITY;
+      it = 0;
+      gap_reached = false;
+      h->fs.warm = false;
+      h->fs.persist_ms_last_selection = 0.0;
+    } else {
+      return qst;
+    }
+  }
   const int blocks_m = static_cast<int>((mc + 255) / 256);
   const bool prof = getenv("CSLAM_MAC_PROF") != nullptr;
   double t_act = 0, t_solve = 0, t_sel = 0, t_host = 0;
@@ -4397,7 +4559,7 @@ int cslam_mac_fw_subset_sparse(cslam_mac_t* h, int64_t n_init, const int32_t* in
   static_assert(sizeof(FwState) <= (4 * MAXM + 4) * sizeof(double), "FwState must fit the pinned slots");
   if (getenv("CSLAM_FW_FUSED") && atoi(getenv("CSLAM_FW_FUSED")) == 0) h->fused_tail = 0;
   h->fused_prepare = (getenv("CSLAM_FW_FUSED_PREPARE") && atoi(getenv("CSLAM_FW_FUSED_PREPARE")) == 0) ? 0 : -1;
-  for (; it < max_iters; ++it) {
+  for (; !queued_done && it < max_iters; ++it) {
     // f_i, vec_i = evaluate_fiedler_pair(w_i)                               (mac.py:211)
     double t0 = prof ? now() : 0;
     mark();                                   // 0: iteration start

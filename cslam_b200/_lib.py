@@ -68,6 +68,7 @@ SIGNATURES = {
     "cslam_keymap_erase": (_i, [_vp, _vp, _i64, _vp]),
     "cslam_swarm_hits": (_i, [_i, _i, _i, _vp, _vp, _vp, _d, _vp, _i, _vp]),
     "cslam_swarm_intra": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "cslam_debug_grid_barrier": (_i, [_i, _i, _i, _i, _i, _i, _vp]),
     "cslam_debug_rayleigh_ritz": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _P(_i), _vp]),
     "cslam_fiedler_csr": (_i, [_i, _vp, _vp, _vp, _d, _i, _i, _P(_d), _vp, _P(_i)]),
     # A1-A5 descriptor extraction

@@ -44,6 +44,11 @@ namespace cg = cooperative_groups;
 namespace cslam {
 namespace {
 
+// words of a grid-barrier object: [0] arrival counter, [64 (1 + k)] k-th copy of the release flag
+constexpr int kBarrierWords = 64 * 9;
+#ifndef CSLAM_GRID_BARRIER_VARIANT
+#define CSLAM_GRID_BARRIER_VARIANT 0
+#endif
 constexpr int MAXM = 2;          // LOBPCG block size limit
 constexpr int MAXS = 3 * MAXM;   // basis size limit
 constexpr int NPAIR = MAXS * (MAXS + 1) / 2;
@@ -410,6 +415,70 @@ __global__ void k_fac_c(int n, const double* __restrict__ diag, const double* __
     lfac[i] = l;
     dprev = d;
   }
+}
+
+// Warp totals of N per-lane values at once (N a power of two <= 32): each level halves the list,
+// a lane keeping the half its own lane bit selects and adding the partner's copy of it; after
+// log2 N levels lane l holds the total of value l % N over the lanes that share its bits above
+// N (the whole warp for N = 32).  N - 1 exchanges instead of 5 N; fixed order, deterministic.
+template <int N>
+__device__ __forceinline__ double warp_sum_transpose(double (&v)[N], int lane) {
+  if constexpr (N == 1) {
+    return v[0];
+  } else {
+    constexpr int H = N / 2;
+    const bool hi = (lane & H) != 0;
+    double u[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      const double send = hi ? v[i] : v[i + H];
+      const double keep = hi ? v[i + H] : v[i];
+      u[i] = keep + __shfl_xor_sync(0xffffffffu, send, H);
+    }
+    return warp_sum_transpose<H>(u, lane);
+  }
+}
+
+// Gram entries of the Rayleigh-Ritz basis, packed: entry e < NPAIR is S_k^T (A S)_l, entry
+// NPAIR + e is S_k^T S_l, (k, l) the e-th pair of the upper triangle in row-major order.
+constexpr int gram_tri_k(int idx) {
+  int k = 0, run = 0;
+  while (idx >= run + (MAXS - k)) { run += MAXS - k; ++k; }
+  return k;
+}
+constexpr int gram_tri_l(int idx) {
+  int k = 0, run = 0;
+  while (idx >= run + (MAXS - k)) { run += MAXS - k; ++k; }
+  return k + idx - run;
+}
+template <int E, int CH>
+__device__ __forceinline__ double gram_partial(const double (&v)[CH][MAXS], const double (&av)[CH][MAXS]) {
+  if constexpr (E >= 2 * NPAIR) {
+    return 0.0;
+  } else {
+    constexpr int idx = E % NPAIR, k = gram_tri_k(idx), l = gram_tri_l(idx);
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) acc = fma(v[j][k], E < NPAIR ? av[j][l] : v[j][l], acc);
+    return acc;
+  }
+}
+// group G = packed entries [16 G, 16 G + 16): this thread's partial sums, warp totals, -> dst[entry]
+template <int G, int CH>
+__device__ __forceinline__ void gram_group(const double (&v)[CH][MAXS], const double (&av)[CH][MAXS], int lane,
+                                           double* dst) {
+  double g[16];
+  g[0] = gram_partial<16 * G + 0, CH>(v, av);   g[1] = gram_partial<16 * G + 1, CH>(v, av);
+  g[2] = gram_partial<16 * G + 2, CH>(v, av);   g[3] = gram_partial<16 * G + 3, CH>(v, av);
+  g[4] = gram_partial<16 * G + 4, CH>(v, av);   g[5] = gram_partial<16 * G + 5, CH>(v, av);
+  g[6] = gram_partial<16 * G + 6, CH>(v, av);   g[7] = gram_partial<16 * G + 7, CH>(v, av);
+  g[8] = gram_partial<16 * G + 8, CH>(v, av);   g[9] = gram_partial<16 * G + 9, CH>(v, av);
+  g[10] = gram_partial<16 * G + 10, CH>(v, av); g[11] = gram_partial<16 * G + 11, CH>(v, av);
+  g[12] = gram_partial<16 * G + 12, CH>(v, av); g[13] = gram_partial<16 * G + 13, CH>(v, av);
+  g[14] = gram_partial<16 * G + 14, CH>(v, av); g[15] = gram_partial<16 * G + 15, CH>(v, av);
+  double t = warp_sum_transpose<16>(g, lane);
+  t += __shfl_xor_sync(0xffffffffu, t, 16);
+  if (lane < 16 && 16 * G + lane < 2 * NPAIR) dst[16 * G + lane] = t;
 }
 
 // Affine chunk scans for the two triangular solves, m right-hand sides.
@@ -1717,6 +1786,77 @@ __device__ __forceinline__ bool geig3_lowest(int nb, const double (&Ain)[3][3], 
   return true;
 }
 
+// The same pair by Rayleigh-quotient iteration from e_0 (x_c, the current Ritz vector, is the
+// dominant part of the new one): a step is one 3 x 3 solve through the adjugate (well defined at
+// a singular shift, no pivoting, no square roots) and one division, convergence is cubic (~2
+// steps per solve on the C5 selection), against ~9 Jacobi rotations behind a Cholesky reduction.
+// RQI finds AN eigenpair; that it is the lowest is checked through the leading minors of
+// A - (th - delta) B (Sylvester).  Returns 1 done, 0 B numerically singular (same test as the
+// Cholesky pivots of geig3_lowest), -1 not converged or not the lowest pair: the caller takes the
+// Jacobi path (~10 % of the solves, tools/lobpcg_study.py --fw 20 --rqi; same iterates).
+__device__ __forceinline__ int geig3_lowest_rqi(const double (&Ain)[3][3], const double (&Bin)[3][3],
+                                                double (&y)[3], double& th) {
+  double ds[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double d = Bin[i][i];
+    if (!(d > 0.0) || !isfinite(d)) return 0;
+    ds[i] = rsqrt(d);
+  }
+  const double a00 = Ain[0][0] * ds[0] * ds[0], a11 = Ain[1][1] * ds[1] * ds[1], a22 = Ain[2][2] * ds[2] * ds[2];
+  const double a01 = Ain[0][1] * ds[0] * ds[1], a02 = Ain[0][2] * ds[0] * ds[2], a12 = Ain[1][2] * ds[1] * ds[2];
+  const double b01 = Bin[0][1] * ds[0] * ds[1], b02 = Bin[0][2] * ds[0] * ds[2], b12 = Bin[1][2] * ds[1] * ds[2];
+  // pivots of the Cholesky factorisation of the scaled B: d1 = 1 - b01^2, d2 = det B / d1
+  const double d1 = fma(-b01, b01, 1.0);
+  const double detb = 1.0 + 2.0 * b01 * b02 * b12 - b01 * b01 - b02 * b02 - b12 * b12;
+  if (!(d1 > 1e-14) || !(detb > 1e-14 * d1)) return 0;
+  const double scale = fabs(a00) + fabs(a11) + fabs(a22);
+  double y0 = 1.0, y1 = 0.0, y2 = 0.0, t = a00, den = 1.0;
+  bool conv = false;
+  for (int step = 0; step < 6; ++step) {
+    const double m00 = a00 - t, m11 = a11 - t, m22 = a22 - t;
+    const double m01 = fma(-t, b01, a01), m02 = fma(-t, b02, a02), m12 = fma(-t, b12, a12);
+    const double r0 = y0 + b01 * y1 + b02 * y2, r1 = b01 * y0 + y1 + b12 * y2, r2 = b02 * y0 + b12 * y1 + y2;
+    const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
+    const double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
+    double z0 = c00 * r0 + c01 * r1 + c02 * r2;
+    double z1 = c01 * r0 + c11 * r1 + c12 * r2;
+    double z2 = c02 * r0 + c12 * r1 + c22 * r2;
+    const double zm = fmax(fabs(z0), fmax(fabs(z1), fabs(z2)));
+    if (!(zm > 1e-290) || !isfinite(zm)) break;
+    // power-of-two scaling to O(1) (no division): 2^(1023 - exponent(zm))
+    const int ebits = (__double2hiint(zm) >> 20) & 0x7ff;
+    const double sc = __hiloint2double((2046 - min(ebits, 2045)) << 20, 0);
+    z0 *= sc; z1 *= sc; z2 *= sc;
+    const double az0 = a00 * z0 + a01 * z1 + a02 * z2, az1 = a01 * z0 + a11 * z1 + a12 * z2,
+                 az2 = a02 * z0 + a12 * z1 + a22 * z2;
+    const double bz0 = z0 + b01 * z1 + b02 * z2, bz1 = b01 * z0 + z1 + b12 * z2, bz2 = b02 * z0 + b12 * z1 + z2;
+    const double num = z0 * az0 + z1 * az1 + z2 * az2;
+    den = z0 * bz0 + z1 * bz1 + z2 * bz2;
+    if (!(den > 0.0)) break;
+    const double tn = num / den;
+    y0 = z0; y1 = z1; y2 = z2;
+    const bool done = fabs(tn - t) <= 1e-10 * scale;
+    t = tn;
+    if (done) { conv = true; break; }
+  }
+  if (!conv) return -1;
+  {
+    const double tl = t - 1e-9 * scale;
+    const double m00 = a00 - tl, m11 = a11 - tl, m22 = a22 - tl;
+    const double m01 = fma(-tl, b01, a01), m02 = fma(-tl, b02, a02), m12 = fma(-tl, b12, a12);
+    const double minor2 = m00 * m11 - m01 * m01;
+    const double det = m00 * (m11 * m22 - m12 * m12) + m01 * (m02 * m12 - m01 * m22) + m02 * (m01 * m12 - m02 * m11);
+    if (!(m00 > 0.0 && minor2 > 0.0 && det > 0.0)) return -1;
+  }
+  const double nrm = rsqrt(den);
+  th = t;
+  y[0] = y0 * nrm * ds[0];
+  y[1] = y1 * nrm * ds[1];
+  y[2] = y2 * nrm * ds[2];
+  return 1;
+}
+
 __device__ __noinline__ bool rr_two_stage(int s, int m, const double* GA, const double* GB,
                                           double (*C)[MAXM], double* theta, int max_sweeps, double tol2) {
   static_assert(MAXM == 2 && MAXS == 6, "rr_two_stage is written for blocks of at most 2 vectors");
@@ -1736,7 +1876,10 @@ __device__ __noinline__ bool rr_two_stage(int s, int m, const double* GA, const 
       A3[i][j] = in ? ga(i * m + c, j * m + c) : 0.0;
       B3[i][j] = in ? gb(i * m + c, j * m + c) : 0.0;
     }
-  const bool ok1 = geig3_lowest(nb, A3, B3, max_sweeps, tol2, y, th);
+  // (rr_sweeps < 0: Jacobi path only, with -rr_sweeps sweeps - the comparison switch of the probes)
+  int st1 = (nb == 3 && max_sweeps > 0) ? geig3_lowest_rqi(A3, B3, y, th) : -1;
+  if (st1 < 0) st1 = geig3_lowest(nb, A3, B3, max_sweeps < 0 ? -max_sweeps : max_sweeps, tol2, y, th) ? 1 : 0;
+  const bool ok1 = st1 == 1;
   if (__any_sync(full, lane < m && !ok1)) return false;
   if (m == 1) {
     if (lane == 0) {
@@ -1853,21 +1996,101 @@ __global__ void k_rr_debug(const double* GA, const double* GB, int s, int m, int
 // monotonically increasing counter, release/acquire at GPU scope.  `epoch` is the CTA-uniform
 // number of barriers passed so far.  (cooperative_groups' grid.sync() measured ~11 us per call
 // here; this one is bounded by one L2 atomic round trip.)
+// V selects the memory-ordering recipe (cslam_debug_grid_barrier times them on an empty loop):
+//   0  red.release.gpu, poll with ld.acquire.gpu
+//   1  red.release.gpu, poll with ld.relaxed.gpu, one fence.acq_rel.gpu after the loop
+//   2  atom.acq_rel.gpu returning the old count (the last arriver does not poll), relaxed polls + fence
+//   3  NO ordering at all (red.relaxed, ld.relaxed): not a barrier for data, only to price the fences
+//   4  red.release.gpu, relaxed polls, no acquire fence: likewise only for pricing
+//   5  atom.acq_rel.gpu returning the old count; the LAST arriver stores the epoch to 8 flag words in
+//      different L2 lines and everyone else polls flag b % 8 with ld.acquire.gpu: the polls no longer queue
+//      at the L2 slice that serialises the arrivals
+template <int V = CSLAM_GRID_BARRIER_VARIANT>
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch,
                                              unsigned int nblocks) {
   __syncthreads();
   ++epoch;
+  if (V == 6) {
+    // eight arrival counters in different L2 lines (CTA b arrives on counter b % 8: an eighth of the
+    // serialised atomics per line), lanes 0-7 of warp 0 poll one counter each
+    if (threadIdx.x < 32) {
+      const unsigned int lane = threadIdx.x;
+      if (lane == 0)
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter + 64 * (blockIdx.x & 7)) : "memory");
+      const unsigned int k = lane & 7;
+      const unsigned int tgt = epoch * ((nblocks + 7 - k) / 8);
+      bool ok;
+      do {
+        unsigned int seen = tgt;
+        if (lane < 8)
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter + 64 * k) : "memory");
+        ok = seen >= tgt;
+      } while (!__all_sync(0xffffffffu, ok));
+    }
+    __syncthreads();
+    return;
+  }
   if (threadIdx.x == 0) {
     const unsigned int target = epoch * nblocks;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-    unsigned int seen;
+    unsigned int seen = 0;
+    if (V == 5) {
+      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
+      if (seen + 1 == target) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(counter + 64 * (1 + k)), "r"(epoch) : "memory");
+      } else {
+        const unsigned int* flag = counter + 64 * (1 + (blockIdx.x & 7));
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        } while (seen < epoch);
+      }
+    } else if (V == 2) {
+      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
+      ++seen;
+    } else if (V == 3) {
+      asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    } else {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    }
     // (a __nanosleep back-off of 20-200 ns between polls changed nothing, measured: the time spent
     //  here is the wait for the slowest CTA of the phase, not the polling itself)
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-    } while (seen < target);
+    if (V == 5) {
+    } else if (V == 0) {
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      } while (seen < target);
+    } else {
+      while (seen < target)
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (V < 3) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
   }
   __syncthreads();
+}
+
+// Test hook: `reps` barriers of a co-resident grid with `stores` global stores per thread before each
+// (the W rows a solver phase publishes); cycles per barrier seen by CTA 0.
+template <int V>
+__global__ void k_barrier_debug(unsigned int* counter, double* scratch, int reps, int stores, long long* cycles_out) {
+  unsigned int epoch = 0;
+  const unsigned int nb = gridDim.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t me = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  grid_barrier<V>(counter, epoch, nb);
+  const long long t0 = clock64();
+  double acc = 0.0;
+  for (int r = 0; r < reps; ++r) {
+    for (int k = 0; k < stores; ++k) scratch[me + k * stride] = acc + r;
+    grid_barrier<V>(counter, epoch, nb);
+    if (stores > 0) acc += __ldcg(scratch + (me + 1) % stride);
+  }
+  const long long t1 = clock64();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    cycles_out[0] = (t1 - t0) / (reps > 0 ? reps : 1);
+    cycles_out[1] = static_cast<long long>(acc);
+  }
 }
 
 // (Measured and dropped: an atomic-free variant - every CTA stores its epoch in its own slot and
@@ -1894,15 +2117,15 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 #else
 #define W_LOAD(p) (*(p))
 #endif
-constexpr bool kUseWCache = false;   // shared copy of the CTA's own W rows (measured slower: see DESIGN.md)
 struct PersistArgs {
   int n, m, rpb;         // rows, block size of the eigen-solver, rows per CTA
   int ld;
-  const int *ip0, *c0;   // fixed adjacency
+  const int *ip0, *c0;   // fixed adjacency WITHOUT its entries next to the diagonal (FiedlerSolver::fixr)
   const double* v0;
   const int *ip1, *c1;   // active adjacency (ip1 == nullptr: none)
   const double* v1;
   const double *diag, *dpiv, *lfac;
+  const double* sup;     // sup[i] = L[i][i+1], fixed + active (sup[n-1] = 0)
   double *X, *AX, *W, *P, *AP;     // global copies: X/AX in and out, W exchange buffer
   double *fA, *fB, *bA, *bB;       // [grid], [MAXM][grid] CTA aggregates of the two scans
   double *pres, *pcs, *pgram;      // [MAXM][grid], [MAXM][grid], [2*NPAIR][grid] partial sums
@@ -1950,7 +2173,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   if (a.skip && *a.skip) return;   // grid-uniform
   unsigned int epoch = 0;
   const double lnorm_v = __ldg(a.lnorm);
-#define GRID_SYNC() grid_barrier(a.barrier, epoch, nb_grid)
+#define GRID_SYNC() grid_barrier<>(a.barrier, epoch, nb_grid)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x, nb_grid = gridDim.x;
@@ -1961,17 +2184,20 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   // The matrix does not change during the solve: stage this CTA's (contiguous) slice of both
   // CSR adjacencies in shared memory so that the SpMM only goes to L2 for the W gathers.
   // (Every grid barrier invalidates L1, so global CSR reads would pay L2 latency each time.)
+  // Behind the slices: one product slot per staged entry (lap_apply).
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   double* s_v0 = reinterpret_cast<double*>(dyn_smem);
   double* s_v1 = s_v0 + a.cap0;
-  int* s_c0 = reinterpret_cast<int*>(s_v1 + a.cap1);
+  double* s_p = s_v1 + a.cap1;                                   // [cap0 + cap1][MAXM]
+  int* s_c0 = reinterpret_cast<int*>(s_p + static_cast<size_t>(a.cap0 + a.cap1) * MAXM);
   int* s_c1 = s_c0 + a.cap0;
-  double* s_w = reinterpret_cast<double*>(s_c1 + a.cap1);   // [MAXM][rpb] this CTA's rows of W
-  const int r_lo_cta = min(n, b * a.rpb);
   const int* C0 = a.c0;
   const double* V0 = a.v0;
   const int* C1 = a.c1;
   const double* V1 = a.v1;
+  int tot0 = 0, tot1 = 0;          // staged entries of the two lists (0: that list is read from global memory)
+  double* P0 = s_p;                // product slot of CSR entry q of list 0 / 1: P0[q * MAXM + c]
+  double* P1 = s_p;
   {
     const int r_lo = min(n, b * a.rpb);
     const int base0 = a.ip0[r_lo], cnt0 = a.ip0[row_end > r_lo ? row_end : r_lo] - base0;
@@ -1982,6 +2208,8 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       }
       C0 = s_c0 - base0;
       V0 = s_v0 - base0;
+      tot0 = cnt0;
+      P0 = s_p - static_cast<ptrdiff_t>(base0) * MAXM;
     }
     if (a.ip1) {
       const int base1 = a.ip1[r_lo], cnt1 = a.ip1[row_end > r_lo ? row_end : r_lo] - base1;
@@ -1992,36 +2220,70 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
         }
         C1 = s_c1 - base1;
         V1 = s_v1 - base1;
+        tot1 = cnt1;
+        P1 = s_p + (static_cast<ptrdiff_t>(a.cap0) - base1) * MAXM;
       }
     }
     __syncthreads();
   }
-  int q0s[CH], q0e[CH], q1s[CH], q1e[CH];
+  int q0[CH + 1], q1[CH + 1];   // CSR ranges of this thread's (consecutive) rows: row j owns [q[j], q[j + 1])
+  q0[0] = q1[0] = 0;
   bool valid[CH];
-  double x[CH][MAXM], ax[CH][MAXM], w[CH][MAXM], aw[CH][MAXM], p[CH][MAXM], ap[CH][MAXM];
-  double lf[CH], lf_next[CH], dp[CH], dg[CH];
+  // Per-row constants of the solve live in shared memory, not in registers: the kernel is over its
+  // register budget, and a spilled value costs an L2 round trip per use here (every grid barrier
+  // invalidates L1, local memory included).  k: 0 lfac[i], 1 1 / dpiv[i], 2 diag[i], 3 L[i][i+1].
+  double* s_cst = reinterpret_cast<double*>(s_c1 + a.cap1);      // [4][CH][T]
+  auto cst = [&](int k, int j) -> double& { return s_cst[(k * CH + j) * T + tid]; };
+#define LF(j) cst(0, j)
+#define DP(j) cst(1, j)
+#define DG(j) cst(2, j)
+#define SU(j) cst(3, j)
+#define LF_NEXT(j) ((j) < CH - 1 ? cst(0, (j) + 1 < CH ? (j) + 1 : 0) : lfn_last)
+  double lfn_last = 0.0;                                         // lfac of the row after this thread's last one
+  // X, AX, W, AW in registers; P and AP (used by the Gram sums and the basis update only) in shared memory
+  double x[CH][MAXM], ax[CH][MAXM], w[CH][MAXM], aw[CH][MAXM];
+  double* s_pap = s_cst + 4 * CH * T;                            // [2][CH][MAXM][T]
+#define PV(j, c) s_pap[(((j) * MAXM + (c)) * T) + tid]
+#define APV(j, c) s_pap[(((CH + (j)) * MAXM + (c)) * T) + tid]
+  __shared__ double s_edge[2][NW][MAXM];                  // last / first row of every warp (lap_apply)
+  int slen0 = 0, slen1 = 0;                               // longest list of this thread's rows, per adjacency
+  int maxlen = 0;                                         // longest gather list of this thread's rows among the lists that are NOT staged
 #pragma unroll
   for (int j = 0; j < CH; ++j) {
     const int i = row0 + j;
     valid[j] = i < row_end;
-    lf[j] = valid[j] ? a.lfac[i] : 0.0;
-    lf_next[j] = (valid[j] && i + 1 < n) ? a.lfac[i + 1] : 0.0;
-    dp[j] = valid[j] ? 1.0 / a.dpiv[i] : 1.0;   // reciprocal pivot
-    dg[j] = valid[j] ? a.diag[i] : 0.0;
-    q0s[j] = valid[j] ? a.ip0[i] : 0;
-    q0e[j] = valid[j] ? a.ip0[i + 1] : 0;
-    q1s[j] = (valid[j] && a.ip1) ? a.ip1[i] : 0;
-    q1e[j] = (valid[j] && a.ip1) ? a.ip1[i + 1] : 0;
+    LF(j) = valid[j] ? a.lfac[i] : 0.0;
+    if (j == CH - 1) lfn_last = (valid[j] && i + 1 < n) ? a.lfac[i + 1] : 0.0;
+    DP(j) = valid[j] ? 1.0 / a.dpiv[i] : 1.0;   // reciprocal pivot
+    DG(j) = valid[j] ? a.diag[i] : 0.0;
+    if (j == 0 && valid[0]) {
+      q0[0] = a.ip0[i];
+      q1[0] = a.ip1 ? a.ip1[i] : 0;
+    }
+    q0[j + 1] = valid[j] ? a.ip0[i + 1] : q0[j];
+    q1[j + 1] = (valid[j] && a.ip1) ? a.ip1[i + 1] : q1[j];
+    SU(j) = valid[j] ? a.sup[i] : 0.0;
+    maxlen = max(maxlen, (tot0 ? 0 : q0[j + 1] - q0[j]) + (tot1 ? 0 : q1[j + 1] - q1[j]));
+    slen0 = max(slen0, q0[j + 1] - q0[j]);
+    slen1 = max(slen1, q1[j + 1] - q1[j]);
+    // entries next to the diagonal are part of sup: their staged copies contribute nothing
+    if (tot0)
+      for (int q = q0[j]; q < q0[j + 1]; ++q)
+        if (C0[q] == i + 1 || C0[q] == i - 1) const_cast<double*>(V0)[q] = 0.0;
+    if (tot1)
+      for (int q = q1[j]; q < q1[j + 1]; ++q)
+        if (C1[q] == i + 1 || C1[q] == i - 1) const_cast<double*>(V1)[q] = 0.0;
 #pragma unroll
     for (int c = 0; c < MAXM; ++c) {
       const bool on = valid[j] && c < m;
       x[j][c] = on ? a.X[static_cast<size_t>(c) * ld + i] : 0.0;
       ax[j][c] = on ? a.AX[static_cast<size_t>(c) * ld + i] : 0.0;
-      p[j][c] = (on && a.have_p) ? a.P[static_cast<size_t>(c) * ld + i] : 0.0;
-      ap[j][c] = (on && a.have_p) ? a.AP[static_cast<size_t>(c) * ld + i] : 0.0;
+      PV(j, c) = (on && a.have_p) ? a.P[static_cast<size_t>(c) * ld + i] : 0.0;
+      APV(j, c) = (on && a.have_p) ? a.AP[static_cast<size_t>(c) * ld + i] : 0.0;
       w[j][c] = aw[j][c] = 0.0;
     }
   }
+  const double sl0 = (valid[0] && row0 > 0) ? a.sup[row0 - 1] : 0.0;   // L[row0][row0 - 1]
   double theta[MAXM];
 #pragma unroll
   for (int c = 0; c < MAXM; ++c) theta[c] = a.theta0[c];
@@ -2131,6 +2393,147 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       t_prev = t;
     }
   };
+  // y = L v for this thread's rows.  v (registers) is also published in G (+ mu: the values there are
+  // not centred yet), which serves the entries that are neither in this CTA nor next to the diagonal:
+  //   * the tridiagonal part - every odometry edge - comes from registers: v of rows i-1 and i+1
+  //     lives in this thread, its lane neighbours (shuffle), the neighbouring warp (shared memory) or,
+  //     for the two ends of the CTA's row range, in G;
+  //   * the other entries (fixed loop closures `ip0`, active candidates `ip1`) are gathered from G by
+  //     the CTA as a FLAT list - thread t takes staged entries t, t + T, ... whatever row they belong
+  //     to, four gathers in flight each, and leaves val (G[col] - mu) in the entry's product slot -
+  //     and every row then sums its own slots in CSR order.  The candidates Frank-Wolfe selects pile
+  //     up on a few poses (the ends of the chains the Fiedler vector separates): with one thread per
+  //     row those rows' serial gathers set the pace of the phase for the whole grid.
+  //   * a list whose slice did not fit in shared memory is gathered per row from global memory, in
+  //     waves of E entries, all loads of a wave in flight together.
+  // Active entries next to the diagonal are part of sup already and contribute nothing here.
+  auto lap_apply = [&](const double (&v)[CH][MAXM], const double* G, const double (&mu)[MAXM],
+                       double (&y)[CH][MAXM]) {
+    const unsigned full = 0xffffffffu;
+    double lo[MAXM], hi[MAXM];
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) {
+      lo[c] = __shfl_up_sync(full, v[CH - 1][c], 1);
+      hi[c] = __shfl_down_sync(full, v[0][c], 1);
+      if (lane == 31) s_edge[0][warp][c] = v[CH - 1][c];
+      if (lane == 0) s_edge[1][warp][c] = v[0][c];
+    }
+    // the two ends of the CTA's row range: raw loads now, used (and centred) after the flat pass
+    const bool rem_lo = tid == 0 && row0 > 0 && row0 <= n, rem_hi = valid[0] && row0 + CH >= row_end && row0 + CH < n;
+    double rlo[MAXM], rhi[MAXM];
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) {
+      rlo[c] = (rem_lo && c < m) ? W_LOAD(G + static_cast<size_t>(c) * ld + row0 - 1) : mu[c];
+      rhi[c] = (rem_hi && c < m) ? W_LOAD(G + static_cast<size_t>(c) * ld + row0 + CH) : mu[c];
+    }
+    tick(7);
+    {
+      constexpr int U = 4;
+      const int tot = tot0 + tot1;
+      for (int q = tid; q < tot; q += U * T) {
+        double val[U], g[U][MAXM];
+        int slot[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int e = q + u * T;
+          const bool on = e < tot, f0 = e < tot0;
+          val[u] = 0.0;
+          int col = 0;
+          slot[u] = 0;
+          if (on) {
+            col = f0 ? s_c0[e] : s_c1[e - tot0];
+            val[u] = f0 ? s_v0[e] : s_v1[e - tot0];
+            slot[u] = f0 ? e : a.cap0 + (e - tot0);
+          }
+#pragma unroll
+          for (int c = 0; c < MAXM; ++c)
+            g[u][c] = (on && c < m) ? W_LOAD(G + static_cast<size_t>(c) * ld + col) : mu[c];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (q + u * T < tot) {
+#pragma unroll
+            for (int c = 0; c < MAXM; ++c) s_p[slot[u] * MAXM + c] = val[u] * (g[u][c] - mu[c]);
+          }
+      }
+    }
+    __syncthreads();
+    tick(10);
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) {
+      if (lane == 0 && warp > 0) lo[c] = s_edge[0][warp - 1][c];
+      if (lane == 31 && warp < NW - 1) hi[c] = s_edge[1][warp + 1][c];
+      if (tid == 0) lo[c] = rlo[c] - mu[c];
+      if (valid[0] && row0 + CH >= row_end) hi[c] = rhi[c] - mu[c];
+    }
+    double acc[CH][MAXM];
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+#pragma unroll
+      for (int c = 0; c < MAXM; ++c) acc[j][c] = 0.0;
+    // own slots in CSR order, the rows of the thread side by side (CH independent chains of adds)
+    if (tot0)
+#pragma unroll 2
+      for (int t = 0; t < slen0; ++t)
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          if (q0[j] + t < q0[j + 1]) {
+#pragma unroll
+            for (int c = 0; c < MAXM; ++c) acc[j][c] += P0[(q0[j] + t) * MAXM + c];
+          }
+    if (tot1)
+#pragma unroll 2
+      for (int t = 0; t < slen1; ++t)
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          if (q1[j] + t < q1[j + 1]) {
+#pragma unroll
+            for (int c = 0; c < MAXM; ++c) acc[j][c] += P1[(q1[j] + t) * MAXM + c];
+          }
+    tick(11);
+    constexpr int E = 3;
+    for (int base = 0; base < maxlen; base += E) {
+      double gv[CH][E], gw[CH][E][MAXM];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int n0 = tot0 ? 0 : q0[j + 1] - q0[j], len = n0 + (tot1 ? 0 : q1[j + 1] - q1[j]);
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+          const int e = base + u;
+          const bool on = e < len, fx = e < n0;
+          gv[j][u] = 0.0;
+          int col = 0;
+          if (on) {
+            const int q = fx ? q0[j] + e : q1[j] + (e - n0);
+            col = fx ? C0[q] : C1[q];
+            const int dcol = col - (row0 + j);
+            gv[j][u] = (dcol == 1 || dcol == -1) ? 0.0 : (fx ? V0[q] : V1[q]);
+          }
+#pragma unroll
+          for (int c = 0; c < MAXM; ++c)
+            gw[j][u][c] = (on && c < m) ? W_LOAD(G + static_cast<size_t>(c) * ld + col) : mu[c];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+#pragma unroll
+        for (int u = 0; u < E; ++u)
+#pragma unroll
+          for (int c = 0; c < MAXM; ++c)
+            if (c < m) acc[j][c] = fma(gv[j][u], gw[j][u][c] - mu[c], acc[j][c]);
+    }
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+#pragma unroll
+      for (int c = 0; c < MAXM; ++c)
+        if (c < m) {
+          const double below = j == 0 ? lo[c] : v[j == 0 ? 0 : j - 1][c];
+          const double above = j == CH - 1 ? hi[c] : v[j == CH - 1 ? j : j + 1][c];
+          const double sl = j == 0 ? sl0 : SU(j == 0 ? 0 : j - 1);
+          y[j][c] = fma(DG(j), v[j][c], fma(sl, below, fma(SU(j), above, acc[j][c])));
+        }
+    __syncthreads();   // the product slots and s_edge are free again
+  };
   // AX = L X with X published through global memory (start-up pass, periodic refresh)
   auto ax_from_x = [&]() {
 #pragma unroll
@@ -2140,24 +2543,8 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
         for (int c = 0; c < MAXM; ++c)
           if (c < m) a.X[static_cast<size_t>(c) * ld + row0 + j] = x[j][c];
     GRID_SYNC();
-#pragma unroll
-    for (int j = 0; j < CH; ++j)
-      if (valid[j]) {
-        double acc[MAXM];
-#pragma unroll
-        for (int c = 0; c < MAXM; ++c) acc[c] = 0.0;
-        for (int q = q0s[j]; q < q0e[j]; ++q)
-#pragma unroll
-          for (int c = 0; c < MAXM; ++c)
-            if (c < m) acc[c] = fma(V0[q], __ldcg(a.X + static_cast<size_t>(c) * ld + C0[q]), acc[c]);
-        for (int q = q1s[j]; q < q1e[j]; ++q)
-#pragma unroll
-          for (int c = 0; c < MAXM; ++c)
-            if (c < m) acc[c] = fma(V1[q], __ldcg(a.X + static_cast<size_t>(c) * ld + C1[q]), acc[c]);
-#pragma unroll
-        for (int c = 0; c < MAXM; ++c)
-          if (c < m) ax[j][c] = fma(dg[j], x[j][c], acc[c]);
-      }
+    const double zero[MAXM] = {0.0, 0.0};
+    lap_apply(x, a.X, zero, ax);
   };
 
   bool init_pass = a.init != 0;
@@ -2183,14 +2570,14 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       if (valid[j]) {
-        A = -lf[j] * A;
+        A = -LF(j) * A;
 #pragma unroll
         for (int c = 0; c < MAXM; ++c)
           if (c < m) {
             const double r = fma(-theta[c], x[j][c], ax[j][c]);
             w[j][c] = r;
             loc[c] += fabs(r);
-            B[c] = fma(-lf[j], B[c], r);
+            B[c] = fma(-LF(j), B[c], r);
           }
       }
     }
@@ -2223,8 +2610,8 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 #pragma unroll
         for (int c = 0; c < MAXM; ++c)
           if (c < m) {
-            y[c] = fma(-lf[j], y[c], w[j][c]);
-            w[j][c] = y[c] * dp[j];  // z = y / d
+            y[c] = fma(-LF(j), y[c], w[j][c]);
+            w[j][c] = y[c] * DP(j);  // z = y / d
           }
       }
     A = 1.0;
@@ -2233,10 +2620,10 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 #pragma unroll
     for (int j = CH - 1; j >= 0; --j)
       if (valid[j]) {
-        A = -lf_next[j] * A;
+        A = -LF_NEXT(j) * A;
 #pragma unroll
         for (int c = 0; c < MAXM; ++c)
-          if (c < m) B[c] = fma(-lf_next[j], B[c], w[j][c]);
+          if (c < m) B[c] = fma(-LF_NEXT(j), B[c], w[j][c]);
       }
     block_scan_affine<true>(A, B, shA, shB);
     s_incA[tid] = A;
@@ -2265,11 +2652,10 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 #pragma unroll
         for (int c = 0; c < MAXM; ++c)
           if (c < m) {
-            xb[c] = fma(-lf_next[j], xb[c], w[j][c]);
+            xb[c] = fma(-LF_NEXT(j), xb[c], w[j][c]);
             w[j][c] = xb[c];
             loc[c] += xb[c];
             a.W[static_cast<size_t>(c) * ld + row0 + j] = xb[c];
-            if (kUseWCache) s_w[c * a.rpb + (row0 + j - r_lo_cta)] = xb[c];
           }
       }
     block_sum2(loc, a.pcs);
@@ -2292,82 +2678,13 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
           if (valid[j] && c < m) x[j][c] -= mu[c];
       ax_from_x();
     }
-    // W entries of this CTA's own row range (the odometry neighbours) come from shared memory,
-    // the rest (loop closures, range boundaries) from L2.  Branch-free: both loads are
-    // predicated so that a thread's remote gathers are all in flight together.
-    auto w_at = [&](int c, int col, bool on) -> double {
-      const bool loc = kUseWCache && col >= r_lo_cta && col < row_end;
-      const int li = loc ? col - r_lo_cta : 0;
-      const double vs = s_w[c * a.rpb + li];
-      double vg = 0.0;
-      if (on && !loc) vg = W_LOAD(a.W + static_cast<size_t>(c) * ld + col);
-      return loc ? vs : vg;
-    };
     if (!init_pass) {
-      // gathers of all rows of the thread are issued before any is consumed: the first two
-      // fixed entries (odometry neighbours) and the first active entry of each row are
-      // predicated, longer rows continue in the loops below
-      constexpr int PF = 2, PA = 1;
-      double gv[CH][PF + PA], gw[CH][PF + PA][MAXM];
 #pragma unroll
-      for (int j = 0; j < CH; ++j) {
+      for (int j = 0; j < CH; ++j)
 #pragma unroll
-        for (int e = 0; e < PF + PA; ++e) {
-          const int q = e < PF ? q0s[j] + e : q1s[j] + (e - PF);
-          const bool on = valid[j] && (e < PF ? q < q0e[j] : q < q1e[j]);
-          gv[j][e] = 0.0;
-          int col = 0;
-          if (on) {
-            gv[j][e] = e < PF ? V0[q] : V1[q];
-            col = e < PF ? C0[q] : C1[q];
-          }
-#pragma unroll
-          for (int c = 0; c < MAXM; ++c)
-            gw[j][e][c] = (on && c < m) ? w_at(c, col, on && c < m) : mu[c];
-        }
-      }
-      tick(10);
-#pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        if (valid[j]) {
-          double acc[MAXM];
-#pragma unroll
-          for (int c = 0; c < MAXM; ++c) acc[c] = 0.0;
-#pragma unroll
-          for (int e = 0; e < PF + PA; ++e)
-#pragma unroll
-            for (int c = 0; c < MAXM; ++c)
-              if (c < m) acc[c] = fma(gv[j][e], gw[j][e][c] - mu[c], acc[c]);
-          // longer rows: four gathers in flight at a time (a serial loop would pay one L2 round
-          // trip per entry, and the slowest row of the CTA sets the pace of the phase)
-          auto tail = [&](const int* Cx, const double* Vx, int q0, int q1) {
-            for (int q = q0; q < q1; q += 4) {
-              double tv[4], tw[4][MAXM];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const bool on = q + u < q1;
-                tv[u] = on ? Vx[q + u] : 0.0;
-                const int col = on ? Cx[q + u] : 0;
-#pragma unroll
-                for (int c = 0; c < MAXM; ++c) tw[u][c] = (on && c < m) ? w_at(c, col, true) : mu[c];
-              }
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int c = 0; c < MAXM; ++c)
-                  if (c < m) acc[c] = fma(tv[u], tw[u][c] - mu[c], acc[c]);
-            }
-          };
-          tail(C0, V0, q0s[j] + PF, q0e[j]);
-          tail(C1, V1, q1s[j] + PA, q1e[j]);
-#pragma unroll
-          for (int c = 0; c < MAXM; ++c)
-            if (c < m) {
-              w[j][c] -= mu[c];
-              aw[j][c] = fma(dg[j], w[j][c], acc[c]);
-            }
-        }
-      }
+        for (int c = 0; c < MAXM; ++c)
+          if (valid[j] && c < m) w[j][c] -= mu[c];
+      lap_apply(w, a.W, mu, aw);
     }
     tick(9);
     // (Measured and dropped: computing the 35 of 42 Gram sums that do not need AW between issuing
@@ -2383,8 +2700,8 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
         // column order of the basis: b * m + c (b = 0 X, 1 W, 2 P); static register indices
         static_assert(MAXM == 2 && MAXS == 6, "basis packing below is written for MAXM == 2");
         const bool two = m == 2;
-        const double p0 = have_p ? p[j][0] : 0.0, p1 = have_p ? p[j][1] : 0.0;
-        const double ap0 = have_p ? ap[j][0] : 0.0, ap1 = have_p ? ap[j][1] : 0.0;
+        const double p0 = have_p ? PV(j, 0) : 0.0, p1 = have_p ? PV(j, 1) : 0.0;
+        const double ap0 = have_p ? APV(j, 0) : 0.0, ap1 = have_p ? APV(j, 1) : 0.0;
         v[j][0] = x[j][0];                 av[j][0] = ax[j][0];
         v[j][1] = two ? x[j][1] : w[j][0]; av[j][1] = two ? ax[j][1] : aw[j][0];
         v[j][2] = two ? w[j][0] : p0;      av[j][2] = two ? aw[j][0] : ap0;
@@ -2392,27 +2709,13 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
         v[j][4] = two ? p0 : 0.0;          av[j][4] = two ? ap0 : 0.0;
         v[j][5] = two ? p1 : 0.0;          av[j][5] = two ? ap1 : 0.0;
       }
-      int idx = 0;
-#pragma unroll
-      for (int k = 0; k < MAXS; ++k)
-#pragma unroll
-        for (int l = k; l < MAXS; ++l) {
-          double ga = 0.0, gb = 0.0;
-          if (l < sdim) {   // CTA-uniform
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
-              ga = fma(v[j][k], av[j][l], ga);
-              gb = fma(v[j][k], v[j][l], gb);
-            }
-            ga = warp_sum(ga);
-            gb = warp_sum(gb);
-          }
-          if (lane == 0) {
-            s_red[warp][idx] = ga;
-            s_red[warp][NPAIR + idx] = gb;
-          }
-          ++idx;
-        }
+      // per-thread partial sums of the 21 + 21 Gram entries (basis columns past sdim are zero), 16 at
+      // a time, each group through ONE transposing warp reduction (lane l ends up with the total of
+      // entry l % 16) instead of 16 separate five-step butterflies: 48 exchanges instead of 210, and
+      // the exchanges of a level are independent of each other
+      gram_group<0, CH>(v, av, lane, s_red[warp]);
+      gram_group<1, CH>(v, av, lane, s_red[warp]);
+      gram_group<2, CH>(v, av, lane, s_red[warp]);
       __syncthreads();
       if (tid < 2 * NPAIR) {
         double acc = 0.0;
@@ -2485,8 +2788,8 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
               nax[c] = fma(ax[j][k], s_C[k][c], nax[c]);
               np_[c] = fma(w[j][k], s_C[m + k][c], np_[c]);
               nap[c] = fma(aw[j][k], s_C[m + k][c], nap[c]);
-              np_[c] = fma(p[j][k], s_C[2 * m + k][c], np_[c]);
-              nap[c] = fma(ap[j][k], s_C[2 * m + k][c], nap[c]);
+              np_[c] = fma(PV(j, k), s_C[2 * m + k][c], np_[c]);
+              nap[c] = fma(APV(j, k), s_C[2 * m + k][c], nap[c]);
             }
         }
       }
@@ -2495,8 +2798,8 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
         if (c < m) {
           x[j][c] = nx[c] + np_[c];
           ax[j][c] = nax[c] + nap[c];
-          p[j][c] = np_[c];
-          ap[j][c] = nap[c];
+          PV(j, c) = np_[c];
+          APV(j, c) = nap[c];
         }
     }
     __syncthreads();
@@ -2523,16 +2826,17 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
           const size_t o = static_cast<size_t>(c) * ld + row0 + j;
           a.X[o] = x[j][c];
           a.AX[o] = ax[j][c];
-          a.P[o] = p[j][c];
-          a.AP[o] = ap[j][c];
+          a.P[o] = PV(j, c);
+          a.AP[o] = APV(j, c);
         }
   if (do_prof) {
     for (int k = 0; k < 7; ++k) a.prof[k] += prof_acc[k];
-    for (int k = 0; k < 5; ++k) a.prof[8 + k] += rrprof_acc[k];
+    a.prof[7] += prof_acc[7];     // lap_apply: mean, centring, neighbour exchange
+    a.prof[8] += prof_acc[10];    // lap_apply: flat gather pass (to the CTA barrier)
+    a.prof[9] += prof_acc[11];    // lap_apply: own product slots summed
     a.prof[13] += it;
     a.prof[14] += prof_acc[8];
-    a.prof[15] += prof_acc[9] + prof_acc[10];
-    a.prof[7] += prof_acc[10];
+    a.prof[15] += prof_acc[7] + prof_acc[9] + prof_acc[10] + prof_acc[11];
   }
   if (b == 0 && tid == 0) {
     for (int c = 0; c < MAXM; ++c) a.out[c] = theta[c];
@@ -2543,6 +2847,13 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 }
 
 #undef GRID_SYNC
+#undef LF
+#undef DP
+#undef DG
+#undef SU
+#undef LF_NEXT
+#undef PV
+#undef APV
 
 // ------------------------------------------------------------------ fused matrix set-up
 // Everything an eigen-solve needs from the current w in ONE cooperative kernel: the adjacency of
@@ -2562,6 +2873,7 @@ struct PrepareArgs {
   const double *w, *cw;
   int* deg;                 // [n] zero at entry and at exit
   double *diag, *dpiv, *lfac, *lnorm;
+  double* supd;    // supd[r] = L[r][r+1] (FiedlerSolver::sup)
   int* bad;
   int* ctot;                // [grid]
   M2* cagg;                 // [grid]
@@ -2780,6 +3092,8 @@ __global__ void __launch_bounds__(256, 1) k_fw_prepare(PrepareArgs a) {
     }
     a.deg[r] = 0;
     a.diag[r] = -s;
+    if (r > 0) a.supd[r - 1] = lo;
+    if (r == a.n - 1) a.supd[r] = 0.0;
     dg[j] = -s;
     low[j] = lo;
     rmax = fmax(rmax, -2.0 * s);   // |diag| + sum |offdiag|
@@ -3180,6 +3494,7 @@ struct FiedlerSolver {
   int m = 2;
   cudaStream_t stream = nullptr;
   Adj fix, act;
+  Adj fixr;   // `fix` without its entries next to the diagonal (the persistent solver takes those from sup)
   bool has_act = false;
   double *diag = nullptr, *sup = nullptr, *rowabs = nullptr, *dpiv = nullptr, *lfac = nullptr;
   double *X = nullptr, *AX = nullptr, *W = nullptr, *AW = nullptr, *P = nullptr, *AP = nullptr;
@@ -3270,7 +3585,7 @@ struct FiedlerSolver {
     CSLAM_TRY(dev_alloc(&ppcs, MAXM * g));
     CSLAM_TRY(dev_alloc(&ppgram, 2 * NPAIR * g));
     CSLAM_TRY(dev_alloc(&pout, MAXM + 4));
-    CSLAM_TRY(dev_alloc(&pbar, 1));
+    CSLAM_TRY(dev_alloc(&pbar, kBarrierWords));
     if (getenv("CSLAM_LOBPCG_PROF")) {
       CSLAM_TRY(dev_alloc(&pprof, 16));
       CSLAM_CUDA(cudaMemsetAsync(pprof, 0, 16 * sizeof(long long), stream));
@@ -3280,7 +3595,7 @@ struct FiedlerSolver {
 
   static int threads_of(int ch) { return persist_threads(ch); }
   static int persist_threads(int ch) {
-    return (ch == 4 || ch == 8) ? 256 : 0;   // 256-thread CTAs, 4 or 8 rows per thread
+    return (ch == 4 || ch == 8) ? 256 : (ch == 2 ? 512 : 0);   // 256-thread CTAs with 4 or 8 rows per thread, 512 with 2
   }
   // rows per thread of the persistent kernel for this problem size (0 = not applicable)
   int persist_rows_per_thread() const {
@@ -3314,9 +3629,9 @@ struct FiedlerSolver {
     if (ctas_env > 0 && ctas_env <= num_sms && static_cast<int64_t>(ctas_env) * rows_cap >= n) grid = ctas_env;
     const int rows = (n + grid - 1) / grid;
     pa.rpb = (rows + ch - 1) / ch * ch;
-    pa.ip0 = fix.indptr; pa.c0 = fix.cols; pa.v0 = fix.vals;
+    pa.ip0 = fixr.indptr; pa.c0 = fixr.cols; pa.v0 = fixr.vals;
     pa.ip1 = has_act ? act.indptr : nullptr; pa.c1 = act.cols; pa.v1 = act.vals;
-    pa.diag = diag; pa.dpiv = dpiv; pa.lfac = lfac;
+    pa.diag = diag; pa.dpiv = dpiv; pa.lfac = lfac; pa.sup = sup;
     pa.X = X; pa.AX = AX; pa.W = W; pa.P = P; pa.AP = AP;
     pa.fA = pfA; pa.fB = pfB; pa.bA = pbA; pa.bB = pbB;
     pa.pres = ppres; pa.pcs = ppcs; pa.pgram = ppgram;
@@ -3329,7 +3644,7 @@ struct FiedlerSolver {
     pa.out = out_rec;
     pa.skip = skip;
     pa.barrier = pbar;
-    CSLAM_CUDA(cudaMemsetAsync(pbar, 0, sizeof(unsigned int), stream));
+    CSLAM_CUDA(cudaMemsetAsync(pbar, 0, kBarrierWords * sizeof(unsigned int), stream));
 
     pa.prof = pprof;
     void* args[] = {&pa};
@@ -3341,6 +3656,11 @@ struct FiedlerSolver {
                     : reinterpret_cast<const void*>(&k_lobpcg_persist<4, 256, 1>);
         threads = 256;
         break;
+      case 2:
+        fn = m == 2 ? reinterpret_cast<const void*>(&k_lobpcg_persist<2, 512, 2>)
+                    : reinterpret_cast<const void*>(&k_lobpcg_persist<2, 512, 1>);
+        threads = 512;
+        break;
       case 8:
         fn = m == 2 ? reinterpret_cast<const void*>(&k_lobpcg_persist<8, 256, 2>)
                     : reinterpret_cast<const void*>(&k_lobpcg_persist<8, 256, 1>);
@@ -3348,12 +3668,21 @@ struct FiedlerSolver {
         break;
       default: set_error("fiedler: bad persistent variant %d", ch); return CSLAM_ERR_INVALID;
     }
-    pa.cap0 = pa.cap1 = 6144;
+    // Staged entries per CTA (fixed adjacency off the tridiagonal / active adjacency; 28 B each with the
+    // product slot).  Together with the 64 KB of per-row state the CTA must stay under the 196 KB
+    // shared-memory carve-out: at the 228 KB one the 28 KB of L1 that remain make every W gather and
+    // CTA-count all-gather slower - 27.6 ms per C5 selection with 5120 staged entries, 24.5 ms with
+    // 2304-3328 (measured); a slice that does not fit is gathered per row from global memory instead
+    // (the heaviest C5 CTA holds 2569 active entries; 28.6 / 33.0 ms with room for 1024 / 512).
+    pa.cap0 = static_cast<int>(std::min<int64_t>(2048, std::max<int64_t>(256, (4 * fixr.nnz / grid + 255) / 256 * 256)));
+    pa.cap1 = 3840 - pa.cap0;
+    if (const char* e = getenv("CSLAM_LOBPCG_CAP1")) pa.cap1 = std::max(0, std::min(4096, atoi(e)));   // (experiments)
+    if (const char* e = getenv("CSLAM_LOBPCG_CAP0")) pa.cap0 = std::max(0, std::min(4096, atoi(e)));
     pa.rr_impl = getenv("CSLAM_RR_IMPL") ? atoi(getenv("CSLAM_RR_IMPL")) : 2;
     pa.rr_sweeps = getenv("CSLAM_RR_SWEEPS") ? atoi(getenv("CSLAM_RR_SWEEPS")) : 3;   // (2-stage solve: 4 / 3 / 2 sweeps = 1082 / 1082 / 1102 iterations per C5 selection)
     pa.rr_tol2 = getenv("CSLAM_RR_TOL2") ? atof(getenv("CSLAM_RR_TOL2")) : 1e-32;
-    const size_t dyn = static_cast<size_t>(pa.cap0 + pa.cap1) * (sizeof(double) + sizeof(int)) +
-                       static_cast<size_t>(MAXM) * pa.rpb * sizeof(double);
+    const size_t dyn = static_cast<size_t>(pa.cap0 + pa.cap1) * ((1 + MAXM) * sizeof(double) + sizeof(int)) +
+                       static_cast<size_t>(4 + 2 * MAXM) * ch * threads * sizeof(double);
     CSLAM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
     CSLAM_CUDA(cudaEventRecord(e0, stream));
     {
@@ -3421,9 +3750,9 @@ struct FiedlerSolver {
       long long hp[16] = {};
       cudaMemcpy(hp, pprof, sizeof(hp), cudaMemcpyDeviceToHost);
       const double it_ = static_cast<double>(std::max<long long>(hp[13], 1));
-      fprintf(stderr, "[cslam lobpcg prof] cycles/iter over %lld iters: p1 %.0f p2 %.0f p3 %.0f p4 %.0f p5 %.0f rr %.0f barriers %.0f | rr: setup %.0f chol %.0f tri %.0f jacobi %.0f back %.0f | p4: gridsum %.0f spmm %.0f (of which gather issue %.0f) (gram = p4)\n",
+      fprintf(stderr, "[cslam lobpcg prof] cycles/iter of CTA 0 over %lld iters: p1 %.0f p2 %.0f p3 %.0f p4 (Gram) %.0f p5 %.0f rr %.0f barriers %.0f | before p4: gridsum %.0f spmm %.0f (centre + exchange %.0f, flat gathers %.0f, own slots %.0f)\n",
               hp[13], hp[0] / it_, hp[1] / it_, hp[2] / it_, hp[3] / it_, hp[4] / it_, hp[5] / it_, hp[6] / it_,
-              hp[8] / it_, hp[9] / it_, hp[10] / it_, hp[11] / it_, hp[12] / it_, hp[14] / it_, hp[15] / it_, hp[7] / it_);
+              hp[14] / it_, hp[15] / it_, hp[7] / it_, hp[8] / it_, hp[9] / it_);
       dev_free(pprof);
     }
     dev_free(pbar);
@@ -3437,7 +3766,7 @@ struct FiedlerSolver {
     h_bad = nullptr;
     if (h_red) cudaFreeHost(h_red);
     h_red = nullptr;
-    for (Adj* a : {&fix, &act}) {
+    for (Adj* a : {&fix, &act, &fixr}) {
       dev_free(a->indptr);
       dev_free(a->cols);
       dev_free(a->src);
@@ -3472,6 +3801,22 @@ struct FiedlerSolver {
     // the host vectors may be destroyed by the caller right after this returns
     CSLAM_CUDA(cudaStreamSynchronize(stream));
     return CSLAM_OK;
+  }
+
+  // the fixed adjacency, and the copy of it without the entries next to the diagonal
+  int upload_fixed(const std::vector<int>& indptr, const std::vector<int>& cols, const std::vector<double>& vals) {
+    CSLAM_TRY(upload(fix, indptr, cols, nullptr, &vals));
+    std::vector<int> ip(indptr.size(), 0), cc;
+    std::vector<double> vv;
+    for (int r = 0; r < n; ++r) {
+      for (int p = indptr[r]; p < indptr[r + 1]; ++p)
+        if (cols[p] != r + 1 && cols[p] != r - 1) {
+          cc.push_back(cols[p]);
+          vv.push_back(vals[p]);
+        }
+      ip[r + 1] = static_cast<int>(cc.size());
+    }
+    return upload(fixr, ip, cc, nullptr, &vv);
   }
 
   int spmm(double* x, double* y, const double* colsum) {
@@ -4078,14 +4423,14 @@ int mac_fused_prepare(cslam_mac* h, const int* skip = nullptr) {
   a.sup = h->d_sup; a.sup_cnt = h->d_sup_cnt; a.ci = h->d_ci; a.cj = h->d_cj;
   a.w = h->d_w; a.cw = h->d_cw;
   a.deg = h->d_deg;
-  a.diag = fs.diag; a.dpiv = fs.dpiv; a.lfac = fs.lfac; a.lnorm = fs.d_lnorm;
+  a.diag = fs.diag; a.dpiv = fs.dpiv; a.lfac = fs.lfac; a.lnorm = fs.d_lnorm; a.supd = fs.sup;
   a.bad = fs.d_bad;
   a.ctot = h->d_prep_ctot;
   a.cagg = h->d_prep_cagg;
   a.barrier = h->d_prep_bar;
   a.skip = skip;
   a.dbg = h->d_dbg;
-  CSLAM_CUDA(cudaMemsetAsync(h->d_prep_bar, 0, sizeof(unsigned int), s));
+  CSLAM_CUDA(cudaMemsetAsync(h->d_prep_bar, 0, kBarrierWords * sizeof(unsigned int), s));
   if (h->deg_dirty) {
     CSLAM_CUDA(cudaMemsetAsync(h->d_deg, 0, static_cast<size_t>(h->n) * sizeof(int), s));
     h->deg_dirty = false;
@@ -4141,7 +4486,7 @@ int mac_fused_tail(cslam_mac* h, int k, int it, double alpha, double gap_tol, in
   a.barrier = h->d_sel_bar;
   a.dbg = h->d_dbg ? h->d_dbg + 0 : nullptr;
   CSLAM_CUDA(cudaMemsetAsync(h->d_sel_hist, 0, 6 * 2048 * sizeof(unsigned int), s));
-  CSLAM_CUDA(cudaMemsetAsync(h->d_sel_bar, 0, sizeof(unsigned int), s));
+  CSLAM_CUDA(cudaMemsetAsync(h->d_sel_bar, 0, kBarrierWords * sizeof(unsigned int), s));
   void* args[] = {&a};
   const cudaError_t le = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_fw_select), dim3(G),
                                                      dim3(kSelThreadsFw), args, 0, s);
@@ -4303,7 +4648,7 @@ int cslam_mac_create(int num_poses, int64_t n_fixed, const int32_t* fi, const in
     build_adjacency(h->n, static_cast<size_t>(n_fixed), h->fi.data(), h->fj.data(), indptr, cols, src);
     std::vector<double> vals(cols.size());
     for (size_t p = 0; p < cols.size(); ++p) vals[p] = -h->fw[src[p]];
-    st = h->fs.upload(h->fs.fix, indptr, cols, nullptr, &vals);
+    st = h->fs.upload_fixed(indptr, cols, vals);
     if (st != CSLAM_OK) return fail(st);
   }
   {
@@ -4334,8 +4679,8 @@ int cslam_mac_create(int num_poses, int64_t n_fixed, const int32_t* fi, const in
       (st = dev_alloc(&h->d_flag, mc)) || (st = dev_alloc(&h->d_sup_cnt, 1)) ||
       (st = dev_alloc(&h->d_fwstate, 1)) || (st = dev_alloc(&h->d_sel_hist, 6 * 2048)) ||
       (st = dev_alloc(&h->d_sel_pairs, 2 * 192)) || (st = dev_alloc(&h->d_sel_part, 2 * 192)) ||
-      (st = dev_alloc(&h->d_sel_bar, 1)) || (st = dev_alloc(&h->d_prep_ctot, 192)) ||
-      (st = dev_alloc(&h->d_prep_cagg, 192)) || (st = dev_alloc(&h->d_prep_bar, 1)) ||
+      (st = dev_alloc(&h->d_sel_bar, kBarrierWords)) || (st = dev_alloc(&h->d_prep_ctot, 192)) ||
+      (st = dev_alloc(&h->d_prep_cagg, 192)) || (st = dev_alloc(&h->d_prep_bar, kBarrierWords)) ||
       (st = dev_alloc(&h->d_deg, static_cast<size_t>(num_poses))))
     return fail(st);
   cudaMemsetAsync(h->d_flag, 0, mc, h->stream);
@@ -4835,6 +5180,45 @@ int cslam_debug_rayleigh_ritz(const double* ga, const double* gb, int s, int m, 
   return CSLAM_OK;
 }
 
+int cslam_debug_grid_barrier(int ctas, int threads, int reps, int stores, int variant, int device,
+                             int64_t* cycles_per_barrier) {
+  CSLAM_REQUIRE(ctas >= 1 && threads >= 32 && threads <= 1024 && reps >= 1 && stores >= 0 && stores <= 16 &&
+                variant >= 0 && variant <= 6 && cycles_per_barrier, "debug_grid_barrier: bad arguments");
+  if (cslam_device_count() <= 0) {
+    set_error("debug_grid_barrier: no CUDA device");
+    return CSLAM_ERR_CUDA;
+  }
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  CSLAM_CUDA(cudaGetDeviceProperties(&prop, device));
+  CSLAM_REQUIRE(ctas <= prop.multiProcessorCount, "debug_grid_barrier: at most one CTA per SM (%d)",
+                prop.multiProcessorCount);
+  unsigned int* dbar = nullptr;
+  double* dscr = nullptr;
+  long long* dcyc = nullptr;
+  CSLAM_TRY(dev_alloc(&dbar, kBarrierWords));
+  CSLAM_TRY(dev_alloc(&dscr, static_cast<size_t>(ctas) * threads * (stores > 0 ? stores : 1)));
+  CSLAM_TRY(dev_alloc(&dcyc, 2));
+  CSLAM_CUDA(cudaMemset(dbar, 0, kBarrierWords * sizeof(unsigned int)));
+  const void* fn = variant == 0 ? reinterpret_cast<const void*>(&k_barrier_debug<0>)
+                 : variant == 1 ? reinterpret_cast<const void*>(&k_barrier_debug<1>)
+                 : variant == 2 ? reinterpret_cast<const void*>(&k_barrier_debug<2>)
+                 : variant == 3 ? reinterpret_cast<const void*>(&k_barrier_debug<3>)
+                 : variant == 4 ? reinterpret_cast<const void*>(&k_barrier_debug<4>)
+                 : variant == 5 ? reinterpret_cast<const void*>(&k_barrier_debug<5>)
+                                : reinterpret_cast<const void*>(&k_barrier_debug<6>);
+  void* args[] = {&dbar, &dscr, &reps, &stores, &dcyc};
+  CSLAM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(ctas), dim3(threads), args, 0, nullptr));
+  CSLAM_CUDA(cudaDeviceSynchronize());
+  long long h[2];
+  CSLAM_CUDA(cudaMemcpy(h, dcyc, sizeof(h), cudaMemcpyDeviceToHost));
+  *cycles_per_barrier = h[0];
+  dev_free(dbar);
+  dev_free(dscr);
+  dev_free(dcyc);
+  return CSLAM_OK;
+}
+
 int cslam_fiedler_csr(int n, const int32_t* indptr, const int32_t* indices, const double* data,
                       double tol, int block_size, int device, double* lambda2, double* vec_out,
                       int* iters_out) {
@@ -4872,7 +5256,7 @@ int cslam_fiedler_csr(int n, const int32_t* indptr, const int32_t* indices, cons
   CSLAM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   FiedlerSolver fs;
   int st = fs.init(n, device, s);
-  if (st == CSLAM_OK) st = fs.upload(fs.fix, ip, cols, nullptr, &vals);
+  if (st == CSLAM_OK) st = fs.upload_fixed(ip, cols, vals);
   if (st == CSLAM_OK) {
     fs.m = block_size;
     st = fs.solve(tol, 20000, lambda2);

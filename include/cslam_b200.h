@@ -226,13 +226,22 @@ int cslam_swarm_intra(int B, int k_search, int k_keep, int64_t rows_before, cons
 
 /* Test hook: the small generalised eigenproblem GA y = theta GB y (s x s, row-major with a
  * leading dimension of 6; 1 <= m <= 2 smallest pairs) that the eigen-solver solves once per
- * iteration, by one warp, `reps` times.  impl 1 = register-resident solver (entry-per-lane
- * Jacobi, the default of the eigen-solver), 0 = shared-memory solver.  c_out [6][2] (GB-orthonormal vectors), theta_out [2],
+ * iteration, by one warp, `reps` times.  impl 2 = the two-stage solve of the eigen-solver (per column
+ * the 3 x 3 problem on {x, w, p}, then the m x m problem on the results; sweeps > 0: Rayleigh-quotient
+ * iteration for the 3 x 3 problems with the Jacobi solve as its fallback, sweeps < 0: Jacobi only with
+ * |sweeps| sweeps), 1 = register-resident 6 x 6 solver (entry-per-lane Jacobi), 0 = shared-memory
+ * 6 x 6 solver.  c_out [6][2] (GB-orthonormal vectors), theta_out [2],
  * *ok_out 0 when GB is not positive definite, cycles_out (nullable) [6]: SM cycles per solve:
  * total, then set-up, Cholesky, triangular transforms, Jacobi sweeps, back substitution. */
 int cslam_debug_rayleigh_ritz(const double* ga, const double* gb, int s, int m, int impl, int sweeps,
                               int reps, int device, double* c_out, double* theta_out, int* ok_out,
                               int64_t* cycles_out);
+
+/* Test hook: cycles per barrier of the solver's grid barrier on an otherwise empty co-resident grid
+ * (`ctas` x `threads`, `stores` global stores per thread before each barrier); `variant` selects the
+ * memory-ordering recipe (csrc/mac.cu grid_barrier). */
+int cslam_debug_grid_barrier(int ctas, int threads, int reps, int stores, int variant, int device,
+                             int64_t* cycles_per_barrier);
 
 /* ---- A1-A5: descriptor extraction around the PyTorch backbone ------------- *
  * All pointers are DEVICE pointers (float32 unless noted); `stream` as above. */

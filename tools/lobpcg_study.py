@@ -83,7 +83,59 @@ class TwoLevel:
         return y + self.tri(R - self.L @ y)
 
 
-def two_stage_rr(S, AS, m):
+RQI_STATS = {"calls": 0, "fallback": 0, "steps": 0}
+
+
+def rqi3_lowest(GA, GB, max_steps=6):
+    """Lowest pair of the (unit-diagonal-scaled) 3 x 3 pencil by Rayleigh-quotient iteration from e_0 with
+    adjugate solves, checked for lowestness through the inertia of A - (theta - delta) B; None = use
+    the Jacobi path (the device routine geig3_lowest_rqi follows this)."""
+    A, B = 0.5 * (GA + GA.T), 0.5 * (GB + GB.T)
+    RQI_STATS["calls"] += 1
+    y = np.array([1.0, 0.0, 0.0])
+    th = A[0, 0] / B[0, 0]
+    scale = abs(A[0, 0]) + abs(A[1, 1]) + abs(A[2, 2])
+    ok = False
+    for step in range(max_steps):
+        M = A - th * B
+        r = B @ y
+        c00 = M[1, 1] * M[2, 2] - M[1, 2] ** 2
+        c01 = M[0, 2] * M[1, 2] - M[0, 1] * M[2, 2]
+        c02 = M[0, 1] * M[1, 2] - M[0, 2] * M[1, 1]
+        c11 = M[0, 0] * M[2, 2] - M[0, 2] ** 2
+        c12 = M[0, 1] * M[0, 2] - M[0, 0] * M[1, 2]
+        c22 = M[0, 0] * M[1, 1] - M[0, 1] ** 2
+        z = np.array([c00 * r[0] + c01 * r[1] + c02 * r[2], c01 * r[0] + c11 * r[1] + c12 * r[2],
+                      c02 * r[0] + c12 * r[1] + c22 * r[2]])
+        zm = np.abs(z).max()
+        if not (zm > 0 and np.isfinite(zm)):
+            break
+        z /= zm
+        zb = z @ B @ z
+        if not zb > 0:
+            break
+        thn = (z @ A @ z) / zb
+        y = z / np.sqrt(zb)
+        RQI_STATS["steps"] += 1
+        done = abs(thn - th) <= 1e-10 * scale
+        th = thn
+        if done:
+            ok = True
+            break
+    if ok:
+        # A - (th - delta) B positive definite (leading minors, no divisions) <=> nothing below th - delta
+        M = A - (th - 1e-9 * scale) * B
+        m2 = M[0, 0] * M[1, 1] - M[0, 1] ** 2
+        det = (M[0, 0] * (M[1, 1] * M[2, 2] - M[1, 2] ** 2) + M[0, 1] * (M[0, 2] * M[1, 2] - M[0, 1] * M[2, 2])
+               + M[0, 2] * (M[0, 1] * M[1, 2] - M[0, 2] * M[1, 1]))
+        ok = M[0, 0] > 0 and m2 > 0 and det > 0
+    if not ok:
+        RQI_STATS["fallback"] += 1
+        return None
+    return th, y
+
+
+def two_stage_rr(S, AS, m, rqi=False):
     """The restricted Rayleigh-Ritz step of rr_two_stage (csrc/mac.cu): per column c the lowest
     pair on span{x_c, w_c, p_c} (3 x 3), then the m x m problem on the results.  Returns
     (theta [m], Y [3m, m]) like the full step."""
@@ -94,8 +146,12 @@ def two_stage_rr(S, AS, m):
         Sc, ASc = S[:, idx], AS[:, idx]
         d = 1.0 / np.sqrt((Sc * Sc).sum(axis=0))
         GA, GB = (Sc.T @ ASc) * np.outer(d, d), (Sc.T @ Sc) * np.outer(d, d)
-        lam, Y = eigh(0.5 * (GA + GA.T), 0.5 * (GB + GB.T))
-        Y6[idx, c] = Y[:, 0] * d
+        got = rqi3_lowest(GA, GB) if (rqi and nb == 3) else None
+        if got is not None:
+            Y6[idx, c] = got[1] * d
+        else:
+            lam, Y = eigh(0.5 * (GA + GA.T), 0.5 * (GB + GB.T))
+            Y6[idx, c] = Y[:, 0] * d
     U, AU = S @ Y6, AS @ Y6
     GA, GB = U.T @ AU, U.T @ U
     lam, Y2 = eigh(0.5 * (GA + GA.T), 0.5 * (GB + GB.T))
@@ -131,8 +187,8 @@ def lobpcg(L, m, prec, tol=1e-10, max_iters=3000, inner=0, inner_omega=None, X0=
         S = [X, W] + ([P] if P is not None else [])
         AS = [AX, AW] + ([AP] if P is not None else [])
         S, AS = np.hstack(S), np.hstack(AS)
-        if rr == "two-stage" and P is not None:
-            th, Y = two_stage_rr(S, AS, m)
+        if rr in ("two-stage", "two-stage-rqi") and P is not None:
+            th, Y = two_stage_rr(S, AS, m, rqi=rr == "two-stage-rqi")
             Pn = S[:, m:] @ Y[m:]
             APn = AS[:, m:] @ Y[m:]
             X = X @ Y[:m] + Pn
@@ -186,6 +242,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the C5 graph (poses, candidates)")
     ap.add_argument("--k", type=int, default=1000)
     ap.add_argument("--fw", type=int, default=0, help="run this many Frank-Wolfe iterations per variant instead")
+    ap.add_argument("--rqi", action="store_true", help="with --fw: only the two-stage variants, Jacobi against RQI stage 1")
     a = ap.parse_args()
     R, Pn, mc = 8, int(12500 * a.scale), int(1_000_000 * a.scale)
     fixed, cand, n = mac_scale_graph(R, Pn, mc)
@@ -200,18 +257,26 @@ def main():
         print(f"n = {n}, {mc} candidates, budget {k}: {a.fw} Frank-Wolfe iterations, warm-started solves")
         base = None
         hats = {h: chain_hats(n, R, Pn, h) for h in (128, 64, 32)}
-        for label, kw in (("block 2 (the GPU solver)", dict(m=2)), ("block 2, two-stage Rayleigh-Ritz", dict(m=2, rr="two-stage")),
+        variants = (("block 2 (the GPU solver)", dict(m=2)), ("block 2, two-stage Rayleigh-Ritz", dict(m=2, rr="two-stage")),
                           ("block 1", dict(m=1)),
                           ("block 2 + 1 smoothing step", dict(m=2, inner=1)),
                           ("block 1 + 1 smoothing step", dict(m=1, inner=1)),
                           ("block 2, two-level h=128", dict(m=2, make_prec=lambda L: TwoLevel(L, hats[128]))),
                           ("block 2, two-level h=64", dict(m=2, make_prec=lambda L: TwoLevel(L, hats[64]))),
-                          ("block 2, two-level h=32", dict(m=2, make_prec=lambda L: TwoLevel(L, hats[32])))):
+                          ("block 2, two-level h=32", dict(m=2, make_prec=lambda L: TwoLevel(L, hats[32]))))
+        if a.rqi:
+            variants = (("block 2, two-stage Rayleigh-Ritz", dict(m=2, rr="two-stage")),
+                        ("block 2, two-stage, RQI stage 1", dict(m=2, rr="two-stage-rqi")))
+        for label, kw in variants:
             t0 = time.time()
             counts, spmm, selection = frank_wolfe(n, fixed, cand, k, a.fw, **kw)
             base = selection if base is None else base
             print(f"  {label:30s} LOBPCG iterations {sum(counts):5d} (first {counts[0]}, then mean {np.mean(counts[1:]):.0f})  "
                   f"SpMM {spmm:5d}  selection differs in {len(set(base) ^ set(selection))} edges  {time.time() - t0:.0f} s", flush=True)
+            if kw.get("rr") == "two-stage-rqi":
+                print(f"    RQI stage 1: {RQI_STATS['calls']} solves, {RQI_STATS['fallback']} fell back to the Jacobi path, "
+                      f"{RQI_STATS['steps'] / max(1, RQI_STATS['calls']):.2f} steps per solve")
+                print("    per solve:", counts)
         return
     print(f"n = {n}, nnz = {L.nnz}, first Frank-Wolfe Laplacian (greedy start, {k} active candidates)")
     ref = None

@@ -2128,7 +2128,7 @@ struct PersistArgs {
   const double* sup;     // sup[i] = L[i][i+1], fixed + active (sup[n-1] = 0)
   double *X, *AX, *W, *P, *AP;     // global copies: X/AX in and out, W exchange buffer
   double *fA, *fB, *bA, *bB;       // [grid], [MAXM][grid] CTA aggregates of the two scans
-  double *pres, *pcs, *pgram;      // [MAXM][grid], [MAXM][grid], [2*NPAIR][grid] partial sums
+  double *pres, *pcs, *pgram;      // [MAXM][grid], [MAXM][grid], [grid][2*NPAIR] partial sums
   double theta0[MAXM];
   double tol;
   const double* lnorm;   // ||L||_inf, device resident (written by prepare_matrix on the same stream)
@@ -2159,6 +2159,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   __shared__ double s_mu[MAXM];
   __shared__ double s_res[MAXM];
   __shared__ double s_G[2 * NPAIR];
+  __shared__ double s_gtmp[2 * NPAIR * 12];   // grid_sum_gram: 12 partial sums per value
   __shared__ double s_C[MAXS][MAXM];
   __shared__ double s_theta[MAXM];
   __shared__ int s_ok;
@@ -2293,14 +2294,20 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   int it = 0;
 
   // value entering this CTA from the CTAs before (forward) / after (backward) it
-  auto cta_prefix = [&](const double* gA, const double* gB, bool rev) {
-    double A = 1.0, B[MAXM];
+  // `extra` (nullable): [grid] values read in the same round trip; their sum over the grid is returned
+  auto cta_prefix = [&](const double* gA, const double* gB, bool rev, const double* extra) -> double {
+    double A = 1.0, B[MAXM], ex = 0.0;
 #pragma unroll
     for (int c = 0; c < MAXM; ++c) B[c] = 0.0;
     if (tid < nb_grid) {
       A = __ldcg(gA + tid);
 #pragma unroll
       for (int c = 0; c < MAXM; ++c) B[c] = __ldcg(gB + static_cast<size_t>(c) * nb_grid + tid);
+      if (extra) ex = __ldcg(extra + tid);
+    }
+    if (extra) {
+      ex = warp_sum(ex);
+      if (lane == 0) s_red[warp][0] = ex;
     }
     if (rev) block_scan_affine<true>(A, B, shA, shB);
     else block_scan_affine<false>(A, B, shA, shB);
@@ -2314,6 +2321,10 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       for (int c = 0; c < MAXM; ++c) s_in[c] = B[c];
     }
     __syncthreads();
+    double total = 0.0;
+    if (extra)
+      for (int k = 0; k < NW; ++k) total += s_red[k][0];
+    return total;
   };
   // CTA-level sums of MAXM per-thread values -> gdst[c][b]  (fixed order: deterministic)
   auto block_sum2 = [&](const double (&vals)[MAXM], double* gdst) {
@@ -2351,37 +2362,45 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     }
     __syncthreads();
   };
-  auto grid_sum_gram = [&](const double* gsrc, double* out_s) {   // 2 * NPAIR values
-    constexpr int PARTS = 6, PER = MAXG / PARTS;
-    static_assert(2 * NPAIR * PARTS <= T, "needs one thread per (value, part)");
-    const int k = tid / PARTS, part = tid % PARTS;
-    double acc = 0.0;
-    if (k < 2 * NPAIR) {
-      double vals[PER];
+  // 2 * NPAIR values; gsrc is [CTA][2 * NPAIR]: a CTA's partials are 336 contiguous bytes, read as
+  // 21 16-byte pairs; 12 threads per pair take every 12th CTA, all loads in flight before the first add
+  auto grid_sum_gram = [&](const double* gsrc, double* out_s) {
+    constexpr int PARTS = 12, PER = MAXG / PARTS, NP2 = NPAIR;   // NPAIR pairs of the 2 * NPAIR values
+    static_assert(NP2 * PARTS <= T, "needs one thread per (pair of values, part)");
+    const int kp = tid % NP2, part = tid / NP2;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (part < PARTS) {
+      double2 vals[PER];
 #pragma unroll
       for (int i = 0; i < PER; ++i) {
         const int q = part + PARTS * i;
-        vals[i] = q < nb_grid ? __ldcg(gsrc + static_cast<size_t>(k) * nb_grid + q) : 0.0;
+        vals[i] = q < nb_grid ? __ldcg(reinterpret_cast<const double2*>(gsrc + static_cast<size_t>(q) * (2 * NPAIR)) + kp)
+                              : make_double2(0.0, 0.0);
       }
 #pragma unroll
-      for (int i = 0; i < PER; ++i) acc += vals[i];
+      for (int i = 0; i < PER; ++i) {
+        acc0 += vals[i].x;
+        acc1 += vals[i].y;
+      }
     }
     __syncthreads();
     // combine the PARTS partial sums of each value in a fixed order through shared memory
-    double* tmp = &s_red[0][0];           // NW * 2 * NPAIR doubles >= 2 * NPAIR * PARTS
-    if (k < 2 * NPAIR) tmp[k * PARTS + part] = acc;
+    if (part < PARTS) {
+      s_gtmp[(2 * kp) * PARTS + part] = acc0;
+      s_gtmp[(2 * kp + 1) * PARTS + part] = acc1;
+    }
     __syncthreads();
     if (tid < 2 * NPAIR) {
       double t2 = 0.0;
 #pragma unroll
-      for (int i = 0; i < PARTS; ++i) t2 += tmp[tid * PARTS + i];
+      for (int i = 0; i < PARTS; ++i) t2 += s_gtmp[tid * PARTS + i];
       out_s[tid] = t2;
     }
     __syncthreads();
   };
 
   long long t_prev = clock64();
-  long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // slots: see the print in FiedlerSolver::release
   __shared__ long long rrprof_acc[8];
   if (tid < 8) rrprof_acc[tid] = 0;
   __syncthreads();
@@ -2598,7 +2617,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     grid_sum2(a.pres, s_res);
     res_out = s_res[0] / lnorm_v;
     if (res_out < a.tol) { status = 0; break; }
-    cta_prefix(a.fA, a.fB, false);
+    cta_prefix(a.fA, a.fB, false, nullptr);
     double y[MAXM];
 #pragma unroll
     for (int c = 0; c < MAXM; ++c)
@@ -2638,7 +2657,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     GRID_SYNC();
     tick(6);
     // ---- phase 3: exact backward walk -> W = M^-1 r, column sums ------------------------------
-    cta_prefix(a.bA, a.bB, true);
+    cta_prefix(a.bA, a.bB, true, nullptr);
     double xb[MAXM];
 #pragma unroll
     for (int c = 0; c < MAXM; ++c)
@@ -2720,7 +2739,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       if (tid < 2 * NPAIR) {
         double acc = 0.0;
         for (int k = 0; k < NW; ++k) acc += s_red[k][tid];
-        a.pgram[static_cast<size_t>(tid) * nb_grid + b] = acc;
+        a.pgram[static_cast<size_t>(b) * (2 * NPAIR) + tid] = acc;
       }
       __syncthreads();
     }
@@ -2748,6 +2767,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       }
     }
     __syncthreads();
+    tick(13);
     if (warp == 0) {
       int use = sdim;
       long long* rrp = (a.prof && b == 0) ? rrprof_acc : nullptr;
@@ -2810,7 +2830,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       continue;
     }
     have_p = true;
-    tick(4);
+    tick(12);
     if (it % 50 == 49) {
       // refresh AX = L X against drift
       ax_from_x();
@@ -2830,13 +2850,8 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
           a.AP[o] = APV(j, c);
         }
   if (do_prof) {
-    for (int k = 0; k < 7; ++k) a.prof[k] += prof_acc[k];
-    a.prof[7] += prof_acc[7];     // lap_apply: mean, centring, neighbour exchange
-    a.prof[8] += prof_acc[10];    // lap_apply: flat gather pass (to the CTA barrier)
-    a.prof[9] += prof_acc[11];    // lap_apply: own product slots summed
-    a.prof[13] += it;
-    a.prof[14] += prof_acc[8];
-    a.prof[15] += prof_acc[7] + prof_acc[9] + prof_acc[10] + prof_acc[11];
+    for (int k = 0; k < 16; ++k) a.prof[k] += prof_acc[k];
+    a.prof[16] += it;
   }
   if (b == 0 && tid == 0) {
     for (int c = 0; c < MAXM; ++c) a.out[c] = theta[c];
@@ -3587,8 +3602,8 @@ struct FiedlerSolver {
     CSLAM_TRY(dev_alloc(&pout, MAXM + 4));
     CSLAM_TRY(dev_alloc(&pbar, kBarrierWords));
     if (getenv("CSLAM_LOBPCG_PROF")) {
-      CSLAM_TRY(dev_alloc(&pprof, 16));
-      CSLAM_CUDA(cudaMemsetAsync(pprof, 0, 16 * sizeof(long long), stream));
+      CSLAM_TRY(dev_alloc(&pprof, 24));
+      CSLAM_CUDA(cudaMemsetAsync(pprof, 0, 24 * sizeof(long long), stream));
     }
     return CSLAM_OK;
   }
@@ -3747,12 +3762,16 @@ struct FiedlerSolver {
       dev_free(*p);
     x0_n = -1;
     if (pprof) {
-      long long hp[16] = {};
+      long long hp[24] = {};
       cudaMemcpy(hp, pprof, sizeof(hp), cudaMemcpyDeviceToHost);
-      const double it_ = static_cast<double>(std::max<long long>(hp[13], 1));
-      fprintf(stderr, "[cslam lobpcg prof] cycles/iter of CTA 0 over %lld iters: p1 %.0f p2 %.0f p3 %.0f p4 (Gram) %.0f p5 %.0f rr %.0f barriers %.0f | before p4: gridsum %.0f spmm %.0f (centre + exchange %.0f, flat gathers %.0f, own slots %.0f)\n",
-              hp[13], hp[0] / it_, hp[1] / it_, hp[2] / it_, hp[3] / it_, hp[4] / it_, hp[5] / it_, hp[6] / it_,
-              hp[14] / it_, hp[15] / it_, hp[7] / it_, hp[8] / it_, hp[9] / it_);
+      const double it_ = static_cast<double>(std::max<long long>(hp[16], 1));
+      auto c = [&](int k) { return hp[k] / it_; };
+      fprintf(stderr,
+              "[cslam lobpcg prof] cycles/iter of CTA 0 over %lld iters: p1 residual+fwd aggregates %.0f | p2 fwd walk+bwd aggregates %.0f | "
+              "p3 bwd walk %.0f | mean all-gather %.0f, centre+exchange %.0f, flat gathers %.0f, own slots %.0f, rest of SpMM %.0f | "
+              "Gram partials %.0f | Gram all-gather %.0f, unpack %.0f, Rayleigh-Ritz %.0f, basis update %.0f | barriers %.0f | total %.0f\n",
+              hp[16], c(0), c(1), c(2), c(8), c(7), c(10), c(11), c(9), c(3), c(4), c(13), c(5), c(12), c(6),
+              c(0) + c(1) + c(2) + c(3) + c(4) + c(5) + c(6) + c(7) + c(8) + c(9) + c(10) + c(11) + c(12) + c(13));
       dev_free(pprof);
     }
     dev_free(pbar);

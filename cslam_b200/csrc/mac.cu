@@ -1792,8 +1792,9 @@ __device__ __forceinline__ bool geig3_lowest(int nb, const double (&Ain)[3][3], 
 // steps per solve on the C5 selection), against ~9 Jacobi rotations behind a Cholesky reduction.
 // RQI finds AN eigenpair; that it is the lowest is checked through the leading minors of
 // A - (th - delta) B (Sylvester).  Returns 1 done, 0 B numerically singular (same test as the
-// Cholesky pivots of geig3_lowest), -1 not converged or not the lowest pair: the caller takes the
-// Jacobi path (~10 % of the solves, tools/lobpcg_study.py --fw 20 --rqi; same iterates).
+// Cholesky pivots of geig3_lowest), -1 not converged or still not the lowest pair after one deflation:
+// the caller takes the Jacobi path (1.4 % of the solves on the C5 selection, 9 % take the deflation
+// step: tools/lobpcg_study.py --fw 20 --rqi; same iterates as with the Jacobi solve).
 __device__ __forceinline__ int geig3_lowest_rqi(const double (&Ain)[3][3], const double (&Bin)[3][3],
                                                 double (&y)[3], double& th) {
   double ds[3];
@@ -1812,42 +1813,92 @@ __device__ __forceinline__ int geig3_lowest_rqi(const double (&Ain)[3][3], const
   if (!(d1 > 1e-14) || !(detb > 1e-14 * d1)) return 0;
   const double scale = fabs(a00) + fabs(a11) + fabs(a22);
   double y0 = 1.0, y1 = 0.0, y2 = 0.0, t = a00, den = 1.0;
-  bool conv = false;
-  for (int step = 0; step < 6; ++step) {
-    const double m00 = a00 - t, m11 = a11 - t, m22 = a22 - t;
-    const double m01 = fma(-t, b01, a01), m02 = fma(-t, b02, a02), m12 = fma(-t, b12, a12);
-    const double r0 = y0 + b01 * y1 + b02 * y2, r1 = b01 * y0 + y1 + b12 * y2, r2 = b02 * y0 + b12 * y1 + y2;
-    const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
-    const double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
-    double z0 = c00 * r0 + c01 * r1 + c02 * r2;
-    double z1 = c01 * r0 + c11 * r1 + c12 * r2;
-    double z2 = c02 * r0 + c12 * r1 + c22 * r2;
-    const double zm = fmax(fabs(z0), fmax(fabs(z1), fabs(z2)));
-    if (!(zm > 1e-290) || !isfinite(zm)) break;
-    // power-of-two scaling to O(1) (no division): 2^(1023 - exponent(zm))
-    const int ebits = (__double2hiint(zm) >> 20) & 0x7ff;
-    const double sc = __hiloint2double((2046 - min(ebits, 2045)) << 20, 0);
-    z0 *= sc; z1 *= sc; z2 *= sc;
-    const double az0 = a00 * z0 + a01 * z1 + a02 * z2, az1 = a01 * z0 + a11 * z1 + a12 * z2,
-                 az2 = a02 * z0 + a12 * z1 + a22 * z2;
-    const double bz0 = z0 + b01 * z1 + b02 * z2, bz1 = b01 * z0 + z1 + b12 * z2, bz2 = b02 * z0 + b12 * z1 + z2;
-    const double num = z0 * az0 + z1 * az1 + z2 * az2;
-    den = z0 * bz0 + z1 * bz1 + z2 * bz2;
-    if (!(den > 0.0)) break;
-    const double tn = num / den;
-    y0 = z0; y1 = z1; y2 = z2;
-    const bool done = fabs(tn - t) <= 1e-10 * scale;
-    t = tn;
-    if (done) { conv = true; break; }
-  }
-  if (!conv) return -1;
-  {
-    const double tl = t - 1e-9 * scale;
-    const double m00 = a00 - tl, m11 = a11 - tl, m22 = a22 - tl;
-    const double m01 = fma(-tl, b01, a01), m02 = fma(-tl, b02, a02), m12 = fma(-tl, b12, a12);
-    const double minor2 = m00 * m11 - m01 * m01;
-    const double det = m00 * (m11 * m22 - m12 * m12) + m01 * (m02 * m12 - m01 * m22) + m02 * (m01 * m12 - m02 * m11);
-    if (!(m00 > 0.0 && minor2 > 0.0 && det > 0.0)) return -1;
+  bool lowest = false;
+  for (int attempt = 0; attempt < 2 && !lowest; ++attempt) {
+    bool conv = false;
+    for (int step = 0; step < 6; ++step) {
+      const double m00 = a00 - t, m11 = a11 - t, m22 = a22 - t;
+      const double m01 = fma(-t, b01, a01), m02 = fma(-t, b02, a02), m12 = fma(-t, b12, a12);
+      const double r0 = y0 + b01 * y1 + b02 * y2, r1 = b01 * y0 + y1 + b12 * y2, r2 = b02 * y0 + b12 * y1 + y2;
+      const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
+      const double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
+      double z0 = c00 * r0 + c01 * r1 + c02 * r2;
+      double z1 = c01 * r0 + c11 * r1 + c12 * r2;
+      double z2 = c02 * r0 + c12 * r1 + c22 * r2;
+      const double zm = fmax(fabs(z0), fmax(fabs(z1), fabs(z2)));
+      if (!(zm > 1e-290) || !isfinite(zm)) break;
+      // power-of-two scaling to O(1) (no division): 2^(1023 - exponent(zm))
+      const int ebits = (__double2hiint(zm) >> 20) & 0x7ff;
+      const double sc = __hiloint2double((2046 - min(ebits, 2045)) << 20, 0);
+      z0 *= sc; z1 *= sc; z2 *= sc;
+      const double az0 = a00 * z0 + a01 * z1 + a02 * z2, az1 = a01 * z0 + a11 * z1 + a12 * z2,
+                   az2 = a02 * z0 + a12 * z1 + a22 * z2;
+      const double bz0 = z0 + b01 * z1 + b02 * z2, bz1 = b01 * z0 + z1 + b12 * z2, bz2 = b02 * z0 + b12 * z1 + z2;
+      const double num = z0 * az0 + z1 * az1 + z2 * az2;
+      den = z0 * bz0 + z1 * bz1 + z2 * bz2;
+      if (!(den > 0.0)) break;
+      const double tn = num / den;
+      y0 = z0; y1 = z1; y2 = z2;
+      const bool done = fabs(tn - t) <= 1e-10 * scale;
+      t = tn;
+      if (done) { conv = true; break; }
+    }
+    if (!conv) return -1;
+    {
+      const double tl = t - 1e-9 * scale;
+      const double m00 = a00 - tl, m11 = a11 - tl, m22 = a22 - tl;
+      const double m01 = fma(-tl, b01, a01), m02 = fma(-tl, b02, a02), m12 = fma(-tl, b12, a12);
+      const double minor2 = m00 * m11 - m01 * m01;
+      const double det = m00 * (m11 * m22 - m12 * m12) + m01 * (m02 * m12 - m01 * m22) + m02 * (m01 * m12 - m02 * m11);
+      lowest = m00 > 0.0 && minor2 > 0.0 && det > 0.0;
+    }
+    if (lowest) break;
+    if (attempt == 1) return -1;
+    // The iteration converged to another pair (t, y) (typical for the second column, whose x sits next
+    // to the SECOND Ritz value of its own 3 x 3 space): deflate it.  With beta = B y (y B-normalised),
+    // q_i = e_i - beta_i y spans the B-orthogonal complement for two indices i, j; on it the pencil is
+    // A_ij - t beta_i beta_j, B_ij - beta_i beta_j, solved in closed form; its lowest vector, lifted,
+    // starts the second iteration (which polishes it and is checked like the first).
+    {
+      const double nrm = rsqrt(den);
+      y0 *= nrm; y1 *= nrm; y2 *= nrm;
+      const double e0 = y0 + b01 * y1 + b02 * y2, e1 = b01 * y0 + y1 + b12 * y2, e2 = b02 * y0 + b12 * y1 + y2;
+      const double w0 = fabs(e0 * y0), w1 = fabs(e1 * y1), w2 = fabs(e2 * y2);
+      const int drop = (w0 >= w1 && w0 >= w2) ? 0 : (w1 >= w2 ? 1 : 2);
+      // (i, j) = the two kept indices, i < j
+      const double aii = drop == 0 ? a11 : a00, ajj = drop == 2 ? a11 : a22;
+      const double aij = drop == 0 ? a12 : (drop == 1 ? a02 : a01);
+      const double bij = drop == 0 ? b12 : (drop == 1 ? b02 : b01);
+      const double ei = drop == 0 ? e1 : e0, ej = drop == 2 ? e1 : e2;
+      const double p11 = aii - t * ei * ei, p12 = aij - t * ei * ej, p22 = ajj - t * ej * ej;
+      const double q11 = 1.0 - ei * ei, q12 = bij - ei * ej, q22 = 1.0 - ej * ej;
+      const double qa = q11 * q22 - q12 * q12;
+      const double qb = p11 * q22 + p22 * q11 - 2.0 * p12 * q12;
+      const double qc = p11 * p22 - p12 * p12;
+      const double disc = qb * qb - 4.0 * qa * qc;
+      if (!(qa > 0.0 && qb > 0.0 && disc >= 0.0)) return -1;
+      const double lam = 2.0 * qc / (qb + sqrt(disc));
+      const double u0 = p12 - lam * q12, u1 = -(p11 - lam * q11);   // null vector of the first row
+      const double v0 = p22 - lam * q22, v1 = -(p12 - lam * q12);   // ... of the second row
+      const bool first = u0 * u0 + u1 * u1 >= v0 * v0 + v1 * v1;
+      const double zi = first ? u0 : v0, zj = first ? u1 : v1;
+      const double sh = zi * ei + zj * ej;
+      double n0 = (drop == 0 ? 0.0 : zi) - sh * y0;                 // index 0 is i unless dropped
+      double n1 = (drop == 1 ? 0.0 : (drop == 0 ? zi : zj)) - sh * y1;
+      double n2 = (drop == 2 ? 0.0 : zj) - sh * y2;
+      const double nm = fmax(fabs(n0), fmax(fabs(n1), fabs(n2)));
+      if (!(nm > 1e-290) || !isfinite(nm)) return -1;
+      const int ebits = (__double2hiint(nm) >> 20) & 0x7ff;
+      const double sc = __hiloint2double((2046 - min(ebits, 2045)) << 20, 0);
+      n0 *= sc; n1 *= sc; n2 *= sc;
+      const double bn0 = n0 + b01 * n1 + b02 * n2, bn1 = b01 * n0 + n1 + b12 * n2, bn2 = b02 * n0 + b12 * n1 + n2;
+      const double an0 = a00 * n0 + a01 * n1 + a02 * n2, an1 = a01 * n0 + a11 * n1 + a12 * n2,
+                   an2 = a02 * n0 + a12 * n1 + a22 * n2;
+      den = n0 * bn0 + n1 * bn1 + n2 * bn2;
+      if (!(den > 0.0)) return -1;
+      t = (n0 * an0 + n1 * an1 + n2 * an2) / den;
+      y0 = n0; y1 = n1; y2 = n2;
+    }
   }
   const double nrm = rsqrt(den);
   th = t;

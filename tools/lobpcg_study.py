@@ -88,51 +88,83 @@ RQI_STATS = {"calls": 0, "fallback": 0, "steps": 0}
 
 def rqi3_lowest(GA, GB, max_steps=6):
     """Lowest pair of the (unit-diagonal-scaled) 3 x 3 pencil by Rayleigh-quotient iteration from e_0 with
-    adjugate solves, checked for lowestness through the inertia of A - (theta - delta) B; None = use
-    the Jacobi path (the device routine geig3_lowest_rqi follows this)."""
+    adjugate solves, checked for lowestness through the leading minors of A - (theta - delta) B.  When the
+    iteration lands on another eigenpair (theta_f, y_f) that pair is deflated: the 2 x 2 pencil on the
+    B-orthogonal complement of y_f is solved in closed form and its lowest vector is the start of a second
+    iteration.  None = use the Jacobi path (the device routine geig3_lowest_rqi follows this)."""
     A, B = 0.5 * (GA + GA.T), 0.5 * (GB + GB.T)
     RQI_STATS["calls"] += 1
     y = np.array([1.0, 0.0, 0.0])
     th = A[0, 0] / B[0, 0]
     scale = abs(A[0, 0]) + abs(A[1, 1]) + abs(A[2, 2])
-    ok = False
-    for step in range(max_steps):
-        M = A - th * B
-        r = B @ y
-        c00 = M[1, 1] * M[2, 2] - M[1, 2] ** 2
-        c01 = M[0, 2] * M[1, 2] - M[0, 1] * M[2, 2]
-        c02 = M[0, 1] * M[1, 2] - M[0, 2] * M[1, 1]
-        c11 = M[0, 0] * M[2, 2] - M[0, 2] ** 2
-        c12 = M[0, 1] * M[0, 2] - M[0, 0] * M[1, 2]
-        c22 = M[0, 0] * M[1, 1] - M[0, 1] ** 2
-        z = np.array([c00 * r[0] + c01 * r[1] + c02 * r[2], c01 * r[0] + c11 * r[1] + c12 * r[2],
-                      c02 * r[0] + c12 * r[1] + c22 * r[2]])
-        zm = np.abs(z).max()
-        if not (zm > 0 and np.isfinite(zm)):
+    for attempt in range(2):
+        ok = False
+        for step in range(max_steps):
+            M = A - th * B
+            r = B @ y
+            c00 = M[1, 1] * M[2, 2] - M[1, 2] ** 2
+            c01 = M[0, 2] * M[1, 2] - M[0, 1] * M[2, 2]
+            c02 = M[0, 1] * M[1, 2] - M[0, 2] * M[1, 1]
+            c11 = M[0, 0] * M[2, 2] - M[0, 2] ** 2
+            c12 = M[0, 1] * M[0, 2] - M[0, 0] * M[1, 2]
+            c22 = M[0, 0] * M[1, 1] - M[0, 1] ** 2
+            z = np.array([c00 * r[0] + c01 * r[1] + c02 * r[2], c01 * r[0] + c11 * r[1] + c12 * r[2],
+                          c02 * r[0] + c12 * r[1] + c22 * r[2]])
+            zm = np.abs(z).max()
+            if not (zm > 0 and np.isfinite(zm)):
+                break
+            z /= zm
+            zb = z @ B @ z
+            if not zb > 0:
+                break
+            thn = (z @ A @ z) / zb
+            y = z / np.sqrt(zb)
+            RQI_STATS["steps"] += 1
+            done = abs(thn - th) <= 1e-10 * scale
+            th = thn
+            if done:
+                ok = True
+                break
+        if not ok:
             break
-        z /= zm
-        zb = z @ B @ z
-        if not zb > 0:
-            break
-        thn = (z @ A @ z) / zb
-        y = z / np.sqrt(zb)
-        RQI_STATS["steps"] += 1
-        done = abs(thn - th) <= 1e-10 * scale
-        th = thn
-        if done:
-            ok = True
-            break
-    if ok:
         # A - (th - delta) B positive definite (leading minors, no divisions) <=> nothing below th - delta
         M = A - (th - 1e-9 * scale) * B
         m2 = M[0, 0] * M[1, 1] - M[0, 1] ** 2
         det = (M[0, 0] * (M[1, 1] * M[2, 2] - M[1, 2] ** 2) + M[0, 1] * (M[0, 2] * M[1, 2] - M[0, 1] * M[2, 2])
                + M[0, 2] * (M[0, 1] * M[1, 2] - M[0, 2] * M[1, 1]))
-        ok = M[0, 0] > 0 and m2 > 0 and det > 0
-    if not ok:
-        RQI_STATS["fallback"] += 1
-        return None
-    return th, y
+        if M[0, 0] > 0 and m2 > 0 and det > 0:
+            return th, y
+        ok = False
+        if attempt == 1:
+            break
+        # deflate (th, y): q_i = e_i - beta_i y spans the B-orthogonal complement for the two indices i, j
+        # with the smallest |beta|; A2 = A_ij - th beta_i beta_j, B2 = B_ij - beta_i beta_j
+        beta = B @ y
+        drop = int(np.argmax(np.abs(beta * y)))
+        i, j = [k for k in range(3) if k != drop]
+        a11, a12, a22 = A[i, i] - th * beta[i] ** 2, A[i, j] - th * beta[i] * beta[j], A[j, j] - th * beta[j] ** 2
+        b11, b12, b22 = B[i, i] - beta[i] ** 2, B[i, j] - beta[i] * beta[j], B[j, j] - beta[j] ** 2
+        qa = b11 * b22 - b12 * b12
+        qb = a11 * b22 + a22 * b11 - 2.0 * a12 * b12      # = -(linear coefficient)
+        qc = a11 * a22 - a12 * a12
+        disc = qb * qb - 4.0 * qa * qc
+        if not (qa > 0 and qb > 0 and disc >= 0):
+            break
+        lam = 2.0 * qc / (qb + np.sqrt(disc))
+        r1 = np.array([a12 - lam * b12, -(a11 - lam * b11)])   # null vector of row 1
+        r2 = np.array([a22 - lam * b22, -(a12 - lam * b12)])   # null vector of row 2
+        z2 = r1 if (r1 @ r1) >= (r2 @ r2) else r2
+        ynew = np.zeros(3)
+        ynew[i], ynew[j] = z2[0], z2[1]
+        ynew -= (z2[0] * beta[i] + z2[1] * beta[j]) * y
+        nb2 = ynew @ B @ ynew
+        if not nb2 > 0:
+            break
+        y = ynew / np.sqrt(nb2)
+        th = y @ A @ y
+        RQI_STATS["deflated"] = RQI_STATS.get("deflated", 0) + 1
+    RQI_STATS["fallback"] += 1
+    return None
 
 
 def two_stage_rr(S, AS, m, rqi=False):
@@ -275,7 +307,7 @@ def main():
                   f"SpMM {spmm:5d}  selection differs in {len(set(base) ^ set(selection))} edges  {time.time() - t0:.0f} s", flush=True)
             if kw.get("rr") == "two-stage-rqi":
                 print(f"    RQI stage 1: {RQI_STATS['calls']} solves, {RQI_STATS['fallback']} fell back to the Jacobi path, "
-                      f"{RQI_STATS['steps'] / max(1, RQI_STATS['calls']):.2f} steps per solve")
+                      f"{RQI_STATS['steps'] / max(1, RQI_STATS['calls']):.2f} steps per solve, {RQI_STATS.get('deflated', 0)} second attempts after deflation")
                 print("    per solve:", counts)
         return
     print(f"n = {n}, nnz = {L.nnz}, first Frank-Wolfe Laplacian (greedy start, {k} active candidates)")

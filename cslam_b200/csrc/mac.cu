@@ -2164,9 +2164,9 @@ __global__ void k_barrier_debug(unsigned int* counter, double* scratch, int reps
 // W gathers after the grid barrier: the barrier's acquire makes plain (L1-allocating) loads see
 // the other CTAs' stores; CSLAM_W_LDCG selects ld.global.cg instead (compile-time experiment)
 #ifdef CSLAM_W_LDCG
-#define W_LOAD(p) __ldcg(p)
+#define W_LOAD2(p) __ldcg(p)
 #else
-#define W_LOAD(p) (*(p))
+#define W_LOAD2(p) (*(p))
 #endif
 struct PersistArgs {
   int n, m, rpb;         // rows, block size of the eigen-solver, rows per CTA
@@ -2177,9 +2177,9 @@ struct PersistArgs {
   const double* v1;
   const double *diag, *dpiv, *lfac;
   const double* sup;     // sup[i] = L[i][i+1], fixed + active (sup[n-1] = 0)
-  double *X, *AX, *W, *P, *AP;     // global copies: X/AX in and out, W exchange buffer
-  double *fA, *fB, *bA, *bB;       // [grid], [MAXM][grid] CTA aggregates of the two scans
-  double *pres, *pcs, *pgram;      // [MAXM][grid], [MAXM][grid], [grid][2*NPAIR] partial sums
+  double *X, *AX, *W, *P, *AP;     // global copies: X/AX in and out; W = exchange buffer of the kernel, layout [row][2]
+  double *fA, *fB, *bA, *bB;       // fA / bA: [grid][4] = (A, B0, B1, -) CTA aggregates of the two scans (fB, bB unused)
+  double *pres, *pcs, *pgram;      // [grid][MAXM], [grid][MAXM], [grid][2*NPAIR] partial sums
   double theta0[MAXM];
   double tol;
   const double* lnorm;   // ||L||_inf, device resident (written by prepare_matrix on the same stream)
@@ -2350,10 +2350,12 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     double A = 1.0, B[MAXM], ex = 0.0;
 #pragma unroll
     for (int c = 0; c < MAXM; ++c) B[c] = 0.0;
-    if (tid < nb_grid) {
-      A = __ldcg(gA + tid);
-#pragma unroll
-      for (int c = 0; c < MAXM; ++c) B[c] = __ldcg(gB + static_cast<size_t>(c) * nb_grid + tid);
+    if (tid < nb_grid) {   // gA: [CTA][4] = (A, B0, B1, -), one 32 B sector per CTA
+      const double2 t0 = __ldcg(reinterpret_cast<const double2*>(gA) + 2 * tid);
+      const double2 t1 = __ldcg(reinterpret_cast<const double2*>(gA) + 2 * tid + 1);
+      A = t0.x;
+      B[0] = t0.y;
+      B[1] = t1.x;
       if (extra) ex = __ldcg(extra + tid);
     }
     if (extra) {
@@ -2377,7 +2379,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       for (int k = 0; k < NW; ++k) total += s_red[k][0];
     return total;
   };
-  // CTA-level sums of MAXM per-thread values -> gdst[c][b]  (fixed order: deterministic)
+  // CTA-level sums of MAXM per-thread values -> gdst[b][c]  (fixed order: deterministic)
   auto block_sum2 = [&](const double (&vals)[MAXM], double* gdst) {
 #pragma unroll
     for (int k = 0; k < MAXM; ++k) {
@@ -2388,28 +2390,37 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     if (tid < MAXM) {
       double acc = 0.0;
       for (int k = 0; k < NW; ++k) acc += s_red[k][tid];
-      gdst[static_cast<size_t>(tid) * nb_grid + b] = acc;
+      gdst[static_cast<size_t>(b) * MAXM + tid] = acc;
     }
     __syncthreads();
   };
-  // every CTA: out_s[k] = sum over CTAs of gsrc[k][*] in a fixed order.  All loads of a thread
+  // every CTA: out_s[k] = sum over CTAs of gsrc[*][k] in a fixed order.  All loads of a thread
   // are issued before the first use (fully unrolled, predicated), so a reduction costs one L2
   // round trip instead of one per loop iteration.
   constexpr int MAXG = 192;                 // upper bound on the grid size (one CTA per SM)
-  auto grid_sum2 = [&](const double* gsrc, double* out_s) {   // MAXM values, one warp each
+  auto grid_sum2 = [&](const double* gsrc, double* out_s) {   // MAXM = 2 values per CTA, one 16-byte load each
     constexpr int PER = MAXG / 32;
-    if (warp < MAXM) {
-      double vals[PER];
+    static_assert(MAXM == 2, "one double2 per CTA");
+    if (warp == 0) {
+      double2 vals[PER];
 #pragma unroll
       for (int i = 0; i < PER; ++i) {
         const int q = lane + 32 * i;
-        vals[i] = q < nb_grid ? __ldcg(gsrc + static_cast<size_t>(warp) * nb_grid + q) : 0.0;
+        vals[i] = q < nb_grid ? __ldcg(reinterpret_cast<const double2*>(gsrc) + q) : make_double2(0.0, 0.0);
       }
-      double acc = 0.0;
+      double ax_ = 0.0, ay_ = 0.0;
 #pragma unroll
-      for (int i = 0; i < PER; ++i) acc += vals[i];
-      acc = warp_sum(acc);
-      if (lane == 0) out_s[warp] = acc;
+      for (int i = 0; i < PER; ++i) {
+        ax_ += vals[i].x;
+        ay_ += vals[i].y;
+      }
+      // both totals in five exchange steps: the lower half-warp collects x, the upper one y
+      const bool hi = (lane & 16) != 0;
+      double keep = (hi ? ay_ : ax_) + __shfl_xor_sync(0xffffffffu, hi ? ax_ : ay_, 16);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+      if (lane == 0) out_s[0] = keep;
+      if (lane == 16) out_s[1] = keep;
     }
     __syncthreads();
   };
@@ -2463,6 +2474,13 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       t_prev = t;
     }
   };
+  // this thread's rows of a block vector -> the exchange buffer a.W, layout [row][2]
+  auto publish = [&](const double (&v)[CH][MAXM]) {
+    double2* dst = reinterpret_cast<double2*>(a.W) + row0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (valid[j]) dst[j] = make_double2(v[j][0], v[j][1]);
+  };
   // y = L v for this thread's rows.  v (registers) is also published in G (+ mu: the values there are
   // not centred yet), which serves the entries that are neither in this CTA nor next to the diagonal:
   //   * the tridiagonal part - every odometry edge - comes from registers: v of rows i-1 and i+1
@@ -2479,6 +2497,8 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   // Active entries next to the diagonal are part of sup already and contribute nothing here.
   auto lap_apply = [&](const double (&v)[CH][MAXM], const double* G, const double (&mu)[MAXM],
                        double (&y)[CH][MAXM]) {
+    static_assert(MAXM == 2, "the exchange buffer holds one 16-byte pair per row");
+    const double2* G2 = reinterpret_cast<const double2*>(G);   // [row] = (column 0, column 1)
     const unsigned full = 0xffffffffu;
     double lo[MAXM], hi[MAXM];
 #pragma unroll
@@ -2492,9 +2512,16 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     const bool rem_lo = tid == 0 && row0 > 0 && row0 <= n, rem_hi = valid[0] && row0 + CH >= row_end && row0 + CH < n;
     double rlo[MAXM], rhi[MAXM];
 #pragma unroll
-    for (int c = 0; c < MAXM; ++c) {
-      rlo[c] = (rem_lo && c < m) ? W_LOAD(G + static_cast<size_t>(c) * ld + row0 - 1) : mu[c];
-      rhi[c] = (rem_hi && c < m) ? W_LOAD(G + static_cast<size_t>(c) * ld + row0 + CH) : mu[c];
+    for (int c = 0; c < MAXM; ++c) rlo[c] = rhi[c] = mu[c];
+    if (rem_lo) {
+      const double2 t2 = W_LOAD2(G2 + (row0 - 1));
+      rlo[0] = t2.x;
+      rlo[1] = t2.y;
+    }
+    if (rem_hi) {
+      const double2 t2 = W_LOAD2(G2 + (row0 + CH));
+      rhi[0] = t2.x;
+      rhi[1] = t2.y;
     }
     tick(7);
     {
@@ -2515,9 +2542,13 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
             val[u] = f0 ? s_v0[e] : s_v1[e - tot0];
             slot[u] = f0 ? e : a.cap0 + (e - tot0);
           }
-#pragma unroll
-          for (int c = 0; c < MAXM; ++c)
-            g[u][c] = (on && c < m) ? W_LOAD(G + static_cast<size_t>(c) * ld + col) : mu[c];
+          g[u][0] = mu[0];
+          g[u][1] = mu[1];
+          if (on) {
+            const double2 t2 = W_LOAD2(G2 + col);
+            g[u][0] = t2.x;
+            g[u][1] = t2.y;
+          }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -2579,9 +2610,13 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
             const int dcol = col - (row0 + j);
             gv[j][u] = (dcol == 1 || dcol == -1) ? 0.0 : (fx ? V0[q] : V1[q]);
           }
-#pragma unroll
-          for (int c = 0; c < MAXM; ++c)
-            gw[j][u][c] = (on && c < m) ? W_LOAD(G + static_cast<size_t>(c) * ld + col) : mu[c];
+          gw[j][u][0] = mu[0];
+          gw[j][u][1] = mu[1];
+          if (on) {
+            const double2 t2 = W_LOAD2(G2 + col);
+            gw[j][u][0] = t2.x;
+            gw[j][u][1] = t2.y;
+          }
         }
       }
 #pragma unroll
@@ -2606,15 +2641,10 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   };
   // AX = L X with X published through global memory (start-up pass, periodic refresh)
   auto ax_from_x = [&]() {
-#pragma unroll
-    for (int j = 0; j < CH; ++j)
-      if (valid[j])
-#pragma unroll
-        for (int c = 0; c < MAXM; ++c)
-          if (c < m) a.X[static_cast<size_t>(c) * ld + row0 + j] = x[j][c];
+    publish(x);
     GRID_SYNC();
     const double zero[MAXM] = {0.0, 0.0};
-    lap_apply(x, a.X, zero, ax);
+    lap_apply(x, a.W, zero, ax);
   };
 
   bool init_pass = a.init != 0;
@@ -2657,9 +2687,8 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 #pragma unroll
     for (int c = 0; c < MAXM; ++c) s_incB[c][tid] = B[c];
     if (tid == T - 1) {
-      a.fA[b] = A;
-#pragma unroll
-      for (int c = 0; c < MAXM; ++c) a.fB[static_cast<size_t>(c) * nb_grid + b] = B[c];
+      reinterpret_cast<double2*>(a.fA)[2 * b] = make_double2(A, B[0]);
+      reinterpret_cast<double2*>(a.fA)[2 * b + 1] = make_double2(B[1], 0.0);
     }
     tick(0);
     GRID_SYNC();
@@ -2700,9 +2729,8 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 #pragma unroll
     for (int c = 0; c < MAXM; ++c) s_incB[c][tid] = B[c];
     if (tid == 0) {
-      a.bA[b] = A;
-#pragma unroll
-      for (int c = 0; c < MAXM; ++c) a.bB[static_cast<size_t>(c) * nb_grid + b] = B[c];
+      reinterpret_cast<double2*>(a.bA)[2 * b] = make_double2(A, B[0]);
+      reinterpret_cast<double2*>(a.bA)[2 * b + 1] = make_double2(B[1], 0.0);
     }
     tick(1);
     GRID_SYNC();
@@ -2725,9 +2753,11 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
             xb[c] = fma(-LF_NEXT(j), xb[c], w[j][c]);
             w[j][c] = xb[c];
             loc[c] += xb[c];
-            a.W[static_cast<size_t>(c) * ld + row0 + j] = xb[c];
           }
       }
+    // publish W in the exchange layout [row][2]: the thread's CH rows are 16 CH contiguous bytes and a
+    // warp's stores are contiguous too (the SpMM then gathers both columns of a row with one 16-byte load)
+    publish(w);
     block_sum2(loc, a.pcs);
     tick(2);
     GRID_SYNC();
@@ -3643,9 +3673,9 @@ struct FiedlerSolver {
     if (!coop) persist_variant = 0;
     if (const char* e = getenv("CSLAM_LOBPCG_VARIANT")) persist_variant = atoi(e);
     const size_t g = static_cast<size_t>(std::max(num_sms, 1));
-    CSLAM_TRY(dev_alloc(&pfA, g));
+    CSLAM_TRY(dev_alloc(&pfA, 4 * g));   // [CTA][4] = (A, B0, B1, -): scan aggregates of the forward substitution
     CSLAM_TRY(dev_alloc(&pfB, MAXM * g));
-    CSLAM_TRY(dev_alloc(&pbA, g));
+    CSLAM_TRY(dev_alloc(&pbA, 4 * g));   // ... of the backward substitution
     CSLAM_TRY(dev_alloc(&pbB, MAXM * g));
     CSLAM_TRY(dev_alloc(&ppres, MAXM * g));
     CSLAM_TRY(dev_alloc(&ppcs, MAXM * g));

@@ -2207,6 +2207,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   __shared__ double s_incB[MAXM][T];
   __shared__ double s_red[NW][2 * NPAIR];
   __shared__ double s_in[MAXM];
+  __shared__ double s_cf[MAXM];
   __shared__ double s_mu[MAXM];
   __shared__ double s_res[MAXM];
   __shared__ double s_G[2 * NPAIR];
@@ -2284,17 +2285,18 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   // Per-row constants of the solve live in shared memory, not in registers: the kernel is over its
   // register budget, and a spilled value costs an L2 round trip per use here (every grid barrier
   // invalidates L1, local memory included).  k: 0 lfac[i], 1 1 / dpiv[i], 2 diag[i], 3 L[i][i+1].
-  double* s_cst = reinterpret_cast<double*>(s_c1 + a.cap1);      // [4][CH][T]
+  double* s_cst = reinterpret_cast<double*>(s_c1 + a.cap1);      // [5][CH][T]
   auto cst = [&](int k, int j) -> double& { return s_cst[(k * CH + j) * T + tid]; };
 #define LF(j) cst(0, j)
 #define DP(j) cst(1, j)
 #define DG(j) cst(2, j)
 #define SU(j) cst(3, j)
+#define ZP(j) cst(4, j)   /* homogeneous forward solution of the CTA's block / d (see phase 1) */
 #define LF_NEXT(j) ((j) < CH - 1 ? cst(0, (j) + 1 < CH ? (j) + 1 : 0) : lfn_last)
   double lfn_last = 0.0;                                         // lfac of the row after this thread's last one
   // X, AX, W, AW in registers; P and AP (used by the Gram sums and the basis update only) in shared memory
   double x[CH][MAXM], ax[CH][MAXM], w[CH][MAXM], aw[CH][MAXM];
-  double* s_pap = s_cst + 4 * CH * T;                            // [2][CH][MAXM][T]
+  double* s_pap = s_cst + 5 * CH * T;                            // [2][CH][MAXM][T]
 #define PV(j, c) s_pap[(((j) * MAXM + (c)) * T) + tid]
 #define APV(j, c) s_pap[(((CH + (j)) * MAXM + (c)) * T) + tid]
   __shared__ double s_edge[2][NW][MAXM];                  // last / first row of every warp (lap_apply)
@@ -2336,6 +2338,44 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     }
   }
   const double sl0 = (valid[0] && row0 > 0) ? a.sup[row0 - 1] : 0.0;   // L[row0][row0 - 1]
+  // Per-solve constants of the one-exchange tridiagonal solve (phase 1): ZP(j) = y_hom / d with y_hom
+  // the forward solution of this CTA's block for a unit value entering it and a zero right-hand side;
+  // bpi_next = the backward aggregate of ZP over the threads after this one, cta_bpi = over the CTA.
+  double bpi_next = 0.0, cta_bpi = 0.0;
+  {
+    double A = 1.0, B[MAXM];
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) B[c] = 0.0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (valid[j]) A = -LF(j) * A;
+    block_scan_affine<false>(A, B, shA, shB);
+    s_incA[tid] = A;
+    __syncthreads();
+    double yh = tid == 0 ? 1.0 : s_incA[tid - 1];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      if (valid[j]) yh = -LF(j) * yh;
+      ZP(j) = valid[j] ? yh * DP(j) : 0.0;
+    }
+    A = 1.0;
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) B[c] = 0.0;
+#pragma unroll
+    for (int j = CH - 1; j >= 0; --j)
+      if (valid[j]) {
+        A = -LF_NEXT(j) * A;
+        B[0] = fma(-LF_NEXT(j), B[0], ZP(j));
+      }
+    block_scan_affine<true>(A, B, shA, shB);
+    s_incB[0][tid] = B[0];
+    __syncthreads();
+    bpi_next = tid == T - 1 ? 0.0 : s_incB[0][tid + 1];
+    cta_bpi = s_incB[0][0];
+    __syncthreads();
+  }
+
   double theta[MAXM];
 #pragma unroll
   for (int c = 0; c < MAXM; ++c) theta[c] = a.theta0[c];
@@ -2663,7 +2703,13 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
       block_sum2(loc, a.pcs);
       GRID_SYNC();
     } else {
-    // ---- phase 1: residual, forward aggregates -------------------------------------------
+    // ---- phase 1: residual; the tridiagonal solve as far as it goes WITHOUT the other CTAs ------
+    // W = T^-1 r with T = L D L^T: forward y_i = r_i - l_i y_{i-1}, z = y / d, backward
+    // x_i = z_i - l_{i+1} x_{i+1}.  Both recurrences are affine in the value c that enters the CTA's
+    // row range, so the CTA runs them with c = 0 now (y_loc, z_loc, and the backward aggregates of
+    // z_loc) and corrects with the per-solve constants ZP = (homogeneous forward solution) / d and
+    // its backward aggregates once c is known: ONE grid exchange for the whole solve instead of one
+    // per substitution.
     double A = 1.0, B[MAXM];
 #pragma unroll
     for (int c = 0; c < MAXM; ++c) B[c] = 0.0;
@@ -2683,25 +2729,16 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     }
     block_sum2(loc, a.pres);
     block_scan_affine<false>(A, B, shA, shB);
-    s_incA[tid] = A;
 #pragma unroll
     for (int c = 0; c < MAXM; ++c) s_incB[c][tid] = B[c];
     if (tid == T - 1) {
       reinterpret_cast<double2*>(a.fA)[2 * b] = make_double2(A, B[0]);
       reinterpret_cast<double2*>(a.fA)[2 * b + 1] = make_double2(B[1], 0.0);
     }
-    tick(0);
-    GRID_SYNC();
-    tick(6);
-    // ---- phase 2: convergence test, exact forward walk, backward aggregates ----------------
-    grid_sum2(a.pres, s_res);
-    res_out = s_res[0] / lnorm_v;
-    if (res_out < a.tol) { status = 0; break; }
-    cta_prefix(a.fA, a.fB, false, nullptr);
+    __syncthreads();
     double y[MAXM];
 #pragma unroll
-    for (int c = 0; c < MAXM; ++c)
-      y[c] = tid == 0 ? s_in[c] : fma(s_incA[tid - 1], s_in[c], s_incB[c][tid - 1]);
+    for (int c = 0; c < MAXM; ++c) y[c] = tid == 0 ? 0.0 : s_incB[c][tid - 1];
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < CH; ++j)
@@ -2710,7 +2747,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
         for (int c = 0; c < MAXM; ++c)
           if (c < m) {
             y[c] = fma(-LF(j), y[c], w[j][c]);
-            w[j][c] = y[c] * DP(j);  // z = y / d
+            w[j][c] = y[c] * DP(j);  // z_loc = y_loc / d
           }
       }
     A = 1.0;
@@ -2730,17 +2767,59 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     for (int c = 0; c < MAXM; ++c) s_incB[c][tid] = B[c];
     if (tid == 0) {
       reinterpret_cast<double2*>(a.bA)[2 * b] = make_double2(A, B[0]);
-      reinterpret_cast<double2*>(a.bA)[2 * b + 1] = make_double2(B[1], 0.0);
+      reinterpret_cast<double2*>(a.bA)[2 * b + 1] = make_double2(B[1], cta_bpi);
     }
-    tick(1);
+    tick(0);
     GRID_SYNC();
     tick(6);
-    // ---- phase 3: exact backward walk -> W = M^-1 r, column sums ------------------------------
-    cta_prefix(a.bA, a.bB, true, nullptr);
-    double xb[MAXM];
+    // ---- phase 2: convergence test; the values entering this CTA from both sides; exact walk -----
+    {
+      // thread q: forward aggregates of CTA q - 1 -> inclusive scan = the value entering CTA q
+      // (loaded before the residual sums so that the two all-gathers share one L2 round trip)
+      double FA = 1.0, FB[MAXM], BA = 1.0, BB[MAXM], bpi_q = 0.0;
 #pragma unroll
-    for (int c = 0; c < MAXM; ++c)
-      xb[c] = tid == T - 1 ? s_in[c] : fma(s_incA[tid + 1], s_in[c], s_incB[c][tid + 1]);
+      for (int c = 0; c < MAXM; ++c) FB[c] = BB[c] = 0.0;
+      double2 f0 = make_double2(1.0, 0.0), f1 = make_double2(0.0, 0.0);
+      double2 b0 = make_double2(1.0, 0.0), b1 = make_double2(0.0, 0.0);
+      if (tid >= 1 && tid < nb_grid) {
+        f0 = __ldcg(reinterpret_cast<const double2*>(a.fA) + 2 * (tid - 1));
+        f1 = __ldcg(reinterpret_cast<const double2*>(a.fA) + 2 * (tid - 1) + 1);
+      }
+      if (tid < nb_grid) {
+        b0 = __ldcg(reinterpret_cast<const double2*>(a.bA) + 2 * tid);
+        b1 = __ldcg(reinterpret_cast<const double2*>(a.bA) + 2 * tid + 1);
+      }
+      grid_sum2(a.pres, s_res);
+      res_out = s_res[0] / lnorm_v;
+      if (res_out < a.tol) { status = 0; break; }
+      FA = f0.x; FB[0] = f0.y; FB[1] = f1.x;
+      BA = b0.x; BB[0] = b0.y; BB[1] = b1.x; bpi_q = b1.y;
+      block_scan_affine<false>(FA, FB, shA, shB);
+      if (tid == b) {
+#pragma unroll
+        for (int c = 0; c < MAXM; ++c) s_cf[c] = FB[c];
+      }
+      // backward aggregates of CTA q, corrected for the value that enters CTA q -> inclusive suffix scan
+#pragma unroll
+      for (int c = 0; c < MAXM; ++c) BB[c] = fma(FB[c], bpi_q, BB[c]);
+      __syncthreads();   // (shA / shB are reused)
+      block_scan_affine<true>(BA, BB, shA, shB);
+      if (tid == 0 && b + 1 >= nb_grid) {
+#pragma unroll
+        for (int c = 0; c < MAXM; ++c) s_in[c] = 0.0;
+      }
+      if (tid == b + 1) {
+#pragma unroll
+        for (int c = 0; c < MAXM; ++c) s_in[c] = BB[c];
+      }
+      __syncthreads();
+    }
+    double cf[MAXM], xb[MAXM];
+#pragma unroll
+    for (int c = 0; c < MAXM; ++c) {
+      cf[c] = s_cf[c];
+      xb[c] = tid == T - 1 ? s_in[c] : fma(s_incA[tid + 1], s_in[c], fma(cf[c], bpi_next, s_incB[c][tid + 1]));
+    }
     __syncthreads();
 #pragma unroll
     for (int c = 0; c < MAXM; ++c) loc[c] = 0.0;
@@ -2750,7 +2829,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 #pragma unroll
         for (int c = 0; c < MAXM; ++c)
           if (c < m) {
-            xb[c] = fma(-LF_NEXT(j), xb[c], w[j][c]);
+            xb[c] = fma(-LF_NEXT(j), xb[c], fma(cf[c], ZP(j), w[j][c]));
             w[j][c] = xb[c];
             loc[c] += xb[c];
           }
@@ -2947,6 +3026,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
 #undef DP
 #undef DG
 #undef SU
+#undef ZP
 #undef LF_NEXT
 #undef PV
 #undef APV
@@ -3765,20 +3845,20 @@ struct FiedlerSolver {
       default: set_error("fiedler: bad persistent variant %d", ch); return CSLAM_ERR_INVALID;
     }
     // Staged entries per CTA (fixed adjacency off the tridiagonal / active adjacency; 28 B each with the
-    // product slot).  Together with the 64 KB of per-row state the CTA must stay under the 196 KB
+    // product slot).  Together with the 72 KB of per-row state the CTA must stay under the 196 KB
     // shared-memory carve-out: at the 228 KB one the 28 KB of L1 that remain make every W gather and
     // CTA-count all-gather slower - 27.6 ms per C5 selection with 5120 staged entries, 24.5 ms with
     // 2304-3328 (measured); a slice that does not fit is gathered per row from global memory instead
     // (the heaviest C5 CTA holds 2569 active entries; 28.6 / 33.0 ms with room for 1024 / 512).
     pa.cap0 = static_cast<int>(std::min<int64_t>(2048, std::max<int64_t>(256, (4 * fixr.nnz / grid + 255) / 256 * 256)));
-    pa.cap1 = 3840 - pa.cap0;
+    pa.cap1 = 3456 - pa.cap0;
     if (const char* e = getenv("CSLAM_LOBPCG_CAP1")) pa.cap1 = std::max(0, std::min(4096, atoi(e)));   // (experiments)
     if (const char* e = getenv("CSLAM_LOBPCG_CAP0")) pa.cap0 = std::max(0, std::min(4096, atoi(e)));
     pa.rr_impl = getenv("CSLAM_RR_IMPL") ? atoi(getenv("CSLAM_RR_IMPL")) : 2;
     pa.rr_sweeps = getenv("CSLAM_RR_SWEEPS") ? atoi(getenv("CSLAM_RR_SWEEPS")) : 3;   // (2-stage solve: 4 / 3 / 2 sweeps = 1082 / 1082 / 1102 iterations per C5 selection)
     pa.rr_tol2 = getenv("CSLAM_RR_TOL2") ? atof(getenv("CSLAM_RR_TOL2")) : 1e-32;
     const size_t dyn = static_cast<size_t>(pa.cap0 + pa.cap1) * ((1 + MAXM) * sizeof(double) + sizeof(int)) +
-                       static_cast<size_t>(4 + 2 * MAXM) * ch * threads * sizeof(double);
+                       static_cast<size_t>(5 + 2 * MAXM) * ch * threads * sizeof(double);
     CSLAM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
     CSLAM_CUDA(cudaEventRecord(e0, stream));
     {

@@ -2198,7 +2198,9 @@ struct PersistArgs {
 
 // MB = block size of the eigen-solver as a compile-time constant: every `c < m` guard below folds
 // away (fewer instructions in a loop body whose instruction fetch is a measured cost).
-template <int CH, int T, int MB>
+// PROF: the in-kernel cycle profile (CSLAM_LOBPCG_PROF=1) is a separate instantiation - its counters
+// cost registers the production kernel does not have.
+template <int CH, int T, int MB, bool PROF = false>
 __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   constexpr int NW = T / 32;
   __shared__ double shA[32];
@@ -2506,9 +2508,9 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   __shared__ long long rrprof_acc[8];
   if (tid < 8) rrprof_acc[tid] = 0;
   __syncthreads();
-  const bool do_prof = a.prof != nullptr && b == 0 && tid == 0;
+  const bool do_prof = PROF && a.prof != nullptr && b == 0 && tid == 0;
   auto tick = [&](int slot) {
-    if (do_prof) {
+    if (PROF && do_prof) {
       const long long t = clock64();
       prof_acc[slot] += t - t_prev;
       t_prev = t;
@@ -2930,7 +2932,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
     tick(13);
     if (warp == 0) {
       int use = sdim;
-      long long* rrp = (a.prof && b == 0) ? rrprof_acc : nullptr;
+      long long* rrp = (PROF && a.prof && b == 0) ? rrprof_acc : nullptr;
       auto solve = [&](int dim, long long* prof_to) {
         if (a.rr_impl == 2) return rr_two_stage(dim, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps, a.rr_tol2);
         return a.rr_impl ? rr_warp_elem(dim, m, s_GA, s_GB, s_C, s_th2, a.rr_sweeps, a.rr_tol2, s_rrtab, prof_to)
@@ -3009,7 +3011,7 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
           a.P[o] = PV(j, c);
           a.AP[o] = APV(j, c);
         }
-  if (do_prof) {
+  if (PROF && do_prof) {
     for (int k = 0; k < 16; ++k) a.prof[k] += prof_acc[k];
     a.prof[16] += it;
   }
@@ -3828,7 +3830,8 @@ struct FiedlerSolver {
     int threads = 0;
     switch (ch) {
       case 4:
-        fn = m == 2 ? reinterpret_cast<const void*>(&k_lobpcg_persist<4, 256, 2>)
+        fn = m == 2 ? (pprof ? reinterpret_cast<const void*>(&k_lobpcg_persist<4, 256, 2, true>)
+                             : reinterpret_cast<const void*>(&k_lobpcg_persist<4, 256, 2>))
                     : reinterpret_cast<const void*>(&k_lobpcg_persist<4, 256, 1>);
         threads = 256;
         break;

@@ -649,11 +649,11 @@ def run_ours(args):
                 "share_of_step": c_ms / (ms_dev / args.steps)}
     # The kernel with the largest share of the step: the persistent eigen-solver of the MAC stage
     # (one launch per Fiedler solve).  Its working set is register / shared-memory / L2 resident
-    # and every LOBPCG iteration is a chain of 4 grid-wide phases + a small eigen-solve, so it is
-    # LATENCY-bound: ncu (profiles/r2_lobpcg_persist_ncu_full.txt) shows DRAM at 0.02 % and L2 at
-    # 5.8 % of their peaks, 42 % of warp time at barriers.  The HBM fraction below is what the
-    # contract asks for (algorithmic bytes of one SpMM per iteration over the launch duration);
-    # us per LOBPCG iteration is the figure that matters.
+    # and every LOBPCG iteration is a chain of 3 grid-wide phases + a small eigen-solve, so it is
+    # LATENCY-bound: ncu (profiles/r2k_lobpcg_persist_ncu_full.txt) shows DRAM at 0.03 % and L2 at
+    # 2.7 % of their peaks, 54 % of the warp stall time at CTA barriers.  The HBM fraction below is
+    # what the contract asks for (algorithmic bytes of one SpMM per iteration over the launch
+    # duration); us per LOBPCG iteration is the figure that matters.
     roofline = roof_nns
     if mac is not None:
         st = mac.solver_timing()

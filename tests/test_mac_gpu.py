@@ -241,6 +241,66 @@ def test_two_stage_rayleigh_ritz_against_numpy():
     assert ok.value == 0
 
 
+def test_two_stage_rqi_lands_on_the_lowest_pair():
+    """The 3 x 3 problems of the two-stage step are solved by Rayleigh-quotient iteration from e_0; when
+    e_0 sits next to the SECOND eigenvector of its 3 x 3 pencil the iteration converges there, the
+    lowestness check (leading minors) fails and the pair is deflated.  Either way the result must be
+    the lowest pair: compared with the Jacobi-only form (negative sweep count) and with scipy."""
+    import ctypes
+    from scipy.linalg import eigh
+    from cslam_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(21)
+    for trial in range(40):
+        GA, GB = np.zeros((6, 6)), np.zeros((6, 6))
+        for c in range(2):
+            idx = [c, 2 + c, 4 + c]
+            Rm = rng.normal(size=(3, 3))
+            B3 = np.eye(3) + 0.2 * (Rm + Rm.T) / 2            # SPD, moderately coupled
+            lam = np.sort(rng.uniform(1e-6, 1.0, 3)) * (10.0 ** rng.integers(-6, 1))
+            if trial % 4 == 3:
+                lam[1] = lam[0] * (1 + 1e-4)                  # a close lowest pair
+            V = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+            # B-orthonormal eigenvectors Y with Y[:, k] ~ e_0 for k = trial % 3 (k = 1, 2: RQI lands elsewhere)
+            Lc = np.linalg.cholesky(B3)
+            k = trial % 3
+            V[:, k] = Lc.T @ np.array([1.0, 0.0, 0.0]) + 0.05 * rng.normal(size=3)
+            V = np.linalg.qr(V[:, [k] + [q for q in range(3) if q != k]])[0]
+            order = [k] + [q for q in range(3) if q != k]
+            Y = np.linalg.solve(Lc.T, V)                      # Y^T B Y = I
+            lam_c = np.empty(3)
+            lam_c[0], lam_c[1:] = lam[k], lam[[q for q in range(3) if q != k]]
+            Yi = np.linalg.inv(Y)
+            A3 = Yi.T @ np.diag(lam_c) @ Yi
+            GA[np.ix_(idx, idx)] = 0.5 * (A3 + A3.T)
+            GB[np.ix_(idx, idx)] = B3
+        out = {}
+        for sweeps in (8, -8):
+            C, th, ok = np.zeros((6, 2)), np.zeros(2), ctypes.c_int()
+            _lib.check(lib.cslam_debug_rayleigh_ritz(_lib.ptr(GA), _lib.ptr(GB), 6, 2, 2, sweeps, 1, 0,
+                                                     _lib.ptr(C), _lib.ptr(th), ctypes.byref(ok), None))
+            assert ok.value == 1
+            out[sweeps] = (th.copy(), C.copy())
+        lam_ref, _ = _two_stage_reference(GA, GB, 6, 2)
+        # (a lowest pair closer than the check's delta = 1e-9 x scale is one value for the purposes of the step)
+        rtol = 2e-4 if trial % 4 == 3 else 1e-9
+        for sweeps in (8, -8):
+            np.testing.assert_allclose(out[sweeps][0], lam_ref, rtol=rtol, atol=1e-30)
+        np.testing.assert_allclose(out[8][0], out[-8][0], rtol=max(rtol, 1e-10))
+
+
+def test_grid_barrier_hook_runs():
+    """The barrier micro-benchmark (profiles/r2k_barrier_ubench.txt) returns a plausible cycle count
+    for every recipe; recipe 0 is the barrier of the persistent kernels."""
+    import ctypes
+    from cslam_b200 import _lib
+    lib = _lib.load()
+    for variant in range(7):
+        c = ctypes.c_int64()
+        _lib.check(lib.cslam_debug_grid_barrier(16, 256, 200, 4, variant, 0, ctypes.byref(c)))
+        assert 100 < c.value < 200000
+
+
 def test_two_stage_solver_gives_the_same_selection(monkeypatch):
     """The whole Frank-Wolfe selection with the two-stage small eigen-solve: same Fiedler values
     and per-iteration sets as the reference goldens (the eigen-solver converges to the same pair;

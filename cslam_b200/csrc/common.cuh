@@ -63,17 +63,31 @@ struct DeviceGuard {
   }
 };
 
+// Device allocations.  Buffers up to kPoolMaxBytes come from the device's stream-ordered memory pool
+// with its release threshold raised to "never": a handle that is created and destroyed per call
+// (cslam_mac: ~40 buffers per selection) then recycles its memory instead of going to the driver,
+// where a cudaFree / cudaMalloc that trims or maps memory was observed to stall for up to a second.
+// Semantics stay those of cudaMalloc / cudaFree: the memory is usable on every stream when
+// dev_alloc returns, and dev_free waits for the device before the buffer can be reused.
+// CSLAM_DEV_POOL=0 switches the pool off.  Larger buffers (keyframe pools) use cudaMalloc / cudaFree.
+constexpr size_t kPoolMaxBytes = size_t(64) << 20;
+int pool_alloc(void** p, size_t bytes);   // lib.cu; CSLAM_OK, or a status with *p = nullptr (caller falls back)
+bool pool_free(void* p);                  // true: p came from the pool and has been returned to it
+
 template <typename T>
 inline int dev_alloc(T** p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
-  CSLAM_CUDA(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  const size_t bytes = count * sizeof(T);
+  if (bytes <= kPoolMaxBytes && pool_alloc(reinterpret_cast<void**>(p), bytes) == CSLAM_OK && *p) return CSLAM_OK;
+  *p = nullptr;
+  CSLAM_CUDA(cudaMalloc(reinterpret_cast<void**>(p), bytes));
   return CSLAM_OK;
 }
 
 template <typename T>
 inline void dev_free(T*& p) {
-  if (p) cudaFree(p);
+  if (p && !pool_free(p)) cudaFree(p);
   p = nullptr;
 }
 

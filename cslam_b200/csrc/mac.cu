@@ -2149,18 +2149,21 @@ __global__ void k_barrier_debug(unsigned int* counter, double* scratch, int reps
 //  per selection: 148 x 148 polling loads per round swamp the L2 slice that holds the slots.)
 
 // ------------------------------------------------------------------ persistent LOBPCG
-// The whole LOBPCG iteration as ONE cooperative kernel: one CTA per SM, every thread owns CH
-// consecutive rows and keeps its rows of X, AX, W, AW, P, AP in REGISTERS for the entire
-// solve; the only vector that travels through global memory is W (the SpMM gathers
-// neighbours' entries).  Four grid barriers per iteration:
-//   1  residual + forward substitution (thread / CTA aggregates)      | barrier
-//   2  CTA-prefix, exact forward re-walk, z = y / d, backward aggregates | barrier
-//   3  CTA-prefix, exact backward re-walk -> W, column sums             | barrier
-//   4  AW = L (W - mean), W -= mean, Gram partial sums                   | barrier
-//   5  every CTA reduces the Gram partials in the same fixed order, thread 0 solves the
-//      (<= 6x6) Rayleigh-Ritz problem, all threads update X, AX, P, AP in registers
+// The whole LOBPCG loop as ONE cooperative kernel: as few CTAs as hold the rows, every thread owns CH
+// consecutive rows and keeps its rows of X, AX, W, AW in REGISTERS for the entire solve; P, AP, the
+// per-row constants and the CTA's slice of both CSR adjacencies (with one product slot per entry)
+// live in shared memory; the only vector that travels through global memory is W, through an
+// exchange buffer in [row][2] layout.  Three grid barriers per iteration:
+//   1  residual; forward and backward substitution of W = T^-1 r with ZERO inflow into the CTA's
+//      row range; their CTA aggregates                                              | barrier
+//   2  scan of the forward aggregates, backward aggregates corrected through the per-solve
+//      homogeneous solution, scan of those; exact walk -> W, published; column sums  | barrier
+//   3  AW = L (W - mean): tridiagonal part from registers / shuffles, the rest as a flat
+//      CTA-wide gather; Gram partial sums (transposing warp reductions)             | barrier
+//   4  every CTA reduces the Gram partials in the same fixed order, warp 0 solves the two-stage
+//      Rayleigh-Ritz problem, all threads update X, AX, P, AP; back to 1 without a barrier
 // The multi-kernel path above needs ~13 launches and one host round trip per iteration
-// (~140 us at n = 100k); this kernel needs neither.
+// (~140 us at n = 100k); this kernel needs neither (17 us per iteration at n = 100k).
 // W gathers after the grid barrier: the barrier's acquire makes plain (L1-allocating) loads see
 // the other CTAs' stores; CSLAM_W_LDCG selects ld.global.cg instead (compile-time experiment)
 #ifdef CSLAM_W_LDCG
@@ -2386,41 +2389,6 @@ __global__ void __launch_bounds__(T, 1) k_lobpcg_persist(PersistArgs a) {
   double res_out = 0.0;
   int it = 0;
 
-  // value entering this CTA from the CTAs before (forward) / after (backward) it
-  // `extra` (nullable): [grid] values read in the same round trip; their sum over the grid is returned
-  auto cta_prefix = [&](const double* gA, const double* gB, bool rev, const double* extra) -> double {
-    double A = 1.0, B[MAXM], ex = 0.0;
-#pragma unroll
-    for (int c = 0; c < MAXM; ++c) B[c] = 0.0;
-    if (tid < nb_grid) {   // gA: [CTA][4] = (A, B0, B1, -), one 32 B sector per CTA
-      const double2 t0 = __ldcg(reinterpret_cast<const double2*>(gA) + 2 * tid);
-      const double2 t1 = __ldcg(reinterpret_cast<const double2*>(gA) + 2 * tid + 1);
-      A = t0.x;
-      B[0] = t0.y;
-      B[1] = t1.x;
-      if (extra) ex = __ldcg(extra + tid);
-    }
-    if (extra) {
-      ex = warp_sum(ex);
-      if (lane == 0) s_red[warp][0] = ex;
-    }
-    if (rev) block_scan_affine<true>(A, B, shA, shB);
-    else block_scan_affine<false>(A, B, shA, shB);
-    const int src = rev ? b + 1 : b - 1;
-    if (tid == 0 && (src < 0 || src >= nb_grid)) {
-#pragma unroll
-      for (int c = 0; c < MAXM; ++c) s_in[c] = 0.0;
-    }
-    if (tid == src) {
-#pragma unroll
-      for (int c = 0; c < MAXM; ++c) s_in[c] = B[c];
-    }
-    __syncthreads();
-    double total = 0.0;
-    if (extra)
-      for (int k = 0; k < NW; ++k) total += s_red[k][0];
-    return total;
-  };
   // CTA-level sums of MAXM per-thread values -> gdst[b][c]  (fixed order: deterministic)
   auto block_sum2 = [&](const double (&vals)[MAXM], double* gdst) {
 #pragma unroll

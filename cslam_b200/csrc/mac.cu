@@ -3821,15 +3821,26 @@ struct FiedlerSolver {
     // CTA-count all-gather slower - 27.6 ms per C5 selection with 5120 staged entries, 24.5 ms with
     // 2304-3328 (measured); a slice that does not fit is gathered per row from global memory instead
     // (the heaviest C5 CTA holds 2569 active entries; 28.6 / 33.0 ms with room for 1024 / 512).
-    pa.cap0 = static_cast<int>(std::min<int64_t>(2048, std::max<int64_t>(256, (4 * fixr.nnz / grid + 255) / 256 * 256)));
-    pa.cap1 = 3456 - pa.cap0;
+    // (per-row state: 5 constants + P + AP = 9 doubles per row; static shared memory ~19 KB)
+    const size_t state_bytes = static_cast<size_t>(5 + 2 * MAXM) * ch * threads * sizeof(double);
+    const size_t entry_bytes = (1 + MAXM) * sizeof(double) + sizeof(int);
+    const size_t dyn_pref = 196 * 1024 - 20 * 1024, dyn_max = 227 * 1024 - 20 * 1024;
+    int64_t entries = dyn_pref > state_bytes ? static_cast<int64_t>((dyn_pref - state_bytes) / entry_bytes) : 0;
+    if (entries < 2048)   // 8 rows per thread: the state alone is 144 KB - take the larger carve-out
+      entries = dyn_max > state_bytes ? static_cast<int64_t>((dyn_max - state_bytes) / entry_bytes) : 0;
+    entries = std::min<int64_t>(entries, 3456) / 256 * 256;
+    if (entries < 512) {    // no room to stage anything useful: multi-kernel path
+      persist_variant = 0;
+      return kPersistUnavailable;
+    }
+    pa.cap0 = static_cast<int>(std::min<int64_t>(entries / 2, std::max<int64_t>(256, (4 * fixr.nnz / grid + 255) / 256 * 256)));
+    pa.cap1 = static_cast<int>(entries) - pa.cap0;
     if (const char* e = getenv("CSLAM_LOBPCG_CAP1")) pa.cap1 = std::max(0, std::min(4096, atoi(e)));   // (experiments)
     if (const char* e = getenv("CSLAM_LOBPCG_CAP0")) pa.cap0 = std::max(0, std::min(4096, atoi(e)));
     pa.rr_impl = getenv("CSLAM_RR_IMPL") ? atoi(getenv("CSLAM_RR_IMPL")) : 2;
     pa.rr_sweeps = getenv("CSLAM_RR_SWEEPS") ? atoi(getenv("CSLAM_RR_SWEEPS")) : 3;   // (2-stage solve: 4 / 3 / 2 sweeps = 1082 / 1082 / 1102 iterations per C5 selection)
     pa.rr_tol2 = getenv("CSLAM_RR_TOL2") ? atof(getenv("CSLAM_RR_TOL2")) : 1e-32;
-    const size_t dyn = static_cast<size_t>(pa.cap0 + pa.cap1) * ((1 + MAXM) * sizeof(double) + sizeof(int)) +
-                       static_cast<size_t>(5 + 2 * MAXM) * ch * threads * sizeof(double);
+    const size_t dyn = static_cast<size_t>(pa.cap0 + pa.cap1) * entry_bytes + state_bytes;
     CSLAM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
     CSLAM_CUDA(cudaEventRecord(e0, stream));
     {

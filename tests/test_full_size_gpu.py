@@ -161,3 +161,35 @@ def test_config5_fw_subset_against_the_reference_golden():
         assert len(set(tsel[it].tolist()) ^ set(ref.tolist())) <= k // 100
     np.testing.assert_allclose(tf, g["lambda2_iter"], rtol=1e-3)
     assert abs(u - float(g["u"])) <= 2e-3 * abs(float(g["u"]))
+
+
+def test_fiedler_pair_between_151k_and_303k_poses():
+    """180 000 poses: the persistent eigen-solver runs with 8 rows per thread there (its per-row state
+    alone is 144 KB of shared memory, so the staged CSR slices are sized to what is left).  lambda_2 and
+    the vector against scipy's shift-invert Lanczos on the same Laplacian."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    from cslam_b200.mac.mac import MAC
+    from oracle.inputs import mac_scale_graph
+    R, P, m, k = 2, 90000, 20000, 2000
+    fixed, cand, n = mac_scale_graph(R, P, m, seed=3)
+    mac = MAC(fixed, cand, n)
+    mac.set_options(block_size=2)
+    w0 = np.zeros(m)
+    act = np.argpartition(cand[2], -k)[-k:]
+    w0[act] = 1.0
+    lam, vec = mac.evaluate_fiedler_pair(w0)
+    i = np.r_[fixed[0], cand[0][act]]
+    j = np.r_[fixed[1], cand[1][act]]
+    w = np.r_[fixed[2], cand[2][act]]
+    A = sp.coo_matrix((np.r_[w, w], (np.r_[i, j], np.r_[j, i])), shape=(n, n)).tocsr()
+    L = (sp.diags(np.asarray(A.sum(axis=1)).ravel()) - A).tocsc()
+    vals, vecs = spl.eigsh(L, k=2, sigma=-1e-7, which="LM", tol=1e-12)
+    order = np.argsort(vals)
+    lam_ref, v_ref = vals[order[1]], vecs[:, order[1]]
+    assert abs(lam - lam_ref) <= 1e-6 * lam_ref + 1e-13
+    v_ref = v_ref / np.linalg.norm(v_ref)
+    if np.dot(v_ref, vec) < 0:
+        v_ref = -v_ref
+    assert np.abs(vec - v_ref).max() < 1e-4
+    assert not mac.stats()["jacobi_fallback"]

@@ -3910,8 +3910,8 @@ struct FiedlerSolver {
       const double it_ = static_cast<double>(std::max<long long>(hp[16], 1));
       auto c = [&](int k) { return hp[k] / it_; };
       fprintf(stderr,
-              "[cslam lobpcg prof] cycles/iter of CTA 0 over %lld iters: p1 residual+fwd aggregates %.0f | p2 fwd walk+bwd aggregates %.0f | "
-              "p3 bwd walk %.0f | mean all-gather %.0f, centre+exchange %.0f, flat gathers %.0f, own slots %.0f, rest of SpMM %.0f | "
+              "[cslam lobpcg prof] cycles/iter of CTA 0 over %lld iters: residual + local substitutions %.0f | (unused) %.0f | "
+              "aggregate scans + exact walk + publish %.0f | mean all-gather %.0f, centre+exchange %.0f, flat gathers %.0f, own slots %.0f, rest of SpMM %.0f | "
               "Gram partials %.0f | Gram all-gather %.0f, unpack %.0f, Rayleigh-Ritz %.0f, basis update %.0f | barriers %.0f | total %.0f\n",
               hp[16], c(0), c(1), c(2), c(8), c(7), c(10), c(11), c(9), c(3), c(4), c(13), c(5), c(12), c(6),
               c(0) + c(1) + c(2) + c(3) + c(4) + c(5) + c(6) + c(7) + c(8) + c(9) + c(10) + c(11) + c(12) + c(13));
